@@ -1,0 +1,13 @@
+"""Import alias for ``inference-efficient-vision-models_b200/`` (not a valid Python identifier)."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                      "inference-efficient-vision-models_b200")
+__path__.insert(0, _real)
+
+from . import _lib  # noqa: E402
+from .engine import B200HalfResNet, B200QuantizedResNet, kd_eval_loss  # noqa: E402
+from .netdesc import NetSpec, from_converted, from_half_module, from_quantized_state_dict  # noqa: E402
+
+__all__ = ["B200QuantizedResNet", "B200HalfResNet", "kd_eval_loss", "NetSpec", "from_converted",
+           "from_half_module", "from_quantized_state_dict", "_lib"]

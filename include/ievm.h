@@ -1,0 +1,153 @@
+/* ievm.h -- C ABI of the B200 (sm_100a) engine for the hot path of
+ * jaideepmurkute/Inference-Efficient-Vision-Models: the batched forward pass `outputs = model(images)`
+ * of the pruned ResNet-18 student after static INT8 PTQ or FP16 casting, and of the ResNet-50 teacher.
+ *
+ * Reference interfaces replaced (the reference is pure Python; its "FFI" for this path is the
+ * nn.Module call protocol plus the converted module's attribute / state-dict layout):
+ *
+ *   ievm_create        <- the converted module the caller holds: quantize_fx.convert_fx(...)
+ *                         (quantization/engines.py:118, quantization/main.py:242) or
+ *                         deepcopy(model).half() (quantization/engines.py:91-92, main.py:258/262)
+ *   ievm_forward_i8    <- outputs = model(images), f32 NCHW in -> f32 logits out
+ *                         (quantization/engines.py:27,31,60; quantization/main.py:287)
+ *   ievm_forward_f16   <- outputs = model(images.half()) (quantization/engines.py:57-60; main.py:284-287)
+ *                         and teacher_model(images) (knowledge_distillation/train.py:43-44)
+ *   ievm_forward_*_host<- the same calls with `images` still on the host, as the reference's loops
+ *                         hand them over (engines.py:52-60): H2D + forward + D2H in one call
+ *   ievm_kd_loss       <- CE + T^2 * KLDiv(batchmean) soft-target loss
+ *                         (knowledge_distillation/train.py:47-57; main.py:128-129)
+ *   ievm_debug_*       <- no reference counterpart: parity hooks (per-tensor activations and the
+ *                         int32 accumulators torch never exposes)
+ *
+ * Conventions: every function returns 0 on success or a negative ievm_status; ievm_last_error()
+ * describes the last failure on the calling thread.  Device pointers are plain CUDA device
+ * pointers owned by the caller; `stream` is a cudaStream_t passed as void*.  Work is enqueued on the
+ * caller's stream without synchronising or allocating (CUDA-graph capturable) unless stated.
+ * A handle is bound to one device and is not re-entrant.  There is no CPU fallback: creation fails
+ * with IEVM_ERR_CUDA when no sm_100 device is present.
+ */
+#ifndef IEVM_H_
+#define IEVM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ievm_handle ievm_handle;
+
+typedef enum ievm_status {
+  IEVM_OK = 0,
+  IEVM_ERR_BAD_ARG = -1,
+  IEVM_ERR_UNSUPPORTED = -2,
+  IEVM_ERR_CUDA = -3,
+  IEVM_ERR_OOM = -4
+} ievm_status;
+
+typedef enum ievm_dtype { IEVM_DTYPE_I8 = 0, IEVM_DTYPE_F16 = 1 } ievm_dtype;
+
+typedef enum ievm_op {
+  IEVM_OP_CONV = 0,    /* conv (+folded BN) [+ReLU] [+residual add (+ReLU)] */
+  IEVM_OP_MAXPOOL = 1, /* MaxPool2d(3, 2, 1) */
+  IEVM_OP_HEAD = 2     /* AdaptiveAvgPool2d(1) + flatten + Linear (+ dequantize) -> logits */
+} ievm_op;
+
+/* One node of the flattened graph.  Tensor id 0 is the network input (for INT8: the output of
+ * quantize_per_tensor); every other id names the output of exactly one earlier layer. */
+typedef struct ievm_layer_desc {
+  int32_t op;          /* ievm_op */
+  int32_t in_tensor;
+  int32_t res_tensor;  /* residual operand of the fused add, or -1 */
+  int32_t out_tensor;  /* ignored for IEVM_OP_HEAD */
+  int32_t cin, cout;   /* real (un-padded) channel counts; HEAD: cin = features, cout = classes */
+  int32_t ksize, stride, pad;
+  int32_t relu;        /* I8: the module is ConvReLU2d (ReLU on the conv's own output; the fused
+                          add_relu always clamps).  F16: ReLU is the layer's last operation
+                          (after the residual add when res_tensor >= 0). */
+  const void* weight;  /* host pointer. I8: int8 [cout][cin][k][k]; F16: IEEE half bits, BN folded */
+  const float* bias;   /* host pointer, [cout] (BN folded) */
+  const float* w_scale;/* host pointer, [cout], I8 only */
+  float in_scale;  int32_t in_zp;    /* I8: qparams of in_tensor */
+  float out_scale; int32_t out_zp;   /* I8: qparams of this layer's own output (module.scale/zero_point) */
+  float res_scale; int32_t res_zp;   /* I8: qparams of res_tensor */
+  float add_scale; int32_t add_zp;   /* I8: output qparams of quantized.add_relu (used iff res_tensor >= 0) */
+} ievm_layer_desc;
+
+typedef struct ievm_net_desc {
+  int32_t dtype;       /* ievm_dtype */
+  int32_t num_layers;
+  int32_t in_c, in_h, in_w;
+  int32_t num_classes;
+  float in_scale;      /* I8: quantize_per_tensor scale / zero point of the network input */
+  int32_t in_zp;
+  const ievm_layer_desc* layers;
+} ievm_net_desc;
+
+/* Build an engine on `device`: pads/packs weights into the tensor-core layout, uploads them,
+ * allocates the activation workspace for `max_batch` images and encodes the TMA descriptors.
+ * Synchronous.  The descriptor and everything it points to may be freed after the call. */
+int ievm_create(const ievm_net_desc* desc, int device, int max_batch, ievm_handle** out);
+void ievm_destroy(ievm_handle* h);
+
+/* x: device f32 [n][in_c][in_h][in_w]; logits: device f32 [n][num_classes]. n <= max_batch. */
+int ievm_forward_i8(ievm_handle* h, const float* x_nchw, int n, float* logits, void* stream);
+/* x: device f16 [n][in_c][in_h][in_w]; logits: device f16 [n][num_classes]. */
+int ievm_forward_f16(ievm_handle* h, const void* x_nchw, int n, void* logits, void* stream);
+
+/* Host-buffer variants (what a reference caller holds): copies x to the device, runs the forward
+ * and copies the logits back; returns after the logits are in `logits_host`.  Pinned buffers make
+ * the copies asynchronous on the handle's own stream. */
+int ievm_forward_i8_host(ievm_handle* h, const float* x_nchw_host, int n, float* logits_host);
+int ievm_forward_f16_host(ievm_handle* h, const void* x_nchw_host, int n, void* logits_host);
+
+/* Engine options: "conv_impl" 0 = tcgen05 tensor-core kernels (default), 1 = direct CUDA-core
+ * cross-check kernels (tests only); "use_graph" 1 = replay forward() from a CUDA graph cached per
+ * (n, x, logits) triple; "keep_tensors" 1 = one buffer per tensor (parity hooks); "profile" 1 =
+ * per-launch event timing (see ievm_profile_read). */
+int ievm_set_option(ievm_handle* h, const char* name, int value);
+
+/* Introspection used by the benchmark and tests. */
+int ievm_num_tensors(const ievm_handle* h);
+/* Shape of tensor `id` for the last forward: writes {n, h, w, c_real, c_pitch, elem_bytes}. */
+int ievm_tensor_shape(const ievm_handle* h, int id, int32_t out6[6]);
+/* Number of kernel launches one forward() enqueues. */
+int ievm_launches_per_forward(const ievm_handle* h);
+
+/* Per-launch device timing.  With ievm_set_option(h, "profile", 1) every forward brackets each of its
+ * launches with CUDA events on the caller's stream and synchronises at the end (not for timed
+ * throughput runs).  ievm_profile_read copies the accumulated milliseconds and call counts: slot 0 is
+ * the input-quantize launch (INT8), slot 1 + i is layer i.  Returns the number of slots. */
+int ievm_profile_read(const ievm_handle* h, int max_slots, float* ms_sum, int32_t* calls);
+
+/* Parity hooks.  ievm_debug_read_tensor copies tensor `id` as left by the last forward into a host
+ * buffer in the engine's layout [n][h][w][c_pitch] (synchronises the device).  Tensors share
+ * workspace, so call ievm_set_option(h, "keep_tensors", 1) before the forward to give every tensor
+ * its own buffer. */
+int ievm_debug_read_tensor(ievm_handle* h, int id, void* host_out, uint64_t host_bytes);
+/* Re-runs conv layer `layer` on its current input with accumulator dumping enabled and copies the
+ * raw accumulators (int32 for I8, fp32 bits for F16) as [n*ho*wo][c_pitch] to the host. */
+int ievm_debug_conv_acc(ievm_handle* h, int layer, int n, int32_t* host_out, uint64_t host_bytes);
+
+/* Diagnostic: issue ONE im2col-mode TMA load (128 pixels x kc_bytes channels of a u8 NHWC tensor
+ * with channel pitch c_pitch) for the tile that starts at output pixel m0, filter tap
+ * (tap_x, tap_y), channel offset c0, and copy the raw (swizzled) shared-memory image, 128*kc_bytes
+ * bytes, to out_dev.  Synchronous.  Lets the tests pin the TMA unit's im2col semantics
+ * (bounding box, traversal stride, zero fill, swizzle) independently of the MMA path. */
+int ievm_probe_im2col(const void* in_dev, int n, int h, int w, int c_pitch, int ksize, int stride, int pad,
+                      int kc_bytes, int m0, int tap_x, int tap_y, int c0, void* out_dev);
+
+/* Soft-target KD evaluation loss over device logits (f32 [n][classes]) and labels (int64 [n]).
+ * out3 (device, f32[3]) receives {mean CE, mean T^2*KL (batchmean), number correct};
+ * total loss = (1 - alpha) * CE + alpha * KL. */
+int ievm_kd_loss(const float* student_logits, const float* teacher_logits, const int64_t* labels, int n,
+                 int classes, float temperature, float* out3, void* stream);
+
+const char* ievm_last_error(void);
+/* "sm_100a" build tag and ABI version, for the loader to check. */
+const char* ievm_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IEVM_H_ */

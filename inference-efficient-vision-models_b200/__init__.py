@@ -1,0 +1,12 @@
+"""B200-native (sm_100a) engine for the forward pass of the pruned ResNet-18 student (static INT8 or
+FP16) and the ResNet-50 teacher of jaideepmurkute/Inference-Efficient-Vision-Models.
+
+Import as ``ievm_b200`` (the directory name carries the reference's name and is not a valid Python
+identifier; ``ievm_b200/__init__.py`` at the repo root aliases it).
+"""
+from . import _lib
+from .engine import B200HalfResNet, B200QuantizedResNet, kd_eval_loss
+from .netdesc import NetSpec, from_converted, from_half_module, from_quantized_state_dict
+
+__all__ = ["B200QuantizedResNet", "B200HalfResNet", "kd_eval_loss", "NetSpec", "from_converted",
+           "from_half_module", "from_quantized_state_dict", "_lib"]

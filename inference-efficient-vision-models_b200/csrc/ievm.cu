@@ -1,0 +1,924 @@
+// C-ABI implementation (include/ievm.h): graph planning, weight packing, TMA descriptor encoding and
+// kernel sequencing for the INT8 / FP16 ResNet forward on sm_100a.
+#include "../../include/ievm.h"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "simt_kernels.cuh"
+
+namespace {
+
+using namespace ievm;
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(e__ == cudaErrorMemoryAllocation ? IEVM_ERR_OOM : IEVM_ERR_CUDA, "%s failed: %s", \
+                  #expr, cudaGetErrorString(e__));                                                  \
+  } while (0)
+
+// ---- driver entry points for tensor-map encoding (resolved at run time: the library must load on a
+// machine without libcuda so that the CPU-only test tier can check its exports) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+
+int load_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return IEVM_OK;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !fn) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  fn = nullptr;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !fn) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeIm2col not available");
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  return IEVM_OK;
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct TensorInfo {
+  int h = 0, w = 0, c = 0, pitch = 0;   // pitch in elements
+  int elem = 1;
+  int producer = -1;                    // layer index, -1 for the network input
+  int last_use = -1;
+  int buffer = -1;
+  size_t bytes_per_image() const { return static_cast<size_t>(h) * w * pitch * elem; }
+};
+
+struct LayerPlan {
+  ievm_layer_desc d;
+  bool is_stem = false;
+  // conv geometry
+  int h = 0, w = 0, ho = 0, wo = 0;
+  int cin_pitch = 0, cout_pad = 0;
+  int bn = 0, n_tiles = 0;
+  int kc_bytes = 0, kc_elems = 0, kchunks = 0, cin_w = 0;
+  int stages = 0, tmem_cols = 0;
+  size_t smem_bytes = 0;
+  // device operands
+  void* w_packed = nullptr;     // tensor-core layout [cout_pad][taps][cin_w]
+  void* w_stem = nullptr;       // stem layout
+  int* wsum = nullptr;
+  float* ep0 = nullptr;
+  float* ep1 = nullptr;
+  CUtensorMap tmap_a, tmap_b;
+};
+
+}  // namespace
+
+struct ievm_handle {
+  int device = 0;
+  int dtype = 0;
+  int elem = 1;
+  int max_batch = 0;
+  int num_sms = 0;
+  int in_c = 0, in_h = 0, in_w = 0, classes = 0;
+  float in_scale = 1.f;
+  int in_zp = 0;
+  std::vector<LayerPlan> layers;
+  std::vector<TensorInfo> tensors;
+  std::vector<void*> buffers;
+  std::vector<size_t> buffer_bytes;
+  std::vector<void*> owned;            // device allocations freed at destroy
+  int conv_impl = 0;
+  int keep_tensors = 0;
+  int use_graph = 0;
+  int last_n = 0;
+  unsigned int* stuck_host = nullptr;  // mapped pinned word
+  unsigned int* stuck_dev = nullptr;
+  cudaStream_t own_stream = nullptr;
+  void* stage_in = nullptr;            // device staging for the *_host entry points
+  void* stage_out = nullptr;
+  void* pin_in = nullptr;              // pinned host staging
+  void* pin_out = nullptr;
+  size_t pin_in_bytes = 0;
+  std::map<std::tuple<int, const void*, void*>, cudaGraphExec_t> graphs;
+  // per-launch device timing (option "profile"): slot 0 = input quantize, slot 1 + i = layer i
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<double> prof_ms;
+  std::vector<int> prof_calls;
+};
+
+namespace {
+
+template <typename T>
+int dev_upload(ievm_handle* h, const std::vector<T>& host, T** out) {
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, std::max<size_t>(host.size() * sizeof(T), 16)));
+  h->owned.push_back(p);
+  CUDA_TRY(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<T*>(p);
+  return IEVM_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Planning: shapes, channel pitches, tile configuration
+// ----------------------------------------------------------------------------------------------
+int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
+  int max_id = 0;
+  for (int i = 0; i < nd->num_layers; ++i) {
+    const ievm_layer_desc& d = nd->layers[i];
+    max_id = std::max(max_id, std::max(d.in_tensor, std::max(d.res_tensor, d.out_tensor)));
+  }
+  h->tensors.assign(max_id + 1, TensorInfo());
+  TensorInfo& t0 = h->tensors[0];
+  t0.h = nd->in_h;
+  t0.w = nd->in_w;
+  t0.c = nd->in_c;
+  if (h->dtype == IEVM_DTYPE_I8) {
+    t0.pitch = 4;      // quantized NHWC4
+    t0.elem = 1;
+  } else {
+    t0.pitch = nd->in_c;   // caller's f16 NCHW buffer is read in place by the stem
+    t0.elem = 2;
+  }
+  h->layers.resize(nd->num_layers);
+  for (int i = 0; i < nd->num_layers; ++i) {
+    LayerPlan& L = h->layers[i];
+    L.d = nd->layers[i];
+    const ievm_layer_desc& d = L.d;
+    if (d.in_tensor < 0 || d.in_tensor > max_id) return fail(IEVM_ERR_BAD_ARG, "layer %d: bad in_tensor", i);
+    TensorInfo& tin = h->tensors[d.in_tensor];
+    if (tin.h == 0) return fail(IEVM_ERR_BAD_ARG, "layer %d reads tensor %d before it is produced", i, d.in_tensor);
+    tin.last_use = i;
+    if (d.res_tensor >= 0) h->tensors[d.res_tensor].last_use = i;
+    L.h = tin.h;
+    L.w = tin.w;
+    L.cin_pitch = tin.pitch;
+    if (d.op == IEVM_OP_HEAD) {
+      if (d.cin != tin.c) return fail(IEVM_ERR_BAD_ARG, "head: cin %d != producer channels %d", d.cin, tin.c);
+      if (d.cout > kMaxClasses) return fail(IEVM_ERR_UNSUPPORTED, "head: more than %d classes", kMaxClasses);
+      continue;
+    }
+    if (d.out_tensor <= 0 || d.out_tensor > max_id || h->tensors[d.out_tensor].h != 0)
+      return fail(IEVM_ERR_BAD_ARG, "layer %d: bad out_tensor", i);
+    TensorInfo& tout = h->tensors[d.out_tensor];
+    tout.producer = i;
+    tout.elem = h->elem;
+    if (d.op == IEVM_OP_MAXPOOL) {
+      L.ho = (tin.h + 2 - 3) / 2 + 1;
+      L.wo = (tin.w + 2 - 3) / 2 + 1;
+      tout.h = L.ho;
+      tout.w = L.wo;
+      tout.c = tin.c;
+      tout.pitch = tin.pitch;
+      continue;
+    }
+    if (d.op != IEVM_OP_CONV) return fail(IEVM_ERR_BAD_ARG, "layer %d: unknown op %d", i, d.op);
+    if (d.cin != tin.c) return fail(IEVM_ERR_BAD_ARG, "layer %d: cin %d != producer channels %d", i, d.cin, tin.c);
+    L.ho = (tin.h + 2 * d.pad - d.ksize) / d.stride + 1;
+    L.wo = (tin.w + 2 * d.pad - d.ksize) / d.stride + 1;
+    L.n_tiles = (d.cout + 255) / 256;
+    L.bn = round_up((d.cout + L.n_tiles - 1) / L.n_tiles, 16);
+    L.cout_pad = L.n_tiles * L.bn;
+    tout.h = L.ho;
+    tout.w = L.wo;
+    tout.c = d.cout;
+    tout.pitch = L.cout_pad;
+    L.is_stem = d.in_tensor == 0;
+    if (L.is_stem) {
+      if (d.cin != 3 || d.ksize != 7 || d.stride != 2 || d.pad != 3 || d.res_tensor >= 0 || L.n_tiles != 1)
+        return fail(IEVM_ERR_UNSUPPORTED, "stem must be a 3-channel 7x7/2 pad-3 conv with <= 256 outputs");
+      if ((nd->in_h * nd->in_w) % 4 != 0) return fail(IEVM_ERR_UNSUPPORTED, "input plane must be a multiple of 4");
+      continue;
+    }
+    if (!((d.ksize == 3 && d.pad == 1) || (d.ksize == 1 && d.pad == 0)) || d.stride < 1 || d.stride > 2)
+      return fail(IEVM_ERR_UNSUPPORTED, "layer %d: only 3x3/pad1 and 1x1/pad0 convs with stride 1|2", i);
+    if (h->dtype == IEVM_DTYPE_I8 && d.in_zp != 0)
+      return fail(IEVM_ERR_UNSUPPORTED, "layer %d: tensor-core conv input zero-point must be 0 (got %d)", i, d.in_zp);
+    if (d.res_tensor >= 0) {
+      const TensorInfo& tr = h->tensors[d.res_tensor];
+      if (tr.h != L.ho || tr.w != L.wo || tr.c != d.cout || tr.pitch != L.cout_pad)
+        return fail(IEVM_ERR_BAD_ARG, "layer %d: residual shape mismatch", i);
+    }
+    const int row_bytes = L.cin_pitch * h->elem;
+    L.kc_bytes = row_bytes <= 64 ? 64 : 128;
+    L.kc_elems = L.kc_bytes / h->elem;
+    L.kchunks = (d.cin * h->elem + L.kc_bytes - 1) / L.kc_bytes;
+    L.cin_w = L.kchunks * L.kc_elems;
+    const int stage_bytes = kTileM * L.kc_bytes + L.bn * L.kc_bytes;
+    const int num_kb = d.ksize * d.ksize * L.kchunks;
+    L.stages = std::max(2, std::min(std::min(8, num_kb), (200 * 1024) / stage_bytes));
+    L.tmem_cols = 32;
+    while (L.tmem_cols < 2 * L.bn) L.tmem_cols *= 2;
+    L.smem_bytes = static_cast<size_t>(L.stages) * stage_bytes + (2 * L.stages + 4) * 8 + 16 + 1024;
+  }
+  return IEVM_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Weights and epilogue tables
+// ----------------------------------------------------------------------------------------------
+int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
+  const ievm_layer_desc& d = L.d;
+  const int taps = d.ksize * d.ksize;
+  std::vector<float> ep0(L.cout_pad, 0.f), ep1(L.cout_pad, 0.f);
+  if (h->dtype == IEVM_DTYPE_I8) {
+    for (int c = 0; c < d.cout; ++c) {
+      const float atw = d.in_scale * d.w_scale[c];
+      ep0[c] = d.bias[c] / atw;
+      ep1[c] = atw / d.out_scale;
+    }
+  } else {
+    for (int c = 0; c < d.cout; ++c) ep0[c] = d.bias[c];
+  }
+  if (int rc = dev_upload(h, ep0, &L.ep0)) return rc;
+  if (int rc = dev_upload(h, ep1, &L.ep1)) return rc;
+
+  if (L.is_stem) {
+    if (h->dtype == IEVM_DTYPE_I8) {
+      const int8_t* w = static_cast<const int8_t*>(d.weight);     // [cout][3][7][7]
+      std::vector<uint32_t> w4(static_cast<size_t>(49) * L.cout_pad, 0u);
+      std::vector<int> wsum(L.cout_pad, 0);
+      for (int co = 0; co < d.cout; ++co)
+        for (int t = 0; t < 49; ++t) {
+          uint32_t word = 0;
+          for (int c = 0; c < 3; ++c) {
+            const int8_t v = w[(static_cast<size_t>(co) * 3 + c) * 49 + t];
+            word |= static_cast<uint32_t>(static_cast<uint8_t>(v)) << (8 * c);
+            wsum[co] += v;
+          }
+          w4[static_cast<size_t>(t) * L.cout_pad + co] = word;
+        }
+      uint32_t* dw = nullptr;
+      if (int rc = dev_upload(h, w4, &dw)) return rc;
+      L.w_stem = dw;
+      if (int rc = dev_upload(h, wsum, &L.wsum)) return rc;
+    } else {
+      const uint16_t* w = static_cast<const uint16_t*>(d.weight);
+      std::vector<uint16_t> ws(static_cast<size_t>(147) * L.cout_pad, 0);
+      for (int co = 0; co < d.cout; ++co)
+        for (int c = 0; c < 3; ++c)
+          for (int t = 0; t < 49; ++t)
+            ws[(static_cast<size_t>(t) * 3 + c) * L.cout_pad + co] = w[(static_cast<size_t>(co) * 3 + c) * 49 + t];
+      uint16_t* dw = nullptr;
+      if (int rc = dev_upload(h, ws, &dw)) return rc;
+      L.w_stem = dw;
+    }
+    return IEVM_OK;
+  }
+
+  const size_t k_total = static_cast<size_t>(taps) * L.cin_w;
+  if (h->dtype == IEVM_DTYPE_I8) {
+    const int8_t* w = static_cast<const int8_t*>(d.weight);
+    std::vector<int8_t> wp(static_cast<size_t>(L.cout_pad) * k_total, 0);
+    for (int co = 0; co < d.cout; ++co)
+      for (int ci = 0; ci < d.cin; ++ci)
+        for (int t = 0; t < taps; ++t)
+          wp[static_cast<size_t>(co) * k_total + static_cast<size_t>(t) * L.cin_w + ci] =
+              w[(static_cast<size_t>(co) * d.cin + ci) * taps + t];
+    int8_t* dw = nullptr;
+    if (int rc = dev_upload(h, wp, &dw)) return rc;
+    L.w_packed = dw;
+  } else {
+    const uint16_t* w = static_cast<const uint16_t*>(d.weight);
+    std::vector<uint16_t> wp(static_cast<size_t>(L.cout_pad) * k_total, 0);
+    for (int co = 0; co < d.cout; ++co)
+      for (int ci = 0; ci < d.cin; ++ci)
+        for (int t = 0; t < taps; ++t)
+          wp[static_cast<size_t>(co) * k_total + static_cast<size_t>(t) * L.cin_w + ci] =
+              w[(static_cast<size_t>(co) * d.cin + ci) * taps + t];
+    uint16_t* dw = nullptr;
+    if (int rc = dev_upload(h, wp, &dw)) return rc;
+    L.w_packed = dw;
+  }
+  return IEVM_OK;
+}
+
+int upload_head_operands(ievm_handle* h, LayerPlan& L) {
+  const ievm_layer_desc& d = L.d;
+  std::vector<float> ep0(kMaxClasses, 0.f), ep1(kMaxClasses, 0.f);
+  if (h->dtype == IEVM_DTYPE_I8) {
+    for (int c = 0; c < d.cout; ++c) {
+      const float atw = d.in_scale * d.w_scale[c];
+      ep0[c] = d.bias[c] / atw;
+      ep1[c] = atw / d.out_scale;
+    }
+    const int8_t* w = static_cast<const int8_t*>(d.weight);   // [classes][cin]
+    std::vector<int8_t> wp(static_cast<size_t>(d.cout) * L.cin_pitch, 0);
+    for (int o = 0; o < d.cout; ++o)
+      for (int c = 0; c < d.cin; ++c) wp[static_cast<size_t>(o) * L.cin_pitch + c] = w[static_cast<size_t>(o) * d.cin + c];
+    int8_t* dw = nullptr;
+    if (int rc = dev_upload(h, wp, &dw)) return rc;
+    L.w_packed = dw;
+  } else {
+    for (int c = 0; c < d.cout; ++c) ep0[c] = d.bias[c];
+    const uint16_t* w = static_cast<const uint16_t*>(d.weight);
+    std::vector<uint16_t> wp(static_cast<size_t>(d.cout) * L.cin_pitch, 0);
+    for (int o = 0; o < d.cout; ++o)
+      for (int c = 0; c < d.cin; ++c) wp[static_cast<size_t>(o) * L.cin_pitch + c] = w[static_cast<size_t>(o) * d.cin + c];
+    uint16_t* dw = nullptr;
+    if (int rc = dev_upload(h, wp, &dw)) return rc;
+    L.w_packed = dw;
+  }
+  if (int rc = dev_upload(h, ep0, &L.ep0)) return rc;
+  if (int rc = dev_upload(h, ep1, &L.ep1)) return rc;
+  return IEVM_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Workspace: greedy buffer reuse by liveness (or one buffer per tensor with keep_tensors)
+// ----------------------------------------------------------------------------------------------
+int assign_buffers(ievm_handle* h) {
+  for (void* b : h->buffers) cudaFree(b);
+  h->buffers.clear();
+  h->buffer_bytes.clear();
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  h->graphs.clear();
+  std::vector<size_t> need;          // planned size per buffer
+  std::vector<int> free_list;
+  const bool f16 = h->dtype == IEVM_DTYPE_F16;
+  // best fit: the smallest free buffer that is already big enough, else grow the largest free one
+  auto take = [&](size_t bytes) {
+    int best = -1;
+    if (!h->keep_tensors) {
+      for (size_t i = 0; i < free_list.size(); ++i) {
+        if (best < 0) { best = static_cast<int>(i); continue; }
+        const size_t cur = need[free_list[best]], cand = need[free_list[i]];
+        const bool cur_fits = cur >= bytes, cand_fits = cand >= bytes;
+        if ((cand_fits && (!cur_fits || cand < cur)) || (!cand_fits && !cur_fits && cand > cur)) best = static_cast<int>(i);
+      }
+    }
+    if (best >= 0) {
+      const int b = free_list[best];
+      free_list.erase(free_list.begin() + best);
+      need[b] = std::max(need[b], bytes);
+      return b;
+    }
+    need.push_back(bytes);
+    return static_cast<int>(need.size()) - 1;
+  };
+  for (auto& t : h->tensors) t.buffer = -1;
+  if (!f16) h->tensors[0].buffer = take(h->tensors[0].bytes_per_image() * h->max_batch);
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    const LayerPlan& L = h->layers[i];
+    if (L.d.op != IEVM_OP_HEAD) {
+      TensorInfo& t = h->tensors[L.d.out_tensor];
+      t.buffer = take(t.bytes_per_image() * h->max_batch);
+    }
+    if (!h->keep_tensors)
+      for (auto& t : h->tensors)
+        if (t.buffer >= 0 && t.last_use == static_cast<int>(i)) free_list.push_back(t.buffer);
+  }
+  for (size_t b = 0; b < need.size(); ++b) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, need[b] + 256));
+    CUDA_TRY(cudaMemset(p, 0, need[b] + 256));
+    h->buffers.push_back(p);
+    h->buffer_bytes.push_back(need[b]);
+  }
+  return IEVM_OK;
+}
+
+void* tensor_ptr(const ievm_handle* h, int id) {
+  const int b = h->tensors[id].buffer;
+  return b < 0 ? nullptr : h->buffers[b];
+}
+
+int encode_maps(ievm_handle* h) {
+  const CUtensorMapDataType dt = h->dtype == IEVM_DTYPE_I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    LayerPlan& L = h->layers[i];
+    if (L.d.op != IEVM_OP_CONV || L.is_stem) continue;
+    const CUtensorMapSwizzle sw = L.kc_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const size_t e = h->elem;
+    // activations as (C, W, H, N), im2col mode
+    {
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cin_pitch), static_cast<cuuint64_t>(L.w),
+                            static_cast<cuuint64_t>(L.h), static_cast<cuuint64_t>(h->max_batch)};
+      cuuint64_t strides[3] = {L.cin_pitch * e, static_cast<cuuint64_t>(L.w) * L.cin_pitch * e,
+                               static_cast<cuuint64_t>(L.h) * L.w * L.cin_pitch * e};
+      int lower[2] = {-L.d.pad, -L.d.pad};
+      int upper[2] = {L.d.pad - (L.d.ksize - 1), L.d.pad - (L.d.ksize - 1)};
+      cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(L.d.stride), static_cast<cuuint32_t>(L.d.stride), 1};
+      const CUresult r = g_encode_im2col(&L.tmap_a, dt, 4, tensor_ptr(h, L.d.in_tensor), dims, strides, lower, upper,
+                                         static_cast<cuuint32_t>(L.kc_elems), kTileM, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeIm2col failed for layer %zu: CUresult %d", i, (int)r);
+    }
+    // packed weights as (K_total, cout_pad), tiled mode
+    {
+      const size_t k_total = static_cast<size_t>(L.d.ksize) * L.d.ksize * L.cin_w;
+      cuuint64_t dims[2] = {k_total, static_cast<cuuint64_t>(L.cout_pad)};
+      cuuint64_t strides[1] = {k_total * e};
+      cuuint32_t box[2] = {static_cast<cuuint32_t>(L.kc_elems), static_cast<cuuint32_t>(L.bn)};
+      cuuint32_t estr[2] = {1, 1};
+      const CUresult r = g_encode_tiled(&L.tmap_b, dt, 2, L.w_packed, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled failed for layer %zu: CUresult %d", i, (int)r);
+    }
+  }
+  return IEVM_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Launch helpers
+// ----------------------------------------------------------------------------------------------
+ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, int32_t* dump_acc) {
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  const ievm_layer_desc& d = L.d;
+  p.m_total = n * L.ho * L.wo;
+  p.ho = L.ho;
+  p.wo = L.wo;
+  p.stride = d.stride;
+  p.pad = d.pad;
+  p.ksize = d.ksize;
+  p.kchunks = L.kchunks;
+  p.kc_bytes = L.kc_bytes;
+  p.kc_elems = L.kc_elems;
+  p.bn = L.bn;
+  p.n_tiles = L.n_tiles;
+  p.m_tiles = (p.m_total + kTileM - 1) / kTileM;
+  p.stages = L.stages;
+  p.tmem_cols = L.tmem_cols;
+  p.acc_stride = L.tmem_cols / 2;
+  p.idesc = h->dtype == IEVM_DTYPE_I8 ? make_idesc_i8_u8s8(L.bn) : make_idesc_f16(L.bn);
+  p.out = tensor_ptr(h, d.out_tensor);
+  p.out_pitch = L.cout_pad;
+  p.res = d.res_tensor >= 0 ? tensor_ptr(h, d.res_tensor) : nullptr;
+  p.res_pitch = L.cout_pad;
+  p.ep0 = L.ep0;
+  p.ep1 = L.ep1;
+  p.out_zp = d.out_zp;
+  p.out_lo = d.relu ? d.out_zp : 0;
+  p.a_scale = d.out_scale;
+  p.res_scale = d.res_scale;
+  p.res_zp = d.res_zp;
+  p.inv_add_scale = d.res_tensor >= 0 ? 1.0f / d.add_scale : 0.f;
+  p.add_zp = d.add_zp;
+  p.relu = d.relu;
+  p.dump_acc = dump_acc;
+  p.dump_pitch = L.cout_pad;
+  p.stuck_flag = h->stuck_dev;
+  return p;
+}
+
+int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32_t* dump_acc) {
+  const ConvTcParams p = make_conv_params(h, L, n, dump_acc);
+  if (h->conv_impl == 1) {
+    ConvDirectParams g;
+    g.n = n; g.h = L.h; g.w = L.w; g.ho = L.ho; g.wo = L.wo;
+    g.cin_pitch = L.cin_pitch; g.cin_w = L.cin_w; g.cin_real = L.d.cin; g.cout_pad = L.cout_pad;
+    g.ksize = L.d.ksize; g.stride = L.d.stride; g.pad = L.d.pad;
+    const long long total = static_cast<long long>(p.m_total) * L.cout_pad;
+    const unsigned blocks = static_cast<unsigned>((total + 127) / 128);
+    if (h->dtype == IEVM_DTYPE_I8)
+      conv_direct_i8_kernel<<<blocks, 128, 0, s>>>(static_cast<const uint8_t*>(tensor_ptr(h, L.d.in_tensor)),
+                                                   static_cast<const int8_t*>(L.w_packed),
+                                                   static_cast<uint8_t*>(p.out), g, p);
+    else
+      conv_direct_f16_kernel<<<blocks, 128, 0, s>>>(static_cast<const __half*>(tensor_ptr(h, L.d.in_tensor)),
+                                                    static_cast<const __half*>(L.w_packed), g, p);
+    CUDA_TRY(cudaGetLastError());
+    return IEVM_OK;
+  }
+  const int grid = std::min(p.m_tiles * p.n_tiles, h->num_sms);
+  if (h->dtype == IEVM_DTYPE_I8)
+    conv_tc_kernel<kDtypeI8><<<grid, kConvThreads, L.smem_bytes, s>>>(L.tmap_a, L.tmap_b, p);
+  else
+    conv_tc_kernel<kDtypeF16><<<grid, kConvThreads, L.smem_bytes, s>>>(L.tmap_a, L.tmap_b, p);
+  CUDA_TRY(cudaGetLastError());
+  return IEVM_OK;
+}
+
+int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStream_t s) {
+  const bool i8 = h->dtype == IEVM_DTYPE_I8;
+  const bool prof = h->profile != 0;
+  if (prof) {
+    while (h->prof_events.size() < h->layers.size() + 2) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreate(&e));
+      h->prof_events.push_back(e);
+    }
+    h->prof_ms.resize(h->layers.size() + 1, 0.0);
+    h->prof_calls.resize(h->layers.size() + 1, 0);
+    CUDA_TRY(cudaEventRecord(h->prof_events[0], s));
+  }
+  if (i8) {
+    const long long plane = static_cast<long long>(h->in_h) * h->in_w;
+    const long long quads = static_cast<long long>(n) * plane / 4;
+    quantize_nchw3_to_nhwc4_kernel<<<static_cast<unsigned>((quads + 255) / 256), 256, 0, s>>>(
+        static_cast<const float*>(x), static_cast<uint8_t*>(tensor_ptr(h, 0)), quads, static_cast<int>(plane),
+        1.0f / h->in_scale, h->in_zp);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
+  for (size_t li = 0; li < h->layers.size(); ++li) {
+    const LayerPlan& L = h->layers[li];
+    const ievm_layer_desc& d = L.d;
+    if (prof && li > 0) CUDA_TRY(cudaEventRecord(h->prof_events[li + 1], s));
+    if (d.op == IEVM_OP_CONV && L.is_stem) {
+      const long long m_total = static_cast<long long>(n) * L.ho * L.wo;
+      if (i8) {
+        StemParams sp;
+        sp.n = n; sp.h = L.h; sp.w = L.w; sp.ho = L.ho; sp.wo = L.wo; sp.cpad = L.cout_pad; sp.in_zp = h->in_zp;
+        sp.w4 = static_cast<const uint32_t*>(L.w_stem); sp.wsum = L.wsum; sp.bdiv = L.ep0; sp.mult = L.ep1;
+        sp.out_zp = d.out_zp; sp.out_lo = d.relu ? d.out_zp : 0;
+        stem_conv7x7_simt_kernel<<<static_cast<unsigned>((m_total + 127) / 128), 128, 49 * L.cout_pad * 4, s>>>(
+            static_cast<const uint8_t*>(tensor_ptr(h, 0)), static_cast<uint8_t*>(tensor_ptr(h, d.out_tensor)), sp);
+      } else {
+        StemF16Params sp;
+        sp.n = n; sp.h = L.h; sp.w = L.w; sp.ho = L.ho; sp.wo = L.wo; sp.cpad = L.cout_pad;
+        sp.wt = static_cast<const __half*>(L.w_stem); sp.bias = L.ep0;
+        const long long total = m_total * (L.cout_pad / 8);
+        stem_conv7x7_f16_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 147 * L.cout_pad * 2, s>>>(
+            static_cast<const __half*>(x), static_cast<__half*>(tensor_ptr(h, d.out_tensor)), sp);
+      }
+      CUDA_TRY(cudaGetLastError());
+    } else if (d.op == IEVM_OP_CONV) {
+      if (int rc = launch_conv(h, L, n, s, nullptr)) return rc;
+    } else if (d.op == IEVM_OP_MAXPOOL) {
+      const TensorInfo& tin = h->tensors[d.in_tensor];
+      if (i8) {
+        const long long total = static_cast<long long>(n) * L.ho * L.wo * (tin.pitch / 16);
+        maxpool3x3s2_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+            static_cast<const uint8_t*>(tensor_ptr(h, d.in_tensor)), static_cast<uint8_t*>(tensor_ptr(h, d.out_tensor)),
+            n, L.h, L.w, L.ho, L.wo, tin.pitch);
+      } else {
+        const long long total = static_cast<long long>(n) * L.ho * L.wo * (tin.pitch / 8);
+        maxpool3x3s2_f16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+            static_cast<const __half*>(tensor_ptr(h, d.in_tensor)), static_cast<__half*>(tensor_ptr(h, d.out_tensor)),
+            n, L.h, L.w, L.ho, L.wo, tin.pitch);
+      }
+      CUDA_TRY(cudaGetLastError());
+    } else {   // head
+      const TensorInfo& tin = h->tensors[d.in_tensor];
+      if (i8) {
+        HeadParams hp;
+        hp.hw = tin.h * tin.w; hp.c = tin.c; hp.cpad = tin.pitch; hp.classes = d.cout; hp.in_zp = d.in_zp;
+        hp.w = static_cast<const int8_t*>(L.w_packed); hp.bdiv = L.ep0; hp.mult = L.ep1;
+        hp.fc_zp = d.out_zp; hp.fc_scale = d.out_scale;
+        head_i8_kernel<<<n, kHeadThreads, 0, s>>>(static_cast<const uint8_t*>(tensor_ptr(h, d.in_tensor)),
+                                                  static_cast<float*>(logits), nullptr, hp);
+      } else {
+        HeadF16Params hp;
+        hp.hw = tin.h * tin.w; hp.c = tin.c; hp.cpad = tin.pitch; hp.classes = d.cout;
+        hp.w = static_cast<const __half*>(L.w_packed); hp.bias = L.ep0;
+        head_f16_kernel<<<n, kHeadThreads, 0, s>>>(static_cast<const __half*>(tensor_ptr(h, d.in_tensor)),
+                                                   static_cast<__half*>(logits), hp);
+      }
+      CUDA_TRY(cudaGetLastError());
+    }
+  }
+  h->last_n = n;
+  if (prof) {
+    CUDA_TRY(cudaEventRecord(h->prof_events[h->layers.size() + 1], s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (size_t i = 0; i <= h->layers.size(); ++i) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[i], h->prof_events[i + 1]));
+      h->prof_ms[i] += ms;
+      h->prof_calls[i] += 1;
+    }
+  }
+  return IEVM_OK;
+}
+
+int forward_common(ievm_handle* h, int want_dtype, const void* x, int n, void* logits, void* stream) {
+  if (!h || !x || !logits) return fail(IEVM_ERR_BAD_ARG, "null argument");
+  if (h->dtype != want_dtype) return fail(IEVM_ERR_BAD_ARG, "engine dtype does not match this entry point");
+  if (n < 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "batch %d outside [0, %d]", n, h->max_batch);
+  if (n == 0) return IEVM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->use_graph || h->profile) return enqueue_forward(h, x, n, logits, s);
+  const auto key = std::make_tuple(n, x, logits);
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    cudaStream_t cs = h->own_stream;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_forward(h, x, n, logits, cs);
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(IEVM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = h->graphs.emplace(key, exec).first;
+  }
+  CUDA_TRY(cudaGraphLaunch(it->second, s));
+  h->last_n = n;
+  return IEVM_OK;
+}
+
+int check_stuck(ievm_handle* h, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return IEVM_OK;
+  const unsigned code = h->stuck_host ? *reinterpret_cast<volatile unsigned int*>(h->stuck_host) : 0;
+  return fail(IEVM_ERR_CUDA, "%s: %s (pipeline stuck code 0x%x: 0x1xx producer/empty, 0x2xx mma/tmem-empty, "
+              "0x3xx mma/full, 0x4xx epilogue/tmem-full)", what, cudaGetErrorString(e), code);
+}
+
+// Diagnostic: one im2col TMA tile, dumped raw (swizzled) from shared memory.
+__global__ void probe_im2col_kernel(const __grid_constant__ CUtensorMap tmap, int c0, int w0, int h0, int n0,
+                                    int tap_x, int tap_y, int bytes, uint8_t* out, unsigned int* stuck) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + bytes);
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) smem[i] = 0xEE;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, static_cast<uint32_t>(bytes));
+    tma_load_im2col_4d(smem, &tmap, bar, c0, w0, h0, n0, static_cast<uint16_t>(tap_x), static_cast<uint16_t>(tap_y));
+  }
+  wait_or_die(bar, 0, 0x900u, stuck);
+  __syncthreads();
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = smem[i];
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* ievm_last_error(void) { return g_last_error.c_str(); }
+
+const char* ievm_build_info(void) { return "ievm-b200 abi=1 arch=sm_100a kernels=tcgen05.mma(kind::i8,kind::f16)+TMA(im2col)"; }
+
+int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle** out) {
+  if (!nd || !out || !nd->layers || nd->num_layers <= 0 || max_batch <= 0)
+    return fail(IEVM_ERR_BAD_ARG, "ievm_create: bad arguments");
+  if (nd->dtype != IEVM_DTYPE_I8 && nd->dtype != IEVM_DTYPE_F16) return fail(IEVM_ERR_BAD_ARG, "unknown dtype");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(IEVM_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(IEVM_ERR_BAD_ARG, "device %d out of range", device);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(IEVM_ERR_UNSUPPORTED, "device is sm_%d%d; this build is sm_100a only", prop.major, prop.minor);
+  if (int rc = load_driver_entry_points()) return rc;
+
+  ievm_handle* h = new ievm_handle();
+  h->device = device;
+  h->dtype = nd->dtype;
+  h->elem = nd->dtype == IEVM_DTYPE_I8 ? 1 : 2;
+  h->max_batch = max_batch;
+  h->num_sms = prop.multiProcessorCount;
+  h->in_c = nd->in_c; h->in_h = nd->in_h; h->in_w = nd->in_w; h->classes = nd->num_classes;
+  h->in_scale = nd->in_scale; h->in_zp = nd->in_zp;
+  int rc = plan_shapes(h, nd);
+  for (size_t i = 0; rc == IEVM_OK && i < h->layers.size(); ++i) {
+    LayerPlan& L = h->layers[i];
+    if (L.d.op == IEVM_OP_CONV) rc = upload_conv_operands(h, L);
+    else if (L.d.op == IEVM_OP_HEAD) rc = upload_head_operands(h, L);
+    // host pointers in the copied descriptor must not be used after create returns
+    L.d.weight = nullptr; L.d.bias = nullptr; L.d.w_scale = nullptr;
+  }
+  if (rc == IEVM_OK) rc = assign_buffers(h);
+  if (rc == IEVM_OK) rc = encode_maps(h);
+  if (rc == IEVM_OK) {
+    size_t max_smem = 0;
+    for (const LayerPlan& L : h->layers) max_smem = std::max(max_smem, L.smem_bytes);
+    if (max_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) rc = fail(IEVM_ERR_UNSUPPORTED, "smem plan exceeds device limit");
+    if (rc == IEVM_OK && max_smem > 0) {
+      cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<kDtypeI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<kDtypeF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+      if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+  }
+  if (rc == IEVM_OK) {
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h->stuck_host), sizeof(unsigned int), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+      *h->stuck_host = 0;
+      e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->stuck_dev), h->stuck_host, 0);
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "runtime setup: %s", cudaGetErrorString(e));
+  }
+  if (rc != IEVM_OK) {
+    const std::string keep = g_last_error;
+    ievm_destroy(h);
+    g_last_error = keep;
+    return rc;
+  }
+  *out = h;
+  return IEVM_OK;
+}
+
+void ievm_destroy(ievm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  for (void* p : h->buffers) cudaFree(p);
+  for (void* p : h->owned) cudaFree(p);
+  if (h->stage_in) cudaFree(h->stage_in);
+  if (h->stage_out) cudaFree(h->stage_out);
+  if (h->pin_in) cudaFreeHost(h->pin_in);
+  if (h->pin_out) cudaFreeHost(h->pin_out);
+  if (h->stuck_host) cudaFreeHost(h->stuck_host);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int ievm_forward_i8(ievm_handle* h, const float* x, int n, float* logits, void* stream) {
+  return forward_common(h, IEVM_DTYPE_I8, x, n, logits, stream);
+}
+
+int ievm_forward_f16(ievm_handle* h, const void* x, int n, void* logits, void* stream) {
+  return forward_common(h, IEVM_DTYPE_F16, x, n, logits, stream);
+}
+
+static int forward_host_common(ievm_handle* h, int dtype, const void* x_host, int n, void* logits_host) {
+  if (!h || !x_host || !logits_host) return fail(IEVM_ERR_BAD_ARG, "null argument");
+  if (n <= 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "batch %d outside [1, %d]", n, h->max_batch);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t in_elem = dtype == IEVM_DTYPE_I8 ? 4 : 2;
+  const size_t out_elem = dtype == IEVM_DTYPE_I8 ? 4 : 2;
+  const size_t per_img = static_cast<size_t>(h->in_c) * h->in_h * h->in_w * in_elem;
+  if (!h->stage_in) {
+    CUDA_TRY(cudaMalloc(&h->stage_in, per_img * h->max_batch));
+    CUDA_TRY(cudaMalloc(&h->stage_out, out_elem * h->classes * h->max_batch));
+  }
+  cudaStream_t s = h->own_stream;
+  CUDA_TRY(cudaMemcpyAsync(h->stage_in, x_host, per_img * n, cudaMemcpyHostToDevice, s));
+  if (int rc = forward_common(h, dtype, h->stage_in, n, h->stage_out, s)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(logits_host, h->stage_out, out_elem * h->classes * n, cudaMemcpyDeviceToHost, s));
+  return check_stuck(h, cudaStreamSynchronize(s), "forward (host buffers)");
+}
+
+int ievm_forward_i8_host(ievm_handle* h, const float* x_host, int n, float* logits_host) {
+  return forward_host_common(h, IEVM_DTYPE_I8, x_host, n, logits_host);
+}
+int ievm_forward_f16_host(ievm_handle* h, const void* x_host, int n, void* logits_host) {
+  return forward_host_common(h, IEVM_DTYPE_F16, x_host, n, logits_host);
+}
+
+int ievm_set_option(ievm_handle* h, const char* name, int value) {
+  if (!h || !name) return fail(IEVM_ERR_BAD_ARG, "null argument");
+  if (!strcmp(name, "conv_impl")) {
+    if (value != 0 && value != 1) return fail(IEVM_ERR_BAD_ARG, "conv_impl must be 0 or 1");
+    h->conv_impl = value;
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+    return IEVM_OK;
+  }
+  if (!strcmp(name, "profile")) {
+    h->profile = value ? 1 : 0;
+    std::fill(h->prof_ms.begin(), h->prof_ms.end(), 0.0);
+    std::fill(h->prof_calls.begin(), h->prof_calls.end(), 0);
+    return IEVM_OK;
+  }
+  if (!strcmp(name, "use_graph")) {
+    h->use_graph = value ? 1 : 0;
+    return IEVM_OK;
+  }
+  if (!strcmp(name, "keep_tensors")) {
+    if ((value ? 1 : 0) == h->keep_tensors) return IEVM_OK;
+    h->keep_tensors = value ? 1 : 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (int rc = assign_buffers(h)) return rc;
+    return encode_maps(h);
+  }
+  return fail(IEVM_ERR_BAD_ARG, "unknown option '%s'", name);
+}
+
+int ievm_num_tensors(const ievm_handle* h) { return h ? static_cast<int>(h->tensors.size()) : 0; }
+
+int ievm_tensor_shape(const ievm_handle* h, int id, int32_t out6[6]) {
+  if (!h || id < 0 || id >= static_cast<int>(h->tensors.size()) || !out6) return fail(IEVM_ERR_BAD_ARG, "bad tensor id");
+  const TensorInfo& t = h->tensors[id];
+  out6[0] = h->last_n; out6[1] = t.h; out6[2] = t.w; out6[3] = t.c; out6[4] = t.pitch; out6[5] = t.elem;
+  return IEVM_OK;
+}
+
+int ievm_launches_per_forward(const ievm_handle* h) {
+  if (!h) return 0;
+  return static_cast<int>(h->layers.size()) + (h->dtype == IEVM_DTYPE_I8 ? 1 : 0);
+}
+
+int ievm_profile_read(const ievm_handle* h, int max_slots, float* ms_sum, int32_t* calls) {
+  if (!h || !ms_sum || !calls) return fail(IEVM_ERR_BAD_ARG, "null argument");
+  const int slots = static_cast<int>(h->prof_ms.size());
+  for (int i = 0; i < max_slots; ++i) {
+    ms_sum[i] = i < slots ? static_cast<float>(h->prof_ms[i]) : 0.f;
+    calls[i] = i < slots ? h->prof_calls[i] : 0;
+  }
+  return slots;
+}
+
+int ievm_debug_read_tensor(ievm_handle* h, int id, void* host_out, uint64_t host_bytes) {
+  if (!h || id < 0 || id >= static_cast<int>(h->tensors.size()) || !host_out) return fail(IEVM_ERR_BAD_ARG, "bad tensor id");
+  const TensorInfo& t = h->tensors[id];
+  if (t.buffer < 0) return fail(IEVM_ERR_BAD_ARG, "tensor %d has no engine-owned buffer", id);
+  const size_t bytes = t.bytes_per_image() * h->last_n;
+  if (host_bytes < bytes) return fail(IEVM_ERR_BAD_ARG, "host buffer too small: need %zu bytes", bytes);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = check_stuck(h, cudaDeviceSynchronize(), "debug_read_tensor sync")) return rc;
+  CUDA_TRY(cudaMemcpy(host_out, tensor_ptr(h, id), bytes, cudaMemcpyDeviceToHost));
+  return IEVM_OK;
+}
+
+int ievm_debug_conv_acc(ievm_handle* h, int layer, int n, int32_t* host_out, uint64_t host_bytes) {
+  if (!h || layer < 0 || layer >= static_cast<int>(h->layers.size()) || !host_out) return fail(IEVM_ERR_BAD_ARG, "bad layer");
+  const LayerPlan& L = h->layers[layer];
+  if (L.d.op != IEVM_OP_CONV || L.is_stem) return fail(IEVM_ERR_BAD_ARG, "layer %d is not a tensor-core conv", layer);
+  if (!h->keep_tensors) return fail(IEVM_ERR_BAD_ARG, "set keep_tensors=1 before the forward whose accumulators you want");
+  const size_t bytes = static_cast<size_t>(n) * L.ho * L.wo * L.cout_pad * sizeof(int32_t);
+  if (host_bytes < bytes) return fail(IEVM_ERR_BAD_ARG, "host buffer too small: need %zu bytes", bytes);
+  CUDA_TRY(cudaSetDevice(h->device));
+  int32_t* dacc = nullptr;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dacc), bytes));
+  int rc = launch_conv(h, L, n, h->own_stream, dacc);
+  if (rc == IEVM_OK) rc = check_stuck(h, cudaStreamSynchronize(h->own_stream), "debug_conv_acc");
+  if (rc == IEVM_OK && cudaMemcpy(host_out, dacc, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = fail(IEVM_ERR_CUDA, "accumulator copy failed");
+  cudaFree(dacc);
+  return rc;
+}
+
+int ievm_probe_im2col(const void* in_dev, int n, int h, int w, int c_pitch, int ksize, int stride, int pad,
+                      int kc_bytes, int m0, int tap_x, int tap_y, int c0, void* out_dev) {
+  if (!in_dev || !out_dev || (kc_bytes != 64 && kc_bytes != 128)) return fail(IEVM_ERR_BAD_ARG, "probe: bad arguments");
+  if (int rc = load_driver_entry_points()) return rc;
+  CUtensorMap tmap;
+  cuuint64_t dims[4] = {(cuuint64_t)c_pitch, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c_pitch, (cuuint64_t)w * c_pitch, (cuuint64_t)h * w * c_pitch};
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  const CUresult r = g_encode_im2col(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(in_dev), dims, strides,
+                                     lower, upper, (cuuint32_t)kc_bytes, kTileM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     kc_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "probe: cuTensorMapEncodeIm2col CUresult %d", (int)r);
+  const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (w + 2 * pad - ksize) / stride + 1;
+  const int img = m0 / (ho * wo), rem = m0 % (ho * wo);
+  const int oy = rem / wo, ox = rem % wo;
+  unsigned int* stuck_host = nullptr;
+  unsigned int* stuck_dev = nullptr;
+  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&stuck_host), sizeof(unsigned int), cudaHostAllocMapped));
+  *stuck_host = 0;
+  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&stuck_dev), stuck_host, 0));
+  const int bytes = kTileM * kc_bytes;
+  probe_im2col_kernel<<<1, 128, bytes + 1024 + 64>>>(tmap, c0, ox * stride - pad, oy * stride - pad, img, tap_x, tap_y,
+                                                     bytes, static_cast<uint8_t*>(out_dev), stuck_dev);
+  const cudaError_t e = cudaDeviceSynchronize();
+  const unsigned code = *stuck_host;
+  cudaFreeHost(stuck_host);
+  if (e != cudaSuccess) return fail(IEVM_ERR_CUDA, "probe_im2col: %s (stuck code 0x%x)", cudaGetErrorString(e), code);
+  return IEVM_OK;
+}
+
+int ievm_kd_loss(const float* s, const float* t, const int64_t* y, int n, int classes, float temperature, float* out3,
+                 void* stream) {
+  if (!s || !t || !y || !out3 || n <= 0 || classes <= 0) return fail(IEVM_ERR_BAD_ARG, "ievm_kd_loss: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(out3, 0, 3 * sizeof(float), st));
+  kd_loss_kernel<<<(n + 127) / 128, 128, 0, st>>>(s, t, reinterpret_cast<const long long*>(y), n, classes,
+                                                  temperature, out3);
+  kd_finalize_kernel<<<1, 32, 0, st>>>(out3, 1.0f / static_cast<float>(n));
+  CUDA_TRY(cudaGetLastError());
+  return IEVM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,499 @@
+// CUDA-core kernels around the tensor-core convolutions: input quantisation, the 3-channel stem,
+// max-pool, the avgpool+fc+dequantize head, and a plain direct convolution that the parity tests use
+// to cross-check the tcgen05 kernel on the GPU at sizes the CPU oracle cannot reach.
+// All INT8 arithmetic follows the formulas in oracle/int8_forward.py (float32, RNE, no contraction).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "conv_tc.cuh"
+
+namespace ievm {
+
+// --------------------------------------------------------------------------------------------
+// quantize_per_tensor (graph node 1): f32 NCHW [n,3,h,w] -> u8 NHWC4 [n,h,w,4] (4th byte = zp).
+// One thread = 4 consecutive pixels: three coalesced float4 loads, one 16-byte store.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t quant_u8(float x, float inv_scale, int zp) {
+  const int q = __float2int_rn(__fmul_rn(x, inv_scale)) + zp;
+  return static_cast<uint32_t>(min(max(q, 0), 255));
+}
+
+__global__ void __launch_bounds__(256)
+quantize_nchw3_to_nhwc4_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long n_quads,
+                               int plane /* h*w */, float inv_scale, int zp) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_quads) return;
+  const long long pix = i * 4;
+  const long long img = pix / plane;
+  const long long off = pix - img * plane;
+  const float* base = x + img * 3 * plane + off;
+  const float4 r = __ldg(reinterpret_cast<const float4*>(base));
+  const float4 g = __ldg(reinterpret_cast<const float4*>(base + plane));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(base + 2 * plane));
+  const uint32_t z = static_cast<uint32_t>(zp) << 24;
+  uint4 o;
+  o.x = quant_u8(r.x, inv_scale, zp) | (quant_u8(g.x, inv_scale, zp) << 8) | (quant_u8(b.x, inv_scale, zp) << 16) | z;
+  o.y = quant_u8(r.y, inv_scale, zp) | (quant_u8(g.y, inv_scale, zp) << 8) | (quant_u8(b.y, inv_scale, zp) << 16) | z;
+  o.z = quant_u8(r.z, inv_scale, zp) | (quant_u8(g.z, inv_scale, zp) << 8) | (quant_u8(b.z, inv_scale, zp) << 16) | z;
+  o.w = quant_u8(r.w, inv_scale, zp) | (quant_u8(g.w, inv_scale, zp) << 8) | (quant_u8(b.w, inv_scale, zp) << 16) | z;
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
+__device__ __forceinline__ int dp4a_u8s8(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+  return d;
+}
+
+// --------------------------------------------------------------------------------------------
+// Stem: 7x7 stride-2 pad-3 conv over u8 NHWC4 + requant + ReLU -> u8 NHWC(cpad).
+// One thread = one output pixel; the 49 input pixels sit in registers, weights are broadcast from
+// shared memory as [tap][cout] s8x4 words.  sum (xq - zp) w = sum xq w - zp * sum w because
+// out-of-image taps read the value zp.
+// --------------------------------------------------------------------------------------------
+struct StemParams {
+  int n, h, w, ho, wo;
+  int cpad;                  // padded cout (multiple of 16)
+  int in_zp;
+  const uint32_t* w4;        // [49][cpad] s8x4 (c0,c1,c2,0)
+  const int* wsum;           // [cpad]
+  const float* bdiv;
+  const float* mult;
+  int out_zp, out_lo;
+};
+
+__global__ void __launch_bounds__(128)
+stem_conv7x7_simt_kernel(const uint8_t* __restrict__ xq, uint8_t* __restrict__ out, const StemParams p) {
+  extern __shared__ uint32_t s_w[];    // [49][cpad]
+  for (int i = threadIdx.x; i < 49 * p.cpad; i += blockDim.x) s_w[i] = p.w4[i];
+  __syncthreads();
+  const long long m = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long m_total = static_cast<long long>(p.n) * p.ho * p.wo;
+  if (m >= m_total) return;
+  const int hw = p.ho * p.wo;
+  const int img = static_cast<int>(m / hw);
+  const int rem = static_cast<int>(m - static_cast<long long>(img) * hw);
+  const int oy = rem / p.wo, ox = rem - (rem / p.wo) * p.wo;
+  const uint32_t zpix = static_cast<uint32_t>(p.in_zp) * 0x01010101u;
+  const uint32_t* in32 = reinterpret_cast<const uint32_t*>(xq) + static_cast<long long>(img) * p.h * p.w;
+  uint32_t px[49];
+#pragma unroll
+  for (int ky = 0; ky < 7; ++ky) {
+    const int iy = oy * 2 - 3 + ky;
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const int ix = ox * 2 - 3 + kx;
+      const bool ok = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+      px[ky * 7 + kx] = ok ? __ldg(in32 + iy * p.w + ix) : zpix;
+    }
+  }
+  uint8_t* orow = out + m * p.cpad;
+  for (int c0 = 0; c0 < p.cpad; c0 += 16) {
+    int acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0;
+#pragma unroll
+    for (int t = 0; t < 49; ++t) {
+      const uint4* wr = reinterpret_cast<const uint4*>(s_w + t * p.cpad + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 w = wr[j];
+        acc[4 * j] = dp4a_u8s8(px[t], w.x, acc[4 * j]);
+        acc[4 * j + 1] = dp4a_u8s8(px[t], w.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = dp4a_u8s8(px[t], w.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = dp4a_u8s8(px[t], w.w, acc[4 * j + 3]);
+      }
+    }
+    uint32_t packed[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t wd = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int c = c0 + 4 * j + b;
+        const int a = acc[4 * j + b] - p.in_zp * __ldg(p.wsum + c);
+        wd |= static_cast<uint32_t>(requant_i8(a, __ldg(p.bdiv + c), __ldg(p.mult + c), p.out_zp, p.out_lo)) << (8 * b);
+      }
+      packed[j] = wd;
+    }
+    *reinterpret_cast<uint4*>(orow + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// MaxPool2d(3, 2, 1) on u8 NHWC (graph node `maxpool`): padding ignored, qparams pass through.
+// One thread = one output pixel x 16 channels.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n, int h, int w, int ho,
+                       int wo, int cpad) {
+  const int groups = cpad / 16;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * ho * wo * groups;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % groups);
+  const long long pix = i / groups;
+  const int ox = static_cast<int>(pix % wo);
+  const int oy = static_cast<int>((pix / wo) % ho);
+  const int img = static_cast<int>(pix / (static_cast<long long>(wo) * ho));
+  uint4 best = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - 1 + ky;
+    if (iy < 0 || iy >= h) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 - 1 + kx;
+      if (ix < 0 || ix >= w) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+          in + ((static_cast<long long>(img) * h + iy) * w + ix) * cpad + g * 16));
+      best.x = __vmaxu4(best.x, v.x);
+      best.y = __vmaxu4(best.y, v.y);
+      best.z = __vmaxu4(best.z, v.z);
+      best.w = __vmaxu4(best.w, v.w);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + pix * cpad + g * 16) = best;
+}
+
+// FP16 variant: one thread = one output pixel x 8 channels.
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_f16_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n, int h, int w, int ho,
+                        int wo, int cpad) {
+  const int groups = cpad / 8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n) * ho * wo * groups;
+  if (i >= total) return;
+  const int g = static_cast<int>(i % groups);
+  const long long pix = i / groups;
+  const int ox = static_cast<int>(pix % wo);
+  const int oy = static_cast<int>((pix / wo) % ho);
+  const int img = static_cast<int>(pix / (static_cast<long long>(wo) * ho));
+  __half2 best[4];
+  bool first = true;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - 1 + ky;
+    if (iy < 0 || iy >= h) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 - 1 + kx;
+      if (ix < 0 || ix >= w) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+          in + ((static_cast<long long>(img) * h + iy) * w + ix) * cpad + g * 8));
+      const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) best[j] = first ? hv[j] : __hmax2(best[j], hv[j]);
+      first = false;
+    }
+  }
+  *reinterpret_cast<uint4*>(out + pix * cpad + g * 8) = *reinterpret_cast<const uint4*>(best);
+}
+
+// --------------------------------------------------------------------------------------------
+// Head: AdaptiveAvgPool2d(1) + flatten + quantized Linear + dequantize, one CTA per image.
+//   pooled = clamp(rne(float(sum) / count), 0, 255)  (same qparams as the input, zp == in_zp)
+//   acc[o] = sum_c (pooled[c] - in_zp) * w[o][c];  q = requant(acc);  logit = (q - fc_zp) * fc_scale
+// --------------------------------------------------------------------------------------------
+struct HeadParams {
+  int hw;            // pixels per image (7*7)
+  int c;             // real channels
+  int cpad;          // channel pitch
+  int classes;
+  int in_zp;
+  const int8_t* w;   // [classes][cpad]
+  const float* bdiv;
+  const float* mult;
+  int fc_zp;
+  float fc_scale;
+};
+
+constexpr int kHeadThreads = 128;
+constexpr int kMaxClasses = 16;
+
+__global__ void __launch_bounds__(kHeadThreads)
+head_i8_kernel(const uint8_t* __restrict__ in, float* __restrict__ logits, uint8_t* __restrict__ pooled_dbg,
+               const HeadParams p) {
+  __shared__ int s_part[kHeadThreads / 32][kMaxClasses];
+  const int img = blockIdx.x;
+  const uint8_t* base = in + static_cast<long long>(img) * p.hw * p.cpad;
+  int acc[kMaxClasses];
+#pragma unroll
+  for (int o = 0; o < kMaxClasses; ++o) acc[o] = 0;
+  const float cnt = static_cast<float>(p.hw);
+  for (int c4 = threadIdx.x * 4; c4 < p.cpad; c4 += kHeadThreads * 4) {
+    int s[4] = {0, 0, 0, 0};
+    for (int px = 0; px < p.hw; ++px) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + px * p.cpad + c4));
+      s[0] += v & 0xff;
+      s[1] += (v >> 8) & 0xff;
+      s[2] += (v >> 16) & 0xff;
+      s[3] += v >> 24;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c4 + j;
+      if (c >= p.c) continue;
+      int q = __float2int_rn(__fdiv_rn(__int2float_rn(s[j]), cnt));
+      q = min(max(q, 0), 255);
+      if (pooled_dbg) pooled_dbg[static_cast<long long>(img) * p.c + c] = static_cast<uint8_t>(q);
+      const int xv = q - p.in_zp;
+      for (int o = 0; o < p.classes; ++o) acc[o] += xv * static_cast<int>(p.w[o * p.cpad + c]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 0; o < p.classes; ++o) {
+    int v = acc[o];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) s_part[warp][o] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < p.classes) {
+    const int o = threadIdx.x;
+    int a = 0;
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) a += s_part[wv][o];
+    const int q = requant_i8(a, p.bdiv[o], p.mult[o], p.fc_zp, 0);
+    logits[static_cast<long long>(img) * p.classes + o] = __fmul_rn(__int2float_rn(q - p.fc_zp), p.fc_scale);
+  }
+}
+
+// FP16 head: avgpool (fp32 accumulate, rounded to f16 like the reference's pooled tensor) + fc.
+struct HeadF16Params {
+  int hw, c, cpad, classes;
+  const __half* w;   // [classes][cpad]
+  const float* bias;
+};
+
+__global__ void __launch_bounds__(kHeadThreads)
+head_f16_kernel(const __half* __restrict__ in, __half* __restrict__ logits, const HeadF16Params p) {
+  __shared__ float s_part[kHeadThreads / 32][kMaxClasses];
+  const int img = blockIdx.x;
+  const __half* base = in + static_cast<long long>(img) * p.hw * p.cpad;
+  float acc[kMaxClasses];
+#pragma unroll
+  for (int o = 0; o < kMaxClasses; ++o) acc[o] = 0.f;
+  const float inv = 1.0f / static_cast<float>(p.hw);
+  for (int c2 = threadIdx.x * 2; c2 < p.cpad; c2 += kHeadThreads * 2) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int px = 0; px < p.hw; ++px) {
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(base + px * p.cpad + c2));
+      s0 += v.x;
+      s1 += v.y;
+    }
+    const float m0 = __half2float(__float2half_rn(s0 * inv));
+    const float m1 = __half2float(__float2half_rn(s1 * inv));
+    for (int o = 0; o < p.classes; ++o) {
+      if (c2 < p.c) acc[o] += m0 * __half2float(p.w[o * p.cpad + c2]);
+      if (c2 + 1 < p.c) acc[o] += m1 * __half2float(p.w[o * p.cpad + c2 + 1]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 0; o < p.classes; ++o) {
+    float v = acc[o];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) s_part[warp][o] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < p.classes) {
+    const int o = threadIdx.x;
+    float a = p.bias[o];
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) a += s_part[wv][o];
+    logits[static_cast<long long>(img) * p.classes + o] = __float2half_rn(a);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Direct convolution over the same packed operands as the tensor-core kernel (one thread = one
+// output pixel x one output channel).  Test / cross-check path only: never used by forward().
+// --------------------------------------------------------------------------------------------
+struct ConvDirectParams {
+  int n, h, w, ho, wo;
+  int cin_pitch;       // input elements per pixel
+  int cin_w;           // packed weight channels per tap (kchunks * kc_elems)
+  int cin_real;
+  int cout_pad;
+  int ksize, stride, pad;
+};
+
+__global__ void __launch_bounds__(128)
+conv_direct_i8_kernel(const uint8_t* __restrict__ in, const int8_t* __restrict__ wp, uint8_t* __restrict__ out,
+                      const ConvDirectParams g, const ConvTcParams p) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(p.m_total) * g.cout_pad;
+  if (idx >= total) return;
+  const int co = static_cast<int>(idx % g.cout_pad);
+  const long long m = idx / g.cout_pad;
+  const int hw = g.ho * g.wo;
+  const int img = static_cast<int>(m / hw);
+  const int rem = static_cast<int>(m - static_cast<long long>(img) * hw);
+  const int oy = rem / g.wo, ox = rem - (rem / g.wo) * g.wo;
+  int acc = 0;
+  const int taps = g.ksize * g.ksize;
+  for (int ky = 0; ky < g.ksize; ++ky) {
+    const int iy = oy * g.stride - g.pad + ky;
+    if (iy < 0 || iy >= g.h) continue;
+    for (int kx = 0; kx < g.ksize; ++kx) {
+      const int ix = ox * g.stride - g.pad + kx;
+      if (ix < 0 || ix >= g.w) continue;
+      const uint8_t* ip = in + ((static_cast<long long>(img) * g.h + iy) * g.w + ix) * g.cin_pitch;
+      const int8_t* wr = wp + (static_cast<long long>(co) * taps + ky * g.ksize + kx) * g.cin_w;
+      for (int ci = 0; ci < g.cin_real; ++ci) acc += static_cast<int>(ip[ci]) * static_cast<int>(wr[ci]);
+    }
+  }
+  if (p.dump_acc) p.dump_acc[m * p.dump_pitch + co] = acc;
+  int q = requant_i8(acc, p.ep0[co], p.ep1[co], p.out_zp, p.out_lo);
+  if (p.res != nullptr) {
+    const int r = static_cast<const uint8_t*>(p.res)[m * p.res_pitch + co];
+    q = add_relu_i8(q, p.out_zp, p.a_scale, r, p.res_zp, p.res_scale, p.inv_add_scale, p.add_zp);
+  }
+  static_cast<uint8_t*>(p.out)[m * p.out_pitch + co] = static_cast<uint8_t>(q);
+}
+
+__global__ void __launch_bounds__(128)
+conv_direct_f16_kernel(const __half* __restrict__ in, const __half* __restrict__ wp, const ConvDirectParams g,
+                       const ConvTcParams p) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(p.m_total) * g.cout_pad;
+  if (idx >= total) return;
+  const int co = static_cast<int>(idx % g.cout_pad);
+  const long long m = idx / g.cout_pad;
+  const int hw = g.ho * g.wo;
+  const int img = static_cast<int>(m / hw);
+  const int rem = static_cast<int>(m - static_cast<long long>(img) * hw);
+  const int oy = rem / g.wo, ox = rem - (rem / g.wo) * g.wo;
+  float acc = 0.f;
+  const int taps = g.ksize * g.ksize;
+  for (int ky = 0; ky < g.ksize; ++ky) {
+    const int iy = oy * g.stride - g.pad + ky;
+    if (iy < 0 || iy >= g.h) continue;
+    for (int kx = 0; kx < g.ksize; ++kx) {
+      const int ix = ox * g.stride - g.pad + kx;
+      if (ix < 0 || ix >= g.w) continue;
+      const __half* ip = in + ((static_cast<long long>(img) * g.h + iy) * g.w + ix) * g.cin_pitch;
+      const __half* wr = wp + (static_cast<long long>(co) * taps + ky * g.ksize + kx) * g.cin_w;
+      for (int ci = 0; ci < g.cin_real; ++ci) acc += __half2float(ip[ci]) * __half2float(wr[ci]);
+    }
+  }
+  float f = acc + p.ep0[co];
+  if (p.res != nullptr) f += __half2float(static_cast<const __half*>(p.res)[m * p.res_pitch + co]);
+  if (p.relu) f = fmaxf(f, 0.f);
+  static_cast<__half*>(p.out)[m * p.out_pitch + co] = __float2half_rn(f);
+}
+
+// --------------------------------------------------------------------------------------------
+// FP16 stem: 7x7/2 conv over f16 NCHW input (3 channels) + folded-BN bias + ReLU -> f16 NHWC(cpad).
+// One thread = one output pixel x 8 output channels; weights [tap*3 + c][cpad] f16 in shared memory.
+// --------------------------------------------------------------------------------------------
+struct StemF16Params {
+  int n, h, w, ho, wo, cpad;
+  const __half* wt;      // [147][cpad]
+  const float* bias;     // [cpad]
+};
+
+__global__ void __launch_bounds__(128)
+stem_conv7x7_f16_kernel(const __half* __restrict__ x, __half* __restrict__ out, const StemF16Params p) {
+  extern __shared__ uint32_t s_raw[];
+  __half* s_w = reinterpret_cast<__half*>(s_raw);
+  for (int i = threadIdx.x; i < 147 * p.cpad; i += blockDim.x) s_w[i] = p.wt[i];
+  __syncthreads();
+  const int groups = p.cpad / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(p.n) * p.ho * p.wo * groups;
+  if (idx >= total) return;
+  // pixel-major thread order inside a warp keeps the NCHW reads coalesced
+  const long long m = idx % (static_cast<long long>(p.n) * p.ho * p.wo);
+  const int g = static_cast<int>(idx / (static_cast<long long>(p.n) * p.ho * p.wo));
+  const int hw = p.ho * p.wo;
+  const int img = static_cast<int>(m / hw);
+  const int rem = static_cast<int>(m - static_cast<long long>(img) * hw);
+  const int oy = rem / p.wo, ox = rem - (rem / p.wo) * p.wo;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const long long plane = static_cast<long long>(p.h) * p.w;
+  const __half* xin = x + static_cast<long long>(img) * 3 * plane;
+  for (int ky = 0; ky < 7; ++ky) {
+    const int iy = oy * 2 - 3 + ky;
+    if (iy < 0 || iy >= p.h) continue;
+    for (int kx = 0; kx < 7; ++kx) {
+      const int ix = ox * 2 - 3 + kx;
+      if (ix < 0 || ix >= p.w) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float xv = __half2float(__ldg(xin + c * plane + static_cast<long long>(iy) * p.w + ix));
+        const uint4 wv = *reinterpret_cast<const uint4*>(s_w + ((ky * 7 + kx) * 3 + c) * p.cpad + g * 8);
+        const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 w2 = __half22float2(wh[j]);
+          acc[2 * j] = fmaf(xv, w2.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(xv, w2.y, acc[2 * j + 1]);
+        }
+      }
+    }
+  }
+  __half2 o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = fmaxf(acc[2 * j] + p.bias[g * 8 + 2 * j], 0.f);
+    const float b = fmaxf(acc[2 * j + 1] + p.bias[g * 8 + 2 * j + 1], 0.f);
+    o[j] = __floats2half2_rn(a, b);
+  }
+  *reinterpret_cast<uint4*>(out + m * p.cpad + g * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+// --------------------------------------------------------------------------------------------
+// KD evaluation loss (knowledge_distillation/train.py:47-57): per-row CE and T^2 * KL, fp32.
+// out3 += {sum_i CE_i, sum_i KL_i * T^2, correct_count}; the caller divides by the batch size.
+// --------------------------------------------------------------------------------------------
+__global__ void kd_loss_kernel(const float* __restrict__ s, const float* __restrict__ t,
+                               const long long* __restrict__ y, int n, int classes, float temp, float* out3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float ce = 0.f, kl = 0.f, correct = 0.f;
+  if (i < n) {
+    const float* sr = s + static_cast<long long>(i) * classes;
+    const float* tr = t + static_cast<long long>(i) * classes;
+    float ms = -INFINITY, mst = -INFINITY, mtt = -INFINITY;
+    int arg = 0;
+    for (int c = 0; c < classes; ++c) {
+      if (sr[c] > ms) { ms = sr[c]; arg = c; }
+      mst = fmaxf(mst, sr[c] / temp);
+      mtt = fmaxf(mtt, tr[c] / temp);
+    }
+    float zs = 0.f, zst = 0.f, ztt = 0.f;
+    for (int c = 0; c < classes; ++c) {
+      zs += expf(sr[c] - ms);
+      zst += expf(sr[c] / temp - mst);
+      ztt += expf(tr[c] / temp - mtt);
+    }
+    const float lzs = logf(zs), lzst = logf(zst), lztt = logf(ztt);
+    const int label = static_cast<int>(y[i]);
+    ce = -(sr[label] - ms - lzs);
+    for (int c = 0; c < classes; ++c) {
+      const float logp_t = tr[c] / temp - mtt - lztt;
+      const float logp_s = sr[c] / temp - mst - lzst;
+      kl += expf(logp_t) * (logp_t - logp_s);
+    }
+    kl *= temp * temp;
+    correct = arg == label ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    ce += __shfl_xor_sync(0xffffffffu, ce, d);
+    kl += __shfl_xor_sync(0xffffffffu, kl, d);
+    correct += __shfl_xor_sync(0xffffffffu, correct, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out3 + 0, ce);
+    atomicAdd(out3 + 1, kl);
+    atomicAdd(out3 + 2, correct);
+  }
+}
+
+__global__ void kd_finalize_kernel(float* out3, float inv_n) {
+  if (threadIdx.x < 2) out3[threadIdx.x] *= inv_n;     // CE and KL are batch means; [2] stays a count
+}
+
+}  // namespace ievm

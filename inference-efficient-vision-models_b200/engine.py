@@ -1,0 +1,229 @@
+"""``nn.Module`` drop-ins for the reference's hot path, backed by the sm_100a engine (C ABI).
+
+``B200QuantizedResNet`` stands where the reference holds the FX-converted INT8 ``GraphModule``
+(quantization/engines.py:118) and ``B200HalfResNet`` where it holds ``model.half()``
+(quantization/engines.py:91-92): the call ``outputs = model(images)`` (engines.py:27,31,60;
+quantization/main.py:287) keeps its dtypes and shapes -- f32 NCHW in / f32 logits out for INT8, f16 in /
+f16 out for FP16 -- and ``.eval()``, ``.parameters()`` (dtype sniffing at engines.py:20,47),
+``.state_dict()`` and ``.to()/.cpu()`` keep working for the callers that touch them.
+There is no fallback path: if the CUDA library is missing or no B200 is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .netdesc import DTYPE_F16, DTYPE_I8, OP_CONV, OP_HEAD, NetSpec, from_converted, from_half_module, \
+    from_quantized_state_dict
+
+
+def _marshal(net: NetSpec):
+    """NetSpec -> (NetDesc, keepalive list)."""
+    keep = []
+    arr = (_lib.LayerDesc * len(net.layers))()
+    for i, L in enumerate(net.layers):
+        d = arr[i]
+        d.op, d.in_tensor, d.res_tensor, d.out_tensor = L.op, L.in_tensor, L.res_tensor, L.out_tensor
+        d.cin, d.cout, d.ksize, d.stride, d.pad, d.relu = L.cin, L.cout, L.ksize, L.stride, L.pad, int(L.relu)
+        for field_name, a, dt in (("weight", L.weight, None), ("bias", L.bias, np.float32),
+                                  ("w_scale", L.w_scale, np.float32)):
+            if a is None:
+                setattr(d, field_name, None)
+                continue
+            a = np.ascontiguousarray(a if dt is None else a.astype(dt))
+            keep.append(a)
+            setattr(d, field_name, a.ctypes.data)
+        d.in_scale, d.in_zp = L.in_scale, L.in_zp
+        d.out_scale, d.out_zp = L.out_scale, L.out_zp
+        d.res_scale, d.res_zp = L.res_scale, L.res_zp
+        d.add_scale, d.add_zp = L.add_scale, L.add_zp
+    nd = _lib.NetDesc()
+    nd.dtype, nd.num_layers = net.dtype, len(net.layers)
+    nd.in_c, nd.in_h, nd.in_w, nd.num_classes = net.in_c, net.in_h, net.in_w, net.num_classes
+    nd.in_scale, nd.in_zp = net.in_scale, net.in_zp
+    nd.layers = arr
+    keep.append(arr)
+    return nd, keep
+
+
+class _B200Engine(nn.Module):
+    _torch_dtype = torch.float32
+
+    def __init__(self, net: NetSpec, source=None, device: Optional[int] = None, max_batch: int = 256):
+        super().__init__()
+        self._lib = _lib.load()          # raises when the CUDA extension has not been built
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200 engine: no CUDA device visible and there is no CPU fallback")
+        self.net = net
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.max_batch = int(max_batch)
+        self._source = source            # the reference-side module, kept for state_dict()/parameters()
+        # One zero-size parameter of the right dtype keeps `next(model.parameters()).dtype`
+        # (quantization/engines.py:20,47) meaningful.
+        self._dtype_probe = nn.Parameter(torch.empty(0, dtype=self._torch_dtype), requires_grad=False)
+        self._handle = C.c_void_p()
+        nd, keep = _marshal(net)
+        _lib.check(self._lib.ievm_create(C.byref(nd), self.device_index, self.max_batch, C.byref(self._handle)),
+                   "ievm_create")
+        del keep
+
+    # ---- reference-facing protocol ---------------------------------------------------------
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        if images.dim() != 4 or tuple(images.shape[1:]) != (self.net.in_c, self.net.in_h, self.net.in_w):
+            raise ValueError(f"expected [N,{self.net.in_c},{self.net.in_h},{self.net.in_w}], got {tuple(images.shape)}")
+        if images.dtype != self._torch_dtype:
+            raise TypeError(f"expected {self._torch_dtype} input, got {images.dtype}")
+        n = images.shape[0]
+        if n > self.max_batch:
+            return torch.cat([self.forward(images[i:i + self.max_batch]) for i in range(0, n, self.max_batch)])
+        if not images.is_cuda:
+            return self._forward_host(images)
+        x = images.contiguous()
+        out = torch.empty((n, self.net.num_classes), dtype=self._torch_dtype, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self._forward_fn(self._handle, x.data_ptr(), n, out.data_ptr(), stream), "ievm_forward")
+        return out
+
+    def _forward_host(self, images: torch.Tensor) -> torch.Tensor:
+        """CPU tensor in, CPU tensor out (the reference's loops hand over CPU batches:
+        quantization/engines.py:52-60): H2D copy, forward and D2H copy inside the C call."""
+        x = images.contiguous()
+        n = x.shape[0]
+        out = torch.empty((n, self.net.num_classes), dtype=self._torch_dtype)
+        _lib.check(self._forward_host_fn(self._handle, x.data_ptr(), n, out.data_ptr()), "ievm_forward_host")
+        return out
+
+    def state_dict(self, *args, **kwargs):
+        if self._source is not None and hasattr(self._source, "state_dict"):
+            return self._source.state_dict(*args, **kwargs)
+        return super().state_dict(*args, **kwargs)
+
+    def to(self, *args, **kwargs):       # the engine is bound to its B200; .to()/.cpu() are no-ops
+        return self
+
+    def cpu(self):
+        return self
+
+    def cuda(self, device=None):
+        return self
+
+    def half(self):
+        if self._torch_dtype != torch.float16:
+            raise TypeError("an INT8 engine cannot be cast to half")
+        return self
+
+    # ---- engine controls / parity hooks --------------------------------------------------
+    def set_option(self, name: str, value: int) -> None:
+        _lib.check(self._lib.ievm_set_option(self._handle, name.encode(), int(value)), f"set_option({name})")
+
+    @property
+    def launches_per_forward(self) -> int:
+        return int(self._lib.ievm_launches_per_forward(self._handle))
+
+    def profile_read(self):
+        """[(name, total_ms, calls)] per launch slot accumulated since set_option('profile', 1)."""
+        slots = len(self.net.layers) + 1
+        ms = (C.c_float * slots)()
+        calls = (C.c_int32 * slots)()
+        self._lib.ievm_profile_read(self._handle, slots, ms, calls)
+        names = ["quantize_input"] + [L.name for L in self.net.layers]
+        return [(names[i], float(ms[i]), int(calls[i])) for i in range(slots)]
+
+    def tensor_shape(self, tid: int):
+        out = (C.c_int32 * 6)()
+        _lib.check(self._lib.ievm_tensor_shape(self._handle, tid, C.byref(out)), "ievm_tensor_shape")
+        return tuple(out)
+
+    def read_tensor(self, tid: int) -> np.ndarray:
+        """Tensor ``tid`` of the last forward as NCHW over the real channels (needs keep_tensors=1)."""
+        n, h, w, c, pitch, elem = self.tensor_shape(tid)
+        dt = np.uint8 if elem == 1 else np.float16
+        buf = np.empty((n, h, w, pitch), dtype=dt)
+        _lib.check(self._lib.ievm_debug_read_tensor(self._handle, tid, buf.ctypes.data, buf.nbytes), "read_tensor")
+        return np.ascontiguousarray(buf[..., :c].transpose(0, 3, 1, 2))
+
+    def read_tensor_by_name(self, name: str) -> np.ndarray:
+        for tid, nm in self.net.tensor_names.items():
+            if nm == name:
+                return self.read_tensor(tid)
+        raise KeyError(name)
+
+    def conv_accumulators(self, layer_name: str, n: int) -> np.ndarray:
+        """Raw tensor-core accumulators of conv ``layer_name`` as NCHW over real channels."""
+        for li, L in enumerate(self.net.layers):
+            if L.name == layer_name and L.op == OP_CONV:
+                _, h, w, c, pitch, _ = self.tensor_shape(L.out_tensor)
+                buf = np.empty((n, h, w, pitch), dtype=np.int32)
+                _lib.check(self._lib.ievm_debug_conv_acc(self._handle, li, n, buf.ctypes.data, buf.nbytes),
+                           "conv_accumulators")
+                acc = np.ascontiguousarray(buf[..., :c].transpose(0, 3, 1, 2))
+                return acc if self.net.dtype == DTYPE_I8 else acc.view(np.float32)
+        raise KeyError(layer_name)
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.ievm_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class B200QuantizedResNet(_B200Engine):
+    """Drop-in for the converted static-INT8 module (fbgemm semantics, bit-exact target)."""
+    _torch_dtype = torch.float32
+
+    def __init__(self, net: NetSpec, **kw):
+        if net.dtype != DTYPE_I8:
+            raise ValueError("expected an INT8 NetSpec")
+        super().__init__(net, **kw)
+        self._forward_fn = self._lib.ievm_forward_i8
+        self._forward_host_fn = self._lib.ievm_forward_i8_host
+
+    @classmethod
+    def from_converted(cls, gm, **kw) -> "B200QuantizedResNet":
+        return cls(from_converted(gm), source=gm, **kw)
+
+    @classmethod
+    def from_quantized_state_dict(cls, sd, **kw) -> "B200QuantizedResNet":
+        return cls(from_quantized_state_dict(sd), **kw)
+
+
+class B200HalfResNet(_B200Engine):
+    """Drop-in for ``model.half()`` (student ResNet-18 or ResNet-50 teacher)."""
+    _torch_dtype = torch.float16
+
+    def __init__(self, net: NetSpec, **kw):
+        if net.dtype != DTYPE_F16:
+            raise ValueError("expected an FP16 NetSpec")
+        super().__init__(net, **kw)
+        self._forward_fn = self._lib.ievm_forward_f16
+        self._forward_host_fn = self._lib.ievm_forward_f16_host
+
+    @classmethod
+    def from_half_module(cls, model, **kw) -> "B200HalfResNet":
+        return cls(from_half_module(model), source=model, **kw)
+
+
+def kd_eval_loss(student_logits: torch.Tensor, teacher_logits: torch.Tensor, labels: torch.Tensor,
+                 alpha: float = 0.5, temperature: float = 4.0):
+    """Soft-target KD loss of knowledge_distillation/train.py:47-57 on device logits.
+    Returns (loss, ce, kd, n_correct) as a 4-element CUDA tensor without synchronising."""
+    lib = _lib.load()
+    s = student_logits.float().contiguous()
+    t = teacher_logits.float().contiguous()
+    y = labels.to(torch.int64).contiguous()
+    out3 = torch.empty(3, dtype=torch.float32, device=s.device)
+    _lib.check(lib.ievm_kd_loss(s.data_ptr(), t.data_ptr(), y.data_ptr(), s.shape[0], s.shape[1],
+                                float(temperature), out3.data_ptr(),
+                                torch.cuda.current_stream(s.device).cuda_stream), "ievm_kd_loss")
+    loss = (1.0 - alpha) * out3[0] + alpha * out3[1]
+    return torch.stack([loss, out3[0], out3[1], out3[2]])

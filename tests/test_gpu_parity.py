@@ -1,0 +1,246 @@
+"""GPU tier (-m gpu): the CUDA engine, called through the C ABI, against the CPU oracle, the golden
+fixtures recorded from the reference's own engine, and size-independent properties at full batch.
+
+Bars (BASELINE.json north_star): int32 accumulators bit-exact; requantised activations within +-1 LSB
+(we assert bit-exact); INT8 logits identical => top-1 agreement 100 % (lowest index on ties);
+FP16 logits within 1e-2 row-relative of the reference's ``.half()`` path.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from ievm_testutil import cached_quantized  # noqa: E402
+from oracle import int8_forward as O  # noqa: E402
+from oracle import model_factory as mf  # noqa: E402
+
+WIDTHS = {"w57": mf.PRUNED_WIDTHS, "w60": mf.DEFAULT_CFG_WIDTHS, "w64": mf.UNPRUNED_WIDTHS}
+FP16_REL_TOL = 1e-2     # north_star: "FP16 logits within 1e-2 relative" (row-normalised)
+
+
+def _engine(widths, **kw):
+    import ievm_b200
+    return ievm_b200.B200QuantizedResNet.from_converted(cached_quantized(widths), **kw)
+
+
+def _row_rel(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return (np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1.0)).max()
+
+
+# ------------------------------------------------------------------------------------------ TMA probe
+
+def _swizzle(tile, kc):
+    """[128, kc] row-major bytes -> the raw shared-memory image TMA writes (16-byte chunk XOR)."""
+    rows, chunks = tile.shape[0], kc // 16
+    t = tile.reshape(rows, chunks, 16)
+    out = np.empty_like(t)
+    for r in range(rows):
+        x = (r % 8) if kc == 128 else ((r // 2) % 4)
+        for j in range(chunks):
+            out[r, j ^ x] = t[r, j]
+    return out.reshape(rows, kc)
+
+
+def _expected_im2col(x, ksize, stride, pad, kc, m0, tx, ty, c0):
+    n, h, w, cp = x.shape
+    ho, wo = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
+    tile = np.zeros((128, kc), np.uint8)
+    for r in range(128):
+        m = m0 + r
+        if m >= n * ho * wo:
+            continue
+        img, rem = divmod(m, ho * wo)
+        oy, ox = divmod(rem, wo)
+        iy, ix = oy * stride - pad + ty, ox * stride - pad + tx
+        if 0 <= iy < h and 0 <= ix < w:
+            seg = x[img, iy, ix, c0:c0 + kc]
+            tile[r, :len(seg)] = seg
+    return tile
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=2, h=56, w=56, cp=64, k=3, s=1, p=1, kc=64, m0=0, tx=0, ty=0, c0=0),
+    dict(n=2, h=56, w=56, cp=64, k=3, s=1, p=1, kc=64, m0=3072, tx=2, ty=2, c0=0),       # crosses an image boundary
+    dict(n=2, h=28, w=28, cp=128, k=3, s=1, p=1, kc=128, m0=128, tx=1, ty=0, c0=0),
+    dict(n=2, h=56, w=56, cp=64, k=3, s=2, p=1, kc=64, m0=640, tx=0, ty=1, c0=0),        # stride 2
+    dict(n=2, h=28, w=28, cp=128, k=1, s=2, p=0, kc=128, m0=256, tx=0, ty=0, c0=0),      # 1x1 downsample, ragged end
+    dict(n=3, h=7, w=7, cp=480, k=3, s=1, p=1, kc=128, m0=128, tx=2, ty=1, c0=384),      # partial channel chunk + past the last image
+])
+def test_tma_im2col_semantics(case):
+    from ievm_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    x = rng.integers(1, 255, size=(case["n"], case["h"], case["w"], case["cp"]), dtype=np.uint8)
+    xd = torch.from_numpy(x).cuda()
+    out = torch.zeros(128 * case["kc"], dtype=torch.uint8, device="cuda")
+    _lib.check(lib.ievm_probe_im2col(xd.data_ptr(), case["n"], case["h"], case["w"], case["cp"], case["k"], case["s"],
+                                     case["p"], case["kc"], case["m0"], case["tx"], case["ty"], case["c0"],
+                                     out.data_ptr()), "probe")
+    got = out.cpu().numpy().reshape(128, case["kc"])
+    exp = _expected_im2col(x, case["k"], case["s"], case["p"], case["kc"], case["m0"], case["tx"], case["ty"], case["c0"])
+    raw = _swizzle(exp, case["kc"])
+    if not np.array_equal(got, raw):
+        same_rows = np.array_equal(np.sort(got, axis=1), np.sort(raw, axis=1))
+        pytest.fail(f"im2col tile mismatch (rows match up to chunk order: {same_rows}); "
+                    f"first bad row {int(np.argmax((got != raw).any(axis=1)))}")
+
+
+# ------------------------------------------------------------------------------------------ INT8 parity
+
+@pytest.mark.parametrize("tag", ["w57", "w60", "w64"])
+def test_int8_logits_match_reference_golden(tag, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"int8_{tag}.npz"))
+    eng = _engine(WIDTHS[tag], max_batch=8)
+    x = mf.synthetic_images(int(g["n_images"])).cuda()
+    y = eng(x).cpu().numpy()
+    assert np.array_equal(y, g["logits"]), f"max |diff| = {np.abs(y - g['logits']).max()}"
+    eng.close()
+
+
+def test_int8_every_tensor_and_accumulator_bit_exact():
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    net = O.extract_qnet(gm)
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=4)
+    eng.set_option("keep_tensors", 1)
+    x = mf.synthetic_images(3, seed=21)
+    y = eng(x.cuda()).cpu().numpy()
+    yo = O.forward(net, x.numpy(), keep=True)
+    checked = 0
+    for tid, name in sorted(eng.net.tensor_names.items()):
+        if name in net.trace:
+            got = eng.read_tensor(tid)
+            assert np.array_equal(got, net.trace[name]), f"tensor {name}: {(got != net.trace[name]).mean():.3%} bytes differ"
+            checked += 1
+    assert checked == 22
+    for L in eng.net.layers[2:-1]:
+        if L.op == 0:
+            acc = eng.conv_accumulators(L.name, 3)
+            assert np.array_equal(acc, net.trace[L.name + ":acc"]), f"accumulators of {L.name} differ"
+    assert np.array_equal(y, yo)
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 13])
+def test_int8_ragged_batches(n):
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=16)
+    x = mf.synthetic_images(n, seed=30 + n)
+    y = eng(x.cuda()).cpu().numpy()
+    assert np.array_equal(y, O.forward(O.extract_qnet(gm), x.numpy()))
+    eng.close()
+
+
+def test_int8_tensor_core_equals_direct_conv_at_batch_64():
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=64)
+    x = mf.synthetic_images(64, seed=5).cuda()
+    y_tc = eng(x).clone()
+    eng.set_option("conv_impl", 1)
+    y_ref = eng(x)
+    assert torch.equal(y_tc, y_ref)
+    eng.close()
+
+
+def test_int8_host_path_graph_path_and_state_dict_path_agree():
+    import ievm_b200
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=8)
+    x = mf.synthetic_images(8, seed=9)
+    y_dev = eng(x.cuda()).cpu()
+    y_host = eng(x)                       # CPU tensor in -> H2D/D2H inside the C call
+    assert not y_host.is_cuda and torch.equal(y_dev, y_host)
+    eng.set_option("use_graph", 1)
+    xd = x.cuda()
+    y_g1 = eng(xd).cpu()
+    y_g2 = eng(xd).cpu()
+    assert torch.equal(y_dev, y_g1) and torch.equal(y_dev, y_g2)
+    eng2 = ievm_b200.B200QuantizedResNet.from_quantized_state_dict(gm.state_dict(), max_batch=8)
+    assert torch.equal(y_dev, eng2(x.cuda()).cpu())
+    # nn.Module protocol the reference's callers rely on (engines.py:19-20,41-47; utils.py:124)
+    assert eng.eval() is eng and next(eng.parameters()).dtype == torch.float32
+    assert set(eng.state_dict().keys()) == set(gm.state_dict().keys())
+    eng.close()
+    eng2.close()
+
+
+def test_int8_top1_agreement_4096_images_vs_cpu_fbgemm():
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    torch.backends.quantized.engine = "fbgemm"
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=256)
+    agree = total = exact = 0
+    for chunk in range(16):
+        x = mf.synthetic_images(256, seed=1000 + chunk)
+        with torch.no_grad():
+            ref = gm(x)
+        got = eng(x.cuda()).cpu()
+        exact += int(torch.equal(ref, got))
+        agree += int((torch.max(ref, 1)[1] == torch.max(got, 1)[1]).sum())    # lowest index on ties, both sides
+        total += 256
+    assert agree / total >= 0.999, f"top-1 agreement {agree}/{total}"
+    assert exact == 16, f"only {exact}/16 chunks had bit-identical logits"
+    eng.close()
+
+
+def test_batch_sharding_is_bitwise_invariant():
+    """Data-parallel property: logits of a batch do not depend on how it is split across ranks."""
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=32)
+    x = mf.synthetic_images(32, seed=77).cuda()
+    whole = eng(x).clone()
+    parts = torch.cat([eng(x[i:i + 8]).clone() for i in range(0, 32, 8)])
+    assert torch.equal(whole, parts)
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------ FP16 parity
+
+def test_fp16_student_matches_reference_half_path(golden_dir):
+    import ievm_b200
+    g = np.load(os.path.join(golden_dir, "fp16_w57.npz"))
+    m16 = mf.cast_fp16(mf.make_student(mf.PRUNED_WIDTHS))
+    eng = ievm_b200.B200HalfResNet.from_half_module(m16, max_batch=8)
+    x = mf.synthetic_images(int(g["n_images"])).half()
+    y = eng(x.cuda()).float().cpu().numpy()
+    assert _row_rel(y, g["logits_fp16"]) < FP16_REL_TOL      # reference .half() on CPU (fixture)
+    assert _row_rel(y, g["logits_fp32"]) < FP16_REL_TOL
+    with torch.no_grad():                                      # reference .half() on this GPU (cuDNN)
+        y_cudnn = m16.cuda()(x.cuda()).float().cpu().numpy()
+    assert _row_rel(y, y_cudnn) < FP16_REL_TOL
+    assert (y.argmax(1) == y_cudnn.argmax(1)).all()
+    assert next(eng.parameters()).dtype == torch.float16
+    eng.set_option("conv_impl", 1)
+    y_direct = eng(x.cuda()).float().cpu().numpy()
+    assert _row_rel(y, y_direct) < 2e-3
+    eng.close()
+
+
+def test_fp16_teacher_resnet50_matches_reference_half_path(golden_dir):
+    import ievm_b200
+    g = np.load(os.path.join(golden_dir, "fp16_teacher_r50.npz"))
+    m16 = mf.cast_fp16(mf.make_teacher())
+    eng = ievm_b200.B200HalfResNet.from_half_module(m16, max_batch=4)
+    x = mf.synthetic_images(int(g["n_images"])).half()
+    y = eng(x.cuda()).float().cpu().numpy()
+    assert _row_rel(y, g["logits_fp16"]) < FP16_REL_TOL
+    with torch.no_grad():
+        y_cudnn = m16.cuda()(x.cuda()).float().cpu().numpy()
+    assert _row_rel(y, y_cudnn) < FP16_REL_TOL
+    eng.close()
+
+
+def test_kd_eval_loss_matches_torch():
+    import ievm_b200
+    g = torch.Generator().manual_seed(3)
+    s = torch.randn(512, 6, generator=g) * 3
+    t = torch.randn(512, 6, generator=g) * 3
+    y = torch.randint(0, 6, (512,), generator=g)
+    out = ievm_b200.kd_eval_loss(s.cuda(), t.cuda(), y.cuda(), alpha=0.5, temperature=4.0).cpu()
+    T = 4.0   # knowledge_distillation/train.py:47-57
+    ce = torch.nn.functional.cross_entropy(s, y)
+    kd = torch.nn.KLDivLoss(reduction="batchmean")(torch.log_softmax(s / T, 1), torch.softmax(t / T, 1)) * T * T
+    assert abs(out[1] - ce) < 1e-4 and abs(out[2] - kd) < 1e-4
+    assert abs(out[0] - (0.5 * ce + 0.5 * kd)) < 1e-4
+    assert int(out[3]) == int((s.argmax(1) == y).sum())

@@ -1,0 +1,121 @@
+"""CPU tier: host-side logic, the C-ABI surface, and the sharding helpers (gloo, world size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import ievm_b200
+from ievm_b200 import _lib
+from oracle import model_factory as mf
+from ievm_testutil import ROOT, cached_quantized
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = _lib.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "ievm.h")).read()
+    declared = set(re.findall(r"\b(ievm_[a-z0-9_]+)\s*\(", header))
+    assert declared >= {"ievm_create", "ievm_forward_i8", "ievm_forward_f16", "ievm_destroy", "ievm_last_error"}
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ievm.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    info = _lib.load().ievm_build_info().decode()
+    assert "sm_100a" in info
+
+
+def test_sass_contains_blackwell_instructions():
+    out = subprocess.run(["cuobjdump", "-sass", _lib.build()], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCIMMA", "UTCHMMA", "UTMALDG.4D.IM2COL", "LDTM"):
+        assert mnemonic in out, f"{mnemonic} missing from SASS"
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    net = ievm_b200.from_converted(cached_quantized(mf.PRUNED_WIDTHS))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ievm_b200.B200QuantizedResNet(net)
+    # and the C entry point itself refuses rather than degrading
+    from ievm_b200.engine import _marshal
+    nd, keep = _marshal(net)
+    h = ctypes.c_void_p()
+    rc = _lib.load().ievm_create(ctypes.byref(nd), 0, 8, ctypes.byref(h))
+    assert rc == -3 and not h.value
+    assert b"no CPU fallback" in _lib.load().ievm_last_error()
+
+
+def test_flatten_converted_and_state_dict_agree():
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    a = ievm_b200.from_converted(gm)
+    b = ievm_b200.from_quantized_state_dict(gm.state_dict())
+    assert a.tensor_names == b.tensor_names and len(a.layers) == len(b.layers) == 22
+    for la, lb in zip(a.layers, b.layers):
+        for f in la.__dataclass_fields__:
+            va, vb = getattr(la, f), getattr(lb, f)
+            if isinstance(va, np.ndarray):
+                assert np.array_equal(va, vb), (la.name, f)
+            else:
+                assert va == vb, (la.name, f)
+    assert a.conv_macs_per_image() == 1466823640          # 1.4668 GMAC
+    assert [L.cout for L in a.layers if L.op == 0][:2] == [57, 57]
+    # every tensor-core layer's input zero point is 0 (TMA zero fill == real zero)
+    assert all(L.in_zp == 0 for L in a.layers[1:] if L.op == 0)
+
+
+def test_flatten_half_modules():
+    s = ievm_b200.from_half_module(mf.cast_fp16(mf.make_student()))
+    assert len(s.layers) == 22 and s.conv_macs_per_image() == 1466823640
+    t = ievm_b200.from_half_module(mf.cast_fp16(mf.make_teacher()))
+    assert sum(L.op == 0 for L in t.layers) == 53 and t.conv_macs_per_image() == 4087148544
+    # BN folding is exact algebra: conv(x, w') + b' == bn(conv(x, w)) in fp32
+    m = mf.make_student((16, 24, 32, 40))
+    spec = ievm_b200.from_half_module(m)       # fp32 module: fold in fp32, weights rounded to fp16
+    x = torch.randn(2, 3, 32, 32)
+    ref = torch.relu(m.bn1(m.conv1(x)))
+    got = torch.relu(torch.nn.functional.conv2d(x, torch.from_numpy(spec.layers[0].weight).float(), None, 2, 3)
+                     + torch.from_numpy(spec.layers[0].bias).view(1, -1, 1, 1))
+    assert torch.allclose(ref, got, atol=5e-3)
+
+
+def test_unsupported_graphs_fail_loudly():
+    net = ievm_b200.from_converted(cached_quantized(mf.PRUNED_WIDTHS))
+    import copy
+    bad = copy.deepcopy(net)
+    bad.layers[2].in_tensor = 17            # consumes a tensor produced later
+    from ievm_b200.netdesc import _check_order
+    with pytest.raises(ValueError):
+        _check_order(bad)
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import bench
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+lo, hi = bench.shard_bounds(10, rank, 2)
+full = torch.arange(60, dtype=torch.float32).view(10, 6)
+gathered = bench.gather_logits(full[lo:hi], 10, rank, 2)
+ms = bench.max_over_ranks(float(rank + 1), torch.device("cpu"))
+if rank == 0:
+    assert torch.equal(gathered, full), gathered
+assert ms == 2.0
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_sharding_helpers_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 1000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
