@@ -137,6 +137,13 @@ int ievm_debug_conv_acc(ievm_handle* h, int layer, int n, int32_t* host_out, uin
 int ievm_probe_im2col(const void* in_dev, int n, int h, int w, int c_pitch, int ksize, int stride, int pad,
                       int kc_bytes, int m0, int tap_x, int tap_y, int c0, void* out_dev);
 
+/* Diagnostic: ONE tiled 4-D TMA box {rb bytes of C, box_w pixels, box_h rows, 1 image} of a u8 NHWC
+ * tensor starting at pixel (w0, h0) of image `img` (negative / past-the-end coordinates are zero
+ * filled), dumped raw (swizzled) from shared memory: box_w*box_h*rb bytes.  Pins the layout the
+ * halo-patch convolution mode relies on. */
+int ievm_probe_patch(const void* in_dev, int n, int h, int w, int c_pitch, int rb, int img, int w0, int h0, int box_w,
+                     int box_h, void* out_dev);
+
 /* Soft-target KD evaluation loss over device logits (f32 [n][classes]) and labels (int64 [n]).
  * out3 (device, f32[3]) receives {mean CE, mean T^2*KL (batchmean), number correct};
  * total loss = (1 - alpha) * CE + alpha * KL. */

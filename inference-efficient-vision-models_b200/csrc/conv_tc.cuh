@@ -6,15 +6,17 @@
 //   are gathered straight from the NHWC activation tensor by TMA in im2col mode; spatial padding and
 //   the ragged last tile are zero-filled by the TMA unit (zero == the real value 0 because every
 //   tensor-core layer's input zero-point is 0, checked at engine creation).
-// * W tiles come from a pre-packed K-major [cout_pad][taps * cin_chunks * kc] matrix by tiled TMA.
+// * W tiles come from a pre-packed K-major [cout_pad][taps * cin_chunks * kc] matrix by tiled TMA;
+//   when the whole matrix fits in shared memory it is loaded once per CTA and stays resident.
 // * Both land in shared memory in the 64B/128B-swizzled K-major layout tcgen05.mma reads directly.
 // * Accumulators (int32 for kind::i8, fp32 for kind::f16) live in TMEM, double buffered so that the
-//   epilogue of tile i overlaps the MMAs of tile i+1; the kernel is persistent (grid = #SMs).
+//   epilogue of tile i overlaps the MMAs of tile i+1; the kernel is persistent (grid <= #SMs).
 // * The epilogue is fused: INT8 requantisation (+ReLU clamp) and, for a block's last conv, the whole
 //   quantized::add_relu with the residual; FP16 bias (+residual) (+ReLU).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4; the two warps of a quadrant interleave
+// 16-column chunks).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -23,10 +25,19 @@
 namespace ievm {
 
 constexpr int kTileM = 128;
-constexpr int kConvThreads = 192;
-constexpr int kMaxStages = 12;
+constexpr int kEpiWarps = 8;
+constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 
 enum : int { kDtypeI8 = 0, kDtypeF16 = 1 };
+// A-operand feeding modes.
+//  kModeIm2col: one im2col TMA per (filter tap, channel chunk) -- any 1x1/3x3, stride 1|2.
+//  kModeHalo  : 3x3 stride-1 pad-1 convs whose pixel fits one smem row (<= 128 B): the tile is 128
+//               consecutive positions of the image's halo-extended row-major space (rows of W+2), ONE tiled
+//               TMA box brings the (rows+2) x (W+2) input patch with zero-filled borders, and the nine
+//               taps are nine row-shifted views of that patch (descriptor start + (ky*(W+2)+kx) rows).
+//               Cuts shared-memory fill traffic ~4.5x versus per-tap loads; the W+2-W junk columns are
+//               computed and discarded.
+enum : int { kModeIm2col = 0, kModeHalo = 1 };
 
 struct ConvTcParams {
   // implicit-GEMM geometry
@@ -39,8 +50,15 @@ struct ConvTcParams {
   int bn;              // UMMA N (multiple of 16, <= 256)
   int n_tiles, m_tiles;
   int stages;
+  int resident_b;      // 1: all weight k-blocks stay in shared memory (n_tiles == 1)
+  int a_stage_bytes;   // distance between A stages in shared memory
+  int a_tx_bytes;      // bytes one A-operand TMA delivers
+  // halo mode
+  int h_in, w_in, wp;  // input height / width, wp = w_in + 2
+  int tiles_per_img;
   int tmem_cols;       // power of two >= 32 covering two accumulator buffers
   int acc_stride;      // column offset of the second accumulator buffer
+  int cout_pad;        // n_tiles * bn
   uint32_t idesc;
   // epilogue
   void* out;
@@ -77,6 +95,7 @@ __device__ __forceinline__ void wait_or_die(uint64_t* bar, uint32_t parity, uint
 }
 
 // ---- INT8 epilogue arithmetic: float32, no FMA contraction, round-half-even (== fbgemm/ATen) ----
+// Scalar forms (used by the CUDA-core kernels and as the definition the fast forms must equal).
 __device__ __forceinline__ int requant_i8(int acc, float bdiv, float mult, int zp, int lo) {
   const float v = __fmul_rn(__fadd_rn(__int2float_rn(acc), bdiv), mult);
   const int q = __float2int_rn(v) + zp;
@@ -91,7 +110,153 @@ __device__ __forceinline__ int add_relu_i8(int aq, int a_zp, float a_scale, int 
   return min(max(q, 0), 255);
 }
 
-template <int kDtype>
+// (sat_u8(a) << 8 | sat_u8(b)) | c << 16 : two saturating int32 -> u8 conversions per instruction.
+__device__ __forceinline__ uint32_t pack_sat_u8(int a_hi, int b_lo, uint32_t c_upper) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_hi), "r"(b_lo), "r"(c_upper));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack4_sat_u8(int q0, int q1, int q2, int q3) {
+  return pack_sat_u8(q1, q0, pack_sat_u8(q3, q2, 0u));
+}
+
+constexpr float kRoundMagic = 12582912.0f;   // 1.5 * 2^23: (x + M) - M == rint(x) for |x| < 2^22
+
+// Per-thread constants of the fused add_relu epilogue.
+struct AddReluConst {
+  float lo_f, hi_f;        // clamp of the conv's own requantised value, relative to its zero point
+  float a_scale, r_scale, inv_scale;
+  float r_bias;            // kRoundMagic + res_zp: subtracting it turns (magic | byte) into (byte - res_zp)
+  int add_zp;
+};
+
+// 16 accumulators -> 16 requantised bytes (no residual).
+__device__ __forceinline__ uint4 epilogue16_i8(const uint32_t (&v)[16], const float* s_bd, const float* s_mu, int zp,
+                                               int lo) {
+  int q[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bd + 4 * j);
+    const float4 m4 = *reinterpret_cast<const float4*>(s_mu + 4 * j);
+    q[4 * j + 0] = __float2int_rn(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 0])), b4.x), m4.x)) + zp;
+    q[4 * j + 1] = __float2int_rn(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 1])), b4.y), m4.y)) + zp;
+    q[4 * j + 2] = __float2int_rn(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 2])), b4.z), m4.z)) + zp;
+    q[4 * j + 3] = __float2int_rn(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 3])), b4.w), m4.w)) + zp;
+  }
+  if (lo > 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q[i] = max(q[i], lo);
+  }
+  return make_uint4(pack4_sat_u8(q[0], q[1], q[2], q[3]), pack4_sat_u8(q[4], q[5], q[6], q[7]),
+                    pack4_sat_u8(q[8], q[9], q[10], q[11]), pack4_sat_u8(q[12], q[13], q[14], q[15]));
+}
+
+// 16 accumulators + 16 residual bytes -> 16 bytes of quantized::add_relu(requant(acc), residual).
+// All float steps reproduce the scalar definition exactly: clamping before rounding commutes with
+// RNE because the clamp bounds are integers, and (x + M) - M is RNE for |x| <= 256.
+__device__ __forceinline__ uint4 epilogue16_i8_res(const uint32_t (&v)[16], const uint4 r4, const float* s_bd,
+                                                   const float* s_mu, const AddReluConst& k) {
+  const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+  int q[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bd + 4 * j);
+    const float4 m4 = *reinterpret_cast<const float4*>(s_mu + 4 * j);
+    const float bd[4] = {b4.x, b4.y, b4.z, b4.w};
+    const float mu[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = 4 * j + b;
+      float t = __fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[i])), bd[b]), mu[b]);
+      t = fminf(fmaxf(t, k.lo_f), k.hi_f);
+      t = __fadd_rn(__fadd_rn(t, kRoundMagic), -kRoundMagic);          // == float(q2 - zp2)
+      const float a = __fmul_rn(t, k.a_scale);
+      const float rb = __fadd_rn(__uint_as_float(__byte_perm(rw[j], 0x4B400000u, 0x7650 + b)), -k.r_bias);
+      const float s = fmaxf(__fadd_rn(a, __fmul_rn(rb, k.r_scale)), 0.0f);
+      q[i] = __float2int_rn(__fmul_rn(s, k.inv_scale)) + k.add_zp;
+    }
+  }
+  return make_uint4(pack4_sat_u8(q[0], q[1], q[2], q[3]), pack4_sat_u8(q[4], q[5], q[6], q[7]),
+                    pack4_sat_u8(q[8], q[9], q[10], q[11]), pack4_sat_u8(q[12], q[13], q[14], q[15]));
+}
+
+template <bool kHasRes, bool kRelu>
+__device__ __forceinline__ void epilogue16_f16(const uint32_t (&v)[16], const float* s_bias, const __half* rp,
+                                               __half* op, bool valid) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 4 * j);
+    f[4 * j] = __uint_as_float(v[4 * j]) + b4.x;
+    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+  }
+  if (kHasRes && valid) {
+    const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
+    const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
+    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&rw[j]));
+      f[2 * j] += r2.x;
+      f[2 * j + 1] += r2.y;
+    }
+  }
+  uint32_t hw2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x = f[2 * j], y = f[2 * j + 1];
+    if (kRelu) {
+      x = fmaxf(x, 0.0f);
+      y = fmaxf(y, 0.0f);
+    }
+    const __half2 h = __floats2half2_rn(x, y);
+    hw2[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  if (valid) {
+    *reinterpret_cast<uint4*>(op) = make_uint4(hw2[0], hw2[1], hw2[2], hw2[3]);
+    *reinterpret_cast<uint4*>(op + 8) = make_uint4(hw2[4], hw2[5], hw2[6], hw2[7]);
+  }
+}
+
+// One 16-column chunk of the epilogue for pixel row `m`.
+// Residual bytes for one 16-channel chunk of pixel row m (INT8), fetched ahead of the TMEM load so
+// that the L2 latency is hidden behind the wait for the accumulator.
+__device__ __forceinline__ uint4 load_res16_i8(const ConvTcParams& p, int m, bool valid, int ch) {
+  if (!valid) return make_uint4(0u, 0u, 0u, 0u);
+  return __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch));
+}
+
+template <int kDtype, bool kHasRes>
+__device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint32_t (&v)[16], const uint4 r4, int m,
+                                               bool valid, int ch, const float* s_ep0, const float* s_ep1,
+                                               const AddReluConst& k) {
+  if (valid && p.dump_acc != nullptr) {
+    int4* d = reinterpret_cast<int4*>(p.dump_acc + static_cast<size_t>(m) * p.dump_pitch + ch);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      d[j] = make_int4(static_cast<int>(v[4 * j]), static_cast<int>(v[4 * j + 1]), static_cast<int>(v[4 * j + 2]),
+                       static_cast<int>(v[4 * j + 3]));
+  }
+  if (kDtype == kDtypeI8) {
+    uint8_t* op = static_cast<uint8_t*>(p.out) + static_cast<size_t>(m) * p.out_pitch + ch;
+    uint4 o;
+    if (kHasRes) {
+      o = epilogue16_i8_res(v, r4, s_ep0 + ch, s_ep1 + ch, k);
+    } else {
+      o = epilogue16_i8(v, s_ep0 + ch, s_ep1 + ch, p.out_zp, p.out_lo);
+    }
+    if (valid) *reinterpret_cast<uint4*>(op) = o;
+  } else {
+    __half* op = static_cast<__half*>(p.out) + static_cast<size_t>(m) * p.out_pitch + ch;
+    const __half* rp = static_cast<const __half*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch;
+    if (p.relu) epilogue16_f16<kHasRes, true>(v, s_ep0 + ch, rp, op, valid);
+    else epilogue16_f16<kHasRes, false>(v, s_ep0 + ch, rp, op, valid);
+  }
+}
+
+template <int kDtype, bool kHasRes, int kMode>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const ConvTcParams p) {
@@ -100,19 +265,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  const int a_bytes = kTileM * p.kc_bytes;
+  const int num_kb = p.ksize * p.ksize * p.kchunks;
+  const int a_bytes = p.a_stage_bytes;
   const int b_bytes = p.bn * p.kc_bytes;
+  const int b_slots = p.resident_b ? num_kb : p.stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * a_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + p.stages * b_bytes);
+  float* s_ep0 = reinterpret_cast<float*>(sB + b_slots * b_bytes);
+  float* s_ep1 = s_ep0 + p.cout_pad;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ep1 + p.cout_pad);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bres_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;       // warp-uniform
   const int lane = threadIdx.x & 31;
 
+  for (int i = threadIdx.x; i < p.cout_pad; i += kConvThreads) {
+    s_ep0[i] = p.ep0[i];
+    s_ep1[i] = p.ep1[i];
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -122,8 +296,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);        // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], kEpiWarps);   // one arrival per epilogue warp
     }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -136,15 +311,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int num_kb = p.ksize * p.ksize * p.kchunks;
   const int hw = p.ho * p.wo;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
+      if (p.resident_b) {
+        mbar_expect_tx(bres_bar, static_cast<uint32_t>(num_kb * b_bytes));
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sB + kb * b_bytes, &tmap_b, bres_bar, kb * p.kc_elems, 0);
+      }
+      const uint32_t tx_bytes = static_cast<uint32_t>(p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (kMode == kModeHalo) {
+          const int img = tile / p.tiles_per_img;
+          const int p0 = (tile - img * p.tiles_per_img) * kTileM;
+          const int oy_first = p0 / p.wp;
+          wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], 0, -1, oy_first - 1, img);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          continue;
+        }
         const int m_tile = tile / p.n_tiles;
         const int n_tile = tile - m_tile * p.n_tiles;
         const int m0 = m_tile * kTileM;
@@ -159,10 +351,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int tx = 0; tx < p.ksize; ++tx) {
             for (int ch = 0; ch < p.kchunks; ++ch, ++kb) {
               wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
-              mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(a_bytes + b_bytes));
+              mbar_expect_tx(&full_bar[stage], tx_bytes);
               tma_load_im2col_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h,
                                  img, static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
-              tma_load_2d(sB + stage * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems, n_tile * p.bn);
+              if (!p.resident_b)
+                tma_load_2d(sB + stage * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems, n_tile * p.bn);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -178,31 +371,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int ksteps = p.kc_bytes / 32;      // one tcgen05.mma consumes 32 bytes of K per row
+    // One tcgen05.mma consumes 32 bytes of K per row: 2 (64-byte rows) or 4 (128-byte rows) per k-block.
+    // Everything the issuing thread needs per instruction is reduced to one add on a precomputed
+    // descriptor low word: with N = 64 an MMA occupies the tensor pipe for only ~32 cycles, so the
+    // single-thread issue loop is the critical path.
+    const bool wide = p.kc_bytes == 128;
+    const uint32_t hi = smem_desc_hi(static_cast<uint32_t>(p.kc_bytes));
+    const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA));
+    const uint32_t b_lo0 = smem_desc_lo(smem_u32(sB));
+    const uint32_t a_step = static_cast<uint32_t>(a_bytes) >> 4;
+    const uint32_t b_step = static_cast<uint32_t>(b_bytes) >> 4;
+    const uint32_t row16 = static_cast<uint32_t>(p.kc_bytes) >> 4;      // one pixel row in 16-byte units
+    const uint32_t idesc = p.idesc;
+    auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t accum) {
+      if (kDtype == kDtypeI8) umma_i8_lohi(d, a_lo, b_lo, hi, idesc, accum);
+      else umma_f16_lohi(d, a_lo, b_lo, hi, idesc, accum);
+    };
+    auto mma_kblock = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t first_accum) {
+      mma(d, a_lo, b_lo, first_accum);
+      mma(d, a_lo + 2, b_lo + 2, 1u);
+      if (wide) {
+        mma(d, a_lo + 4, b_lo + 4, 1u);
+        mma(d, a_lo + 6, b_lo + 6, 1u);
+      }
+    };
+    uint32_t tap_off[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>((tap / 3) * p.wp + (tap % 3)) * row16;
+    if (p.resident_b) wait_or_die(bres_bar, 0, 0x500u, p.stuck_flag);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       wait_or_die(&tempty_bar[acc], acc_phase ^ 1u, 0x200u | acc, p.stuck_flag);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      if (kMode == kModeHalo) {
+        const int p0 = (tile % p.tiles_per_img) * kTileM;
+        const int x0 = p0 - (p0 / p.wp) * p.wp;
         wait_or_die(&full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_addr = smem_u32(sA + stage * a_bytes);
-          const uint32_t b_addr = smem_u32(sB + stage * b_bytes);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = make_smem_desc(a_addr + k * 32, p.kc_bytes);
-            const uint64_t bdesc = make_smem_desc(b_addr + k * 32, p.kc_bytes);
-            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
-            if (kDtype == kDtypeI8) umma_i8(d_tmem, adesc, bdesc, p.idesc, accum);
-            else umma_f16(d_tmem, adesc, bdesc, p.idesc, accum);
-          }
-          umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+          const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step + static_cast<uint32_t>(x0) * row16;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap)
+            mma_kblock(d_tmem, a_lo + tap_off[tap], b_lo0 + static_cast<uint32_t>(tap) * b_step, tap != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
+        }
+      } else {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          wait_or_die(&full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step;
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(p.resident_b ? kb : stage) * b_step;
+            mma_kblock(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
       acc ^= 1;
@@ -211,106 +445,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ================================ epilogue ================================
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;        // 0 or 1: which of the quadrant's two warps
     const int row = quad * 32 + lane;
+    const int nchunks = p.bn >> 4;
+    AddReluConst k;
+    k.lo_f = static_cast<float>(p.out_lo - p.out_zp);
+    k.hi_f = static_cast<float>(255 - p.out_zp);
+    k.a_scale = p.a_scale;
+    k.r_scale = p.res_scale;
+    k.inv_scale = p.inv_add_scale;
+    k.r_bias = kRoundMagic + static_cast<float>(p.res_zp);
+    k.add_zp = p.add_zp;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles;
-      const int n_tile = tile - m_tile * p.n_tiles;
-      const int m = m_tile * kTileM + row;
-      const bool valid = m < p.m_total;
-      const int n0 = n_tile * p.bn;
+      int m, n0;
+      bool valid;
+      if (kMode == kModeHalo) {
+        const int img = tile / p.tiles_per_img;
+        const int pos = (tile - img * p.tiles_per_img) * kTileM + row;
+        const int oy = pos / p.wp;
+        const int x = pos - oy * p.wp;
+        valid = x < p.w_in && oy < p.h_in;
+        m = (img * p.h_in + oy) * p.w_in + x;
+        n0 = 0;
+      } else {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        m = m_tile * kTileM + row;
+        valid = m < p.m_total;
+        n0 = n_tile * p.bn;
+      }
+      constexpr bool kResI8 = kHasRes && kDtype == kDtypeI8;
+      uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
+      int c = half;
+      if (kResI8 && c < nchunks) ra = load_res16_i8(p, m, valid, n0 + c * 16);   // does not depend on the MMA
       wait_or_die(&tfull_bar[acc], acc_phase, 0x400u | acc, p.stuck_flag);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * p.acc_stride);
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c0), v);
+      // two register buffers: the TMEM load (and residual fetch) of the next chunk is in flight while this
+      // one is processed
+      uint32_t va[16], vb[16];
+      if (c < nchunks) tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), va);
+      while (c < nchunks) {
         tmem_ld_wait();
-        const int ch = n0 + c0;
-        if (valid && p.dump_acc != nullptr) {
-          int4* d = reinterpret_cast<int4*>(p.dump_acc + static_cast<size_t>(m) * p.dump_pitch + ch);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            d[j] = make_int4(static_cast<int>(v[4 * j]), static_cast<int>(v[4 * j + 1]),
-                             static_cast<int>(v[4 * j + 2]), static_cast<int>(v[4 * j + 3]));
+        if (c + 2 < nchunks) {
+          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 2) * 16), vb);
+          if (kResI8) rb = load_res16_i8(p, m, valid, n0 + (c + 2) * 16);
         }
-        if (kDtype == kDtypeI8) {
-          float bd[16], mu[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ep0 + ch) + j);
-            const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.ep1 + ch) + j);
-            bd[4 * j] = b4.x; bd[4 * j + 1] = b4.y; bd[4 * j + 2] = b4.z; bd[4 * j + 3] = b4.w;
-            mu[4 * j] = m4.x; mu[4 * j + 1] = m4.y; mu[4 * j + 2] = m4.z; mu[4 * j + 3] = m4.w;
-          }
-          uint32_t rq[4] = {0u, 0u, 0u, 0u};
-          const bool has_res = p.res != nullptr;
-          if (has_res && valid) {
-            const uint4 r4 = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.res) +
-                                                             static_cast<size_t>(m) * p.res_pitch + ch);
-            rq[0] = r4.x; rq[1] = r4.y; rq[2] = r4.z; rq[3] = r4.w;
-          }
-          uint32_t packed[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int i = 4 * j + b;
-              int q = requant_i8(static_cast<int>(v[i]), bd[i], mu[i], p.out_zp, p.out_lo);
-              if (has_res) {
-                const int r = static_cast<int>((rq[j] >> (8 * b)) & 0xffu);
-                q = add_relu_i8(q, p.out_zp, p.a_scale, r, p.res_zp, p.res_scale, p.inv_add_scale, p.add_zp);
-              }
-              w |= static_cast<uint32_t>(q) << (8 * b);
-            }
-            packed[j] = w;
-          }
-          if (valid) {
-            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.out) + static_cast<size_t>(m) * p.out_pitch + ch) =
-                make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          }
-        } else {
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ep0 + ch) + j);
-            f[4 * j] = __uint_as_float(v[4 * j]) + b4.x;
-            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-          }
-          if (p.res != nullptr && valid) {
-            const __half* rp = static_cast<const __half*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch;
-            const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
-            const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
-            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&rw[j]));
-              f[2 * j] += r2.x;
-              f[2 * j + 1] += r2.y;
-            }
-          }
-          uint32_t hw2[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float x = f[2 * j], y = f[2 * j + 1];
-            if (p.relu) {
-              x = fmaxf(x, 0.0f);
-              y = fmaxf(y, 0.0f);
-            }
-            const __half2 h = __floats2half2_rn(x, y);
-            hw2[j] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-          if (valid) {
-            __half* op = static_cast<__half*>(p.out) + static_cast<size_t>(m) * p.out_pitch + ch;
-            *reinterpret_cast<uint4*>(op) = make_uint4(hw2[0], hw2[1], hw2[2], hw2[3]);
-            *reinterpret_cast<uint4*>(op + 8) = make_uint4(hw2[4], hw2[5], hw2[6], hw2[7]);
-          }
+        epilogue_chunk<kDtype, kHasRes>(p, va, ra, m, valid, n0 + c * 16, s_ep0, s_ep1, k);
+        c += 2;
+        if (c >= nchunks) break;
+        tmem_ld_wait();
+        if (c + 2 < nchunks) {
+          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 2) * 16), va);
+          if (kResI8) ra = load_res16_i8(p, m, valid, n0 + (c + 2) * 16);
         }
+        epilogue_chunk<kDtype, kHasRes>(p, vb, rb, m, valid, n0 + c * 16, s_ep0, s_ep1, k);
+        c += 2;
       }
       tc_fence_before();
       __syncwarp();

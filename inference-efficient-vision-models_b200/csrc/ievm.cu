@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -17,6 +18,7 @@
 
 #include "conv_tc.cuh"
 #include "simt_kernels.cuh"
+#include "stem_tc.cuh"
 
 namespace {
 
@@ -87,12 +89,17 @@ struct LayerPlan {
   int cin_pitch = 0, cout_pad = 0;
   int bn = 0, n_tiles = 0;
   int kc_bytes = 0, kc_elems = 0, kchunks = 0, cin_w = 0;
-  int stages = 0, tmem_cols = 0;
+  int stages = 0, tmem_cols = 0, resident_b = 0;
+  int mode = 0;                 // kModeIm2col | kModeHalo
+  int wp = 0, patch_rows = 0, tiles_per_img = 0, a_stage_bytes = 0, a_tx_bytes = 0;
   size_t smem_bytes = 0;
   // device operands
   void* w_packed = nullptr;     // tensor-core layout [cout_pad][taps][cin_w]
-  void* w_stem = nullptr;       // stem layout
+  void* w_stem = nullptr;       // stem layout (CUDA-core kernels)
+  void* w_stem_tc = nullptr;    // stem layout for the tensor-core kernel: [cout_pad][8 segments x 32 B]
   int* wsum = nullptr;
+  int* zwsum = nullptr;         // in_zp * wsum
+  size_t stem_smem = 0;
   float* ep0 = nullptr;
   float* ep1 = nullptr;
   CUtensorMap tmap_a, tmap_b;
@@ -106,6 +113,10 @@ struct ievm_handle {
   int elem = 1;
   int max_batch = 0;
   int num_sms = 0;
+  int smem_optin = 0;
+  int opt_halo = 1;        // IEVM_HALO=0 disables the halo-patch mode (all convs use per-tap im2col TMA)
+  int opt_halo_rb128 = 0;
+  // IEVM_HALO_RB128=1: 64-byte pixels use 128-byte shared-memory rows in halo mode
   int in_c = 0, in_h = 0, in_w = 0, classes = 0;
   float in_scale = 1.f;
   int in_zp = 0;
@@ -227,16 +238,52 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
         return fail(IEVM_ERR_BAD_ARG, "layer %d: residual shape mismatch", i);
     }
     const int row_bytes = L.cin_pitch * h->elem;
+    constexpr int kMaxStages = 16;
+    const int fixed = 1024 /*alignment slack*/ + 2 * L.cout_pad * 4 + (2 * kMaxStages + 5) * 8 + 16;
+    const int avail = h->smem_optin - fixed;
+    L.tmem_cols = 32;
+    while (L.tmem_cols < 2 * L.bn) L.tmem_cols *= 2;
+    // ---- halo mode: 3x3 stride-1 convs whose pixel fits one shared-memory row, weights resident ----
+    if (h->opt_halo && d.ksize == 3 && d.stride == 1 && d.pad == 1 && L.n_tiles == 1 && row_bytes <= 128) {
+      const int rb = (row_bytes <= 64 && !h->opt_halo_rb128) ? 64 : 128;
+      const int wp = L.w + 2;
+      const int patch_rows = (wp + 126) / wp + 3;
+      const int a_tx = patch_rows * wp * rb;
+      const int a_stage = round_up(a_tx + wp * rb, 1024);
+      const int b_all = 9 * L.bn * rb;
+      if (b_all + 2 * a_stage <= avail && wp <= 256) {
+        L.mode = kModeHalo;
+        L.kc_bytes = rb;
+        L.kc_elems = rb / h->elem;
+        L.kchunks = 1;
+        L.cin_w = L.kc_elems;
+        L.wp = wp;
+        L.patch_rows = patch_rows;
+        L.a_tx_bytes = a_tx;
+        L.a_stage_bytes = a_stage;
+        L.tiles_per_img = (L.h * wp + kTileM - 1) / kTileM;
+        L.resident_b = 1;
+        L.stages = std::min(8, (avail - b_all) / a_stage);
+        L.smem_bytes = static_cast<size_t>(L.stages) * a_stage + b_all + fixed;
+        continue;
+      }
+    }
+    // ---- im2col mode ----
+    L.mode = kModeIm2col;
     L.kc_bytes = row_bytes <= 64 ? 64 : 128;
     L.kc_elems = L.kc_bytes / h->elem;
     L.kchunks = (d.cin * h->elem + L.kc_bytes - 1) / L.kc_bytes;
     L.cin_w = L.kchunks * L.kc_elems;
-    const int stage_bytes = kTileM * L.kc_bytes + L.bn * L.kc_bytes;
+    // shared-memory plan: [A stages][B stages | all B k-blocks][epilogue tables][barriers]
+    const int a_bytes = kTileM * L.kc_bytes, b_bytes = L.bn * L.kc_bytes;
     const int num_kb = d.ksize * d.ksize * L.kchunks;
-    L.stages = std::max(2, std::min(std::min(8, num_kb), (200 * 1024) / stage_bytes));
-    L.tmem_cols = 32;
-    while (L.tmem_cols < 2 * L.bn) L.tmem_cols *= 2;
-    L.smem_bytes = static_cast<size_t>(L.stages) * stage_bytes + (2 * L.stages + 4) * 8 + 16 + 1024;
+    L.a_stage_bytes = L.a_tx_bytes = a_bytes;
+    L.resident_b = (L.n_tiles == 1 && num_kb * b_bytes + 4 * a_bytes <= avail) ? 1 : 0;
+    if (L.resident_b) L.stages = std::min(kMaxStages, (avail - num_kb * b_bytes) / a_bytes);
+    else L.stages = std::min(kMaxStages, avail / (a_bytes + b_bytes));
+    if (L.stages < 2) return fail(IEVM_ERR_UNSUPPORTED, "layer %d: tile does not fit in shared memory", i);
+    L.smem_bytes = static_cast<size_t>(L.stages) * a_bytes +
+                   static_cast<size_t>(L.resident_b ? num_kb : L.stages) * b_bytes + fixed;
   }
   return IEVM_OK;
 }
@@ -279,6 +326,25 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
       if (int rc = dev_upload(h, w4, &dw)) return rc;
       L.w_stem = dw;
       if (int rc = dev_upload(h, wsum, &L.wsum)) return rc;
+      // tensor-core layout: K index = ky*32 + j*4 + c, window pixel j <-> kx = j - 1 (j = 0 is padding)
+      std::vector<int8_t> wt(static_cast<size_t>(L.cout_pad) * kStemKBytes, 0);
+      std::vector<int> zw(L.cout_pad, 0);
+      for (int co = 0; co < d.cout; ++co) {
+        for (int c = 0; c < 3; ++c)
+          for (int ky = 0; ky < 7; ++ky)
+            for (int kx = 0; kx < 7; ++kx)
+              wt[static_cast<size_t>(co) * kStemKBytes + ky * 32 + (kx + 1) * 4 + c] =
+                  w[(static_cast<size_t>(co) * 3 + c) * 49 + ky * 7 + kx];
+        zw[co] = h->in_zp * wsum[co];
+      }
+      int8_t* dwt = nullptr;
+      if (int rc = dev_upload(h, wt, &dwt)) return rc;
+      L.w_stem_tc = dwt;
+      if (int rc = dev_upload(h, zw, &L.zwsum)) return rc;
+      L.tmem_cols = 32;
+      while (L.tmem_cols < 2 * L.cout_pad) L.tmem_cols *= 2;
+      L.stem_smem = 1024 + static_cast<size_t>(kStemStages) * 2 * kTileM * 128 + 2 * static_cast<size_t>(L.cout_pad) * 128 +
+                    3 * static_cast<size_t>(L.cout_pad) * 4 + (2 * kStemStages + 5) * 8 + 16;
     } else {
       const uint16_t* w = static_cast<const uint16_t*>(d.weight);
       std::vector<uint16_t> ws(static_cast<size_t>(147) * L.cout_pad, 0);
@@ -414,9 +480,33 @@ int encode_maps(ievm_handle* h) {
   const CUtensorMapDataType dt = h->dtype == IEVM_DTYPE_I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   for (size_t i = 0; i < h->layers.size(); ++i) {
     LayerPlan& L = h->layers[i];
+    if (L.d.op == IEVM_OP_CONV && L.is_stem && h->dtype == IEVM_DTYPE_I8) {
+      cuuint64_t dims[2] = {static_cast<cuuint64_t>(kStemKBytes), static_cast<cuuint64_t>(L.cout_pad)};
+      cuuint64_t strides[1] = {static_cast<cuuint64_t>(kStemKBytes)};
+      cuuint32_t box[2] = {128, static_cast<cuuint32_t>(L.cout_pad)};
+      cuuint32_t estr[2] = {1, 1};
+      const CUresult r = g_encode_tiled(&L.tmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, L.w_stem_tc, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled failed for the stem: CUresult %d", (int)r);
+      continue;
+    }
     if (L.d.op != IEVM_OP_CONV || L.is_stem) continue;
     const CUtensorMapSwizzle sw = L.kc_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const size_t e = h->elem;
+    if (L.mode == kModeHalo) {
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cin_pitch), static_cast<cuuint64_t>(L.w),
+                            static_cast<cuuint64_t>(L.h), static_cast<cuuint64_t>(h->max_batch)};
+      cuuint64_t strides[3] = {L.cin_pitch * e, static_cast<cuuint64_t>(L.w) * L.cin_pitch * e,
+                               static_cast<cuuint64_t>(L.h) * L.w * L.cin_pitch * e};
+      cuuint32_t box[4] = {static_cast<cuuint32_t>(L.kc_elems), static_cast<cuuint32_t>(L.wp),
+                           static_cast<cuuint32_t>(L.patch_rows), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      const CUresult r = g_encode_tiled(&L.tmap_a, dt, 4, tensor_ptr(h, L.d.in_tensor), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled (halo patch) failed for layer %zu: CUresult %d", i, (int)r);
+    } else
     // activations as (C, W, H, N), im2col mode
     {
       cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cin_pitch), static_cast<cuuint64_t>(L.w),
@@ -466,8 +556,16 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   p.kc_elems = L.kc_elems;
   p.bn = L.bn;
   p.n_tiles = L.n_tiles;
-  p.m_tiles = (p.m_total + kTileM - 1) / kTileM;
+  p.m_tiles = L.mode == kModeHalo ? n * L.tiles_per_img : (p.m_total + kTileM - 1) / kTileM;
   p.stages = L.stages;
+  p.resident_b = L.resident_b;
+  p.a_stage_bytes = L.a_stage_bytes;
+  p.a_tx_bytes = L.a_tx_bytes;
+  p.h_in = L.h;
+  p.w_in = L.w;
+  p.wp = L.wp;
+  p.tiles_per_img = L.tiles_per_img;
+  p.cout_pad = L.cout_pad;
   p.tmem_cols = L.tmem_cols;
   p.acc_stride = L.tmem_cols / 2;
   p.idesc = h->dtype == IEVM_DTYPE_I8 ? make_idesc_i8_u8s8(L.bn) : make_idesc_f16(L.bn);
@@ -511,10 +609,41 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
     return IEVM_OK;
   }
   const int grid = std::min(p.m_tiles * p.n_tiles, h->num_sms);
-  if (h->dtype == IEVM_DTYPE_I8)
-    conv_tc_kernel<kDtypeI8><<<grid, kConvThreads, L.smem_bytes, s>>>(L.tmap_a, L.tmap_b, p);
-  else
-    conv_tc_kernel<kDtypeF16><<<grid, kConvThreads, L.smem_bytes, s>>>(L.tmap_a, L.tmap_b, p);
+  const bool has_res = p.res != nullptr;
+#define IEVM_LAUNCH(DT, RES, MODE) \
+  conv_tc_kernel<DT, RES, MODE><<<grid, kConvThreads, L.smem_bytes, s>>>(L.tmap_a, L.tmap_b, p)
+#define IEVM_LAUNCH_MODE(DT, RES) \
+  do { if (L.mode == kModeHalo) IEVM_LAUNCH(DT, RES, kModeHalo); else IEVM_LAUNCH(DT, RES, kModeIm2col); } while (0)
+  if (h->dtype == IEVM_DTYPE_I8) {
+    if (has_res) IEVM_LAUNCH_MODE(kDtypeI8, true); else IEVM_LAUNCH_MODE(kDtypeI8, false);
+  } else {
+    if (has_res) IEVM_LAUNCH_MODE(kDtypeF16, true); else IEVM_LAUNCH_MODE(kDtypeF16, false);
+  }
+#undef IEVM_LAUNCH_MODE
+#undef IEVM_LAUNCH
+  CUDA_TRY(cudaGetLastError());
+  return IEVM_OK;
+}
+
+int launch_stem_tc(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32_t* dump_acc) {
+  StemTcParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.n = n; sp.h = L.h; sp.w = L.w; sp.ho = L.ho; sp.wo = L.wo;
+  sp.m_total = n * L.ho * L.wo;
+  sp.m_tiles = (sp.m_total + kTileM - 1) / kTileM;
+  sp.cpad = L.cout_pad;
+  sp.in_zp = h->in_zp;
+  sp.tmem_cols = L.tmem_cols;
+  sp.acc_stride = L.tmem_cols / 2;
+  sp.idesc = make_idesc_i8_u8s8(L.cout_pad);
+  sp.xq = static_cast<const uint8_t*>(tensor_ptr(h, 0));
+  sp.out = static_cast<uint8_t*>(tensor_ptr(h, L.d.out_tensor));
+  sp.bdiv = L.ep0; sp.mult = L.ep1; sp.zwsum = L.zwsum;
+  sp.out_zp = L.d.out_zp; sp.out_lo = L.d.relu ? L.d.out_zp : 0;
+  sp.dump_acc = dump_acc;
+  sp.stuck_flag = h->stuck_dev;
+  const int grid = std::min(sp.m_tiles, h->num_sms);
+  stem_tc_kernel<<<grid, kStemThreads, L.stem_smem, s>>>(L.tmap_b, sp);
   CUDA_TRY(cudaGetLastError());
   return IEVM_OK;
 }
@@ -547,7 +676,9 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     if (prof && li > 0) CUDA_TRY(cudaEventRecord(h->prof_events[li + 1], s));
     if (d.op == IEVM_OP_CONV && L.is_stem) {
       const long long m_total = static_cast<long long>(n) * L.ho * L.wo;
-      if (i8) {
+      if (i8 && h->conv_impl == 0) {
+        if (int rc = launch_stem_tc(h, L, n, s, nullptr)) return rc;
+      } else if (i8) {
         StemParams sp;
         sp.n = n; sp.h = L.h; sp.w = L.w; sp.ho = L.ho; sp.wo = L.wo; sp.cpad = L.cout_pad; sp.in_zp = h->in_zp;
         sp.w4 = static_cast<const uint32_t*>(L.w_stem); sp.wsum = L.wsum; sp.bdiv = L.ep0; sp.mult = L.ep1;
@@ -670,6 +801,29 @@ __global__ void probe_im2col_kernel(const __grid_constant__ CUtensorMap tmap, in
   for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = smem[i];
 }
 
+// Diagnostic: one tiled 4D TMA box (halo patch), dumped raw from shared memory.
+__global__ void probe_patch_kernel(const __grid_constant__ CUtensorMap tmap, int c0, int w0, int h0, int n0, int bytes,
+                                   uint8_t* out, unsigned int* stuck) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + ((bytes + 15) & ~15));
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) smem[i] = 0xEE;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, static_cast<uint32_t>(bytes));
+    tma_load_4d(smem, &tmap, bar, c0, w0, h0, n0);
+  }
+  wait_or_die(bar, 0, 0x901u, stuck);
+  __syncthreads();
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = smem[i];
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -702,8 +856,11 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   h->elem = nd->dtype == IEVM_DTYPE_I8 ? 1 : 2;
   h->max_batch = max_batch;
   h->num_sms = prop.multiProcessorCount;
+  h->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
   h->in_c = nd->in_c; h->in_h = nd->in_h; h->in_w = nd->in_w; h->classes = nd->num_classes;
   h->in_scale = nd->in_scale; h->in_zp = nd->in_zp;
+  if (const char* e = getenv("IEVM_HALO")) h->opt_halo = atoi(e);
+  if (const char* e = getenv("IEVM_HALO_RB128")) h->opt_halo_rb128 = atoi(e);
   int rc = plan_shapes(h, nd);
   for (size_t i = 0; rc == IEVM_OK && i < h->layers.size(); ++i) {
     LayerPlan& L = h->layers[i];
@@ -719,10 +876,25 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
     for (const LayerPlan& L : h->layers) max_smem = std::max(max_smem, L.smem_bytes);
     if (max_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) rc = fail(IEVM_ERR_UNSUPPORTED, "smem plan exceeds device limit");
     if (rc == IEVM_OK && max_smem > 0) {
-      cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<kDtypeI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<kDtypeF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+      cudaError_t e = cudaSuccess;
+      const int ms = static_cast<int>(max_smem);
+#define IEVM_ATTR(DT, RES, MODE) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<DT, RES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms)
+      IEVM_ATTR(kDtypeI8, false, kModeIm2col); IEVM_ATTR(kDtypeI8, true, kModeIm2col);
+      IEVM_ATTR(kDtypeI8, false, kModeHalo);   IEVM_ATTR(kDtypeI8, true, kModeHalo);
+      IEVM_ATTR(kDtypeF16, false, kModeIm2col); IEVM_ATTR(kDtypeF16, true, kModeIm2col);
+      IEVM_ATTR(kDtypeF16, false, kModeHalo);   IEVM_ATTR(kDtypeF16, true, kModeHalo);
+#undef IEVM_ATTR
       if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
+  }
+  if (rc == IEVM_OK) {
+    for (const LayerPlan& L : h->layers)
+      if (L.stem_smem > 0) {
+        if (L.stem_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) rc = fail(IEVM_ERR_UNSUPPORTED, "stem smem plan exceeds device limit");
+        else if (cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.stem_smem) != cudaSuccess)
+          rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(stem_tc_kernel) failed");
+      }
   }
   if (rc == IEVM_OK) {
     cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h->stuck_host), sizeof(unsigned int), cudaHostAllocMapped);
@@ -861,14 +1033,15 @@ int ievm_debug_read_tensor(ievm_handle* h, int id, void* host_out, uint64_t host
 int ievm_debug_conv_acc(ievm_handle* h, int layer, int n, int32_t* host_out, uint64_t host_bytes) {
   if (!h || layer < 0 || layer >= static_cast<int>(h->layers.size()) || !host_out) return fail(IEVM_ERR_BAD_ARG, "bad layer");
   const LayerPlan& L = h->layers[layer];
-  if (L.d.op != IEVM_OP_CONV || L.is_stem) return fail(IEVM_ERR_BAD_ARG, "layer %d is not a tensor-core conv", layer);
+  if (L.d.op != IEVM_OP_CONV || (L.is_stem && h->dtype != IEVM_DTYPE_I8))
+    return fail(IEVM_ERR_BAD_ARG, "layer %d is not a tensor-core conv", layer);
   if (!h->keep_tensors) return fail(IEVM_ERR_BAD_ARG, "set keep_tensors=1 before the forward whose accumulators you want");
   const size_t bytes = static_cast<size_t>(n) * L.ho * L.wo * L.cout_pad * sizeof(int32_t);
   if (host_bytes < bytes) return fail(IEVM_ERR_BAD_ARG, "host buffer too small: need %zu bytes", bytes);
   CUDA_TRY(cudaSetDevice(h->device));
   int32_t* dacc = nullptr;
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dacc), bytes));
-  int rc = launch_conv(h, L, n, h->own_stream, dacc);
+  int rc = L.is_stem ? launch_stem_tc(h, L, n, h->own_stream, dacc) : launch_conv(h, L, n, h->own_stream, dacc);
   if (rc == IEVM_OK) rc = check_stuck(h, cudaStreamSynchronize(h->own_stream), "debug_conv_acc");
   if (rc == IEVM_OK && cudaMemcpy(host_out, dacc, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
     rc = fail(IEVM_ERR_CUDA, "accumulator copy failed");
@@ -906,6 +1079,35 @@ int ievm_probe_im2col(const void* in_dev, int n, int h, int w, int c_pitch, int 
   const unsigned code = *stuck_host;
   cudaFreeHost(stuck_host);
   if (e != cudaSuccess) return fail(IEVM_ERR_CUDA, "probe_im2col: %s (stuck code 0x%x)", cudaGetErrorString(e), code);
+  return IEVM_OK;
+}
+
+int ievm_probe_patch(const void* in_dev, int n, int h, int w, int c_pitch, int rb, int img, int w0, int h0, int box_w,
+                     int box_h, void* out_dev) {
+  if (!in_dev || !out_dev || (rb != 64 && rb != 128)) return fail(IEVM_ERR_BAD_ARG, "probe_patch: bad arguments");
+  if (int rc = load_driver_entry_points()) return rc;
+  CUtensorMap tmap;
+  cuuint64_t dims[4] = {(cuuint64_t)c_pitch, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c_pitch, (cuuint64_t)w * c_pitch, (cuuint64_t)h * w * c_pitch};
+  cuuint32_t box[4] = {(cuuint32_t)rb, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = g_encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(in_dev), dims, strides, box,
+                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "probe_patch: cuTensorMapEncodeTiled CUresult %d", (int)r);
+  unsigned int* stuck_host = nullptr;
+  unsigned int* stuck_dev = nullptr;
+  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&stuck_host), sizeof(unsigned int), cudaHostAllocMapped));
+  *stuck_host = 0;
+  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&stuck_dev), stuck_host, 0));
+  const int bytes = box_w * box_h * rb;
+  CUDA_TRY(cudaFuncSetAttribute(probe_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 2048));
+  probe_patch_kernel<<<1, 128, bytes + 2048>>>(tmap, 0, w0, h0, img, bytes, static_cast<uint8_t*>(out_dev), stuck_dev);
+  const cudaError_t e = cudaDeviceSynchronize();
+  const unsigned code = *stuck_host;
+  cudaFreeHost(stuck_host);
+  if (e != cudaSuccess) return fail(IEVM_ERR_CUDA, "probe_patch: %s (stuck code 0x%x)", cudaGetErrorString(e), code);
   return IEVM_OK;
 }
 
