@@ -78,7 +78,10 @@ struct TensorInfo {
   int producer = -1;                    // layer index, -1 for the network input
   int last_use = -1;
   int buffer = -1;
-  size_t bytes_per_image() const { return static_cast<size_t>(h) * w * pitch * elem; }
+  int hp = 0, wp = 0, pad_t = 0, pad_l = 0;   // stored with a constant border when hp > 0 (INT8 network input)
+  size_t bytes_per_image() const {
+    return hp > 0 ? static_cast<size_t>(hp) * wp * pitch * elem : static_cast<size_t>(h) * w * pitch * elem;
+  }
 };
 
 struct LayerPlan {
@@ -116,6 +119,7 @@ struct ievm_handle {
   int smem_optin = 0;
   int opt_halo = 1;        // IEVM_HALO=0 disables the halo-patch mode (all convs use per-tap im2col TMA)
   int opt_halo_rb128 = 0;
+  int front_chunk = 0;     // IEVM_FRONT_CHUNK: images per front-end chunk (0 = whole batch at once, default)
   // IEVM_HALO_RB128=1: 64-byte pixels use 128-byte shared-memory rows in halo mode
   int in_c = 0, in_h = 0, in_w = 0, classes = 0;
   float in_scale = 1.f;
@@ -172,8 +176,12 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
   t0.w = nd->in_w;
   t0.c = nd->in_c;
   if (h->dtype == IEVM_DTYPE_I8) {
-    t0.pitch = 4;      // quantized NHWC4
+    t0.pitch = 4;      // quantized NHWC4 inside a zero-point border (simt_kernels.cuh)
     t0.elem = 1;
+    t0.hp = nd->in_h + kInPadH;
+    t0.wp = nd->in_w + kInPadW;
+    t0.pad_t = kInPadTop;
+    t0.pad_l = kInPadLeft;
   } else {
     t0.pitch = nd->in_c;   // caller's f16 NCHW buffer is read in place by the stem
     t0.elem = 2;
@@ -225,7 +233,7 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
     if (L.is_stem) {
       if (d.cin != 3 || d.ksize != 7 || d.stride != 2 || d.pad != 3 || d.res_tensor >= 0 || L.n_tiles != 1)
         return fail(IEVM_ERR_UNSUPPORTED, "stem must be a 3-channel 7x7/2 pad-3 conv with <= 256 outputs");
-      if ((nd->in_h * nd->in_w) % 4 != 0) return fail(IEVM_ERR_UNSUPPORTED, "input plane must be a multiple of 4");
+      if (nd->in_w % 4 != 0 || nd->in_h % 2 != 0) return fail(IEVM_ERR_UNSUPPORTED, "input width must be a multiple of 4 and height even");
       continue;
     }
     if (!((d.ksize == 3 && d.pad == 1) || (d.ksize == 1 && d.pad == 0)) || d.stride < 1 || d.stride > 2)
@@ -420,6 +428,8 @@ int upload_head_operands(ievm_handle* h, LayerPlan& L) {
 // ----------------------------------------------------------------------------------------------
 // Workspace: greedy buffer reuse by liveness (or one buffer per tensor with keep_tensors)
 // ----------------------------------------------------------------------------------------------
+bool front_end_is_chunked(const ievm_handle* h);
+
 int assign_buffers(ievm_handle* h) {
   for (void* b : h->buffers) cudaFree(b);
   h->buffers.clear();
@@ -450,21 +460,26 @@ int assign_buffers(ievm_handle* h) {
     return static_cast<int>(need.size()) - 1;
   };
   for (auto& t : h->tensors) t.buffer = -1;
-  if (!f16) h->tensors[0].buffer = take(h->tensors[0].bytes_per_image() * h->max_batch);
+  const bool chunked = front_end_is_chunked(h);
+  const size_t front_imgs = chunked ? static_cast<size_t>(std::min(h->max_batch, h->front_chunk)) : h->max_batch;
+  if (!f16) h->tensors[0].buffer = take(h->tensors[0].bytes_per_image() * front_imgs);
   for (size_t i = 0; i < h->layers.size(); ++i) {
     const LayerPlan& L = h->layers[i];
     if (L.d.op != IEVM_OP_HEAD) {
       TensorInfo& t = h->tensors[L.d.out_tensor];
-      t.buffer = take(t.bytes_per_image() * h->max_batch);
+      t.buffer = take(t.bytes_per_image() * ((chunked && i == 0) ? front_imgs : static_cast<size_t>(h->max_batch)));
     }
     if (!h->keep_tensors)
-      for (auto& t : h->tensors)
+      for (size_t ti = (f16 ? 0 : 1); ti < h->tensors.size(); ++ti) {   // the INT8 input keeps its bordered buffer
+        const TensorInfo& t = h->tensors[ti];
         if (t.buffer >= 0 && t.last_use == static_cast<int>(i)) free_list.push_back(t.buffer);
+      }
   }
   for (size_t b = 0; b < need.size(); ++b) {
     void* p = nullptr;
     CUDA_TRY(cudaMalloc(&p, need[b] + 256));
-    CUDA_TRY(cudaMemset(p, 0, need[b] + 256));
+    const int fill = (!f16 && static_cast<int>(b) == h->tensors[0].buffer) ? h->in_zp : 0;   // zero-point border
+    CUDA_TRY(cudaMemset(p, fill, need[b] + 256));
     h->buffers.push_back(p);
     h->buffer_bytes.push_back(need[b]);
   }
@@ -625,7 +640,8 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
   return IEVM_OK;
 }
 
-int launch_stem_tc(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32_t* dump_acc) {
+int launch_stem_tc(ievm_handle* h, const LayerPlan& L, const uint8_t* xq, uint8_t* out, int n, cudaStream_t s,
+                   int32_t* dump_acc) {
   StemTcParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.n = n; sp.h = L.h; sp.w = L.w; sp.ho = L.ho; sp.wo = L.wo;
@@ -636,8 +652,8 @@ int launch_stem_tc(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, in
   sp.tmem_cols = L.tmem_cols;
   sp.acc_stride = L.tmem_cols / 2;
   sp.idesc = make_idesc_i8_u8s8(L.cout_pad);
-  sp.xq = static_cast<const uint8_t*>(tensor_ptr(h, 0));
-  sp.out = static_cast<uint8_t*>(tensor_ptr(h, L.d.out_tensor));
+  sp.xq = xq;
+  sp.out = out;
   sp.bdiv = L.ep0; sp.mult = L.ep1; sp.zwsum = L.zwsum;
   sp.out_zp = L.d.out_zp; sp.out_lo = L.d.relu ? L.d.out_zp : 0;
   sp.dump_acc = dump_acc;
@@ -646,6 +662,64 @@ int launch_stem_tc(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, in
   stem_tc_kernel<<<grid, kStemThreads, L.stem_smem, s>>>(L.tmap_b, sp);
   CUDA_TRY(cudaGetLastError());
   return IEVM_OK;
+}
+
+int launch_quantize(ievm_handle* h, const float* x, int n, uint8_t* xq, cudaStream_t s) {
+  const long long quads = static_cast<long long>(n) * h->in_h * h->in_w / 4;
+  quantize_nchw3_to_nhwc4_kernel<<<static_cast<unsigned>((quads + 255) / 256), 256, 0, s>>>(
+      x, xq, quads, h->in_h, h->in_w, 1.0f / h->in_scale, h->in_zp);
+  CUDA_TRY(cudaGetLastError());
+  return IEVM_OK;
+}
+
+// Stem conv: `in` is the quantised NHWC4 tensor (INT8) or the caller's f16 NCHW batch (FP16).
+int launch_stem(ievm_handle* h, const LayerPlan& L, const void* in, void* out, int n, cudaStream_t s) {
+  const ievm_layer_desc& d = L.d;
+  const long long m_total = static_cast<long long>(n) * L.ho * L.wo;
+  if (h->dtype == IEVM_DTYPE_I8 && h->conv_impl == 0)
+    return launch_stem_tc(h, L, static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), n, s, nullptr);
+  if (h->dtype == IEVM_DTYPE_I8) {
+    StemParams sp;
+    sp.n = n; sp.h = L.h; sp.w = L.w; sp.ho = L.ho; sp.wo = L.wo; sp.cpad = L.cout_pad; sp.in_zp = h->in_zp;
+    sp.w4 = static_cast<const uint32_t*>(L.w_stem); sp.wsum = L.wsum; sp.bdiv = L.ep0; sp.mult = L.ep1;
+    sp.out_zp = d.out_zp; sp.out_lo = d.relu ? d.out_zp : 0;
+    stem_conv7x7_simt_kernel<<<static_cast<unsigned>((m_total + 127) / 128), 128, 49 * L.cout_pad * 4, s>>>(
+        static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), sp);
+  } else {
+    StemF16Params sp;
+    sp.n = n; sp.h = L.h; sp.w = L.w; sp.ho = L.ho; sp.wo = L.wo; sp.cpad = L.cout_pad;
+    sp.wt = static_cast<const __half*>(L.w_stem); sp.bias = L.ep0;
+    const long long total = m_total * (L.cout_pad / 8);
+    stem_conv7x7_f16_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 147 * L.cout_pad * 2, s>>>(
+        static_cast<const __half*>(in), static_cast<__half*>(out), sp);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return IEVM_OK;
+}
+
+int launch_maxpool(ievm_handle* h, const LayerPlan& L, const void* in, void* out, int n, cudaStream_t s) {
+  const int pitch = L.cin_pitch;
+  if (h->dtype == IEVM_DTYPE_I8) {
+    const long long total = static_cast<long long>(n) * L.ho * L.wo * (pitch / 16);
+    maxpool3x3s2_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+        static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), n, L.h, L.w, L.ho, L.wo, pitch);
+  } else {
+    const long long total = static_cast<long long>(n) * L.ho * L.wo * (pitch / 8);
+    maxpool3x3s2_f16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+        static_cast<const __half*>(in), static_cast<__half*>(out), n, L.h, L.w, L.ho, L.wo, pitch);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return IEVM_OK;
+}
+
+// The front end (quantize -> stem -> maxpool) is run in chunks of `front_chunk` images through two
+// small reused buffers: the stem's 112x112xC output (the largest tensor of the net, 0.8 MB/image)
+// is produced and consumed inside L2 and, because every chunk overwrites the same lines, never has
+// to be written back to HBM.
+bool front_end_is_chunked(const ievm_handle* h) {
+  return h->dtype == IEVM_DTYPE_I8 && h->front_chunk > 0 && !h->keep_tensors && h->layers.size() >= 2 &&
+         h->layers[0].is_stem && h->layers[1].d.op == IEVM_OP_MAXPOOL &&
+         h->layers[1].d.in_tensor == h->layers[0].d.out_tensor && h->tensors[h->layers[0].d.out_tensor].last_use == 1;
 }
 
 int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStream_t s) {
@@ -661,55 +735,39 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     h->prof_calls.resize(h->layers.size() + 1, 0);
     CUDA_TRY(cudaEventRecord(h->prof_events[0], s));
   }
-  if (i8) {
-    const long long plane = static_cast<long long>(h->in_h) * h->in_w;
-    const long long quads = static_cast<long long>(n) * plane / 4;
-    quantize_nchw3_to_nhwc4_kernel<<<static_cast<unsigned>((quads + 255) / 256), 256, 0, s>>>(
-        static_cast<const float*>(x), static_cast<uint8_t*>(tensor_ptr(h, 0)), quads, static_cast<int>(plane),
-        1.0f / h->in_scale, h->in_zp);
-    CUDA_TRY(cudaGetLastError());
+  size_t first_layer = 0;
+  if (front_end_is_chunked(h)) {
+    // profile slots: the whole interleaved front end is attributed to the stem's slot
+    if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
+    const LayerPlan& Ls = h->layers[0];
+    const LayerPlan& Lp = h->layers[1];
+    const size_t in_img = static_cast<size_t>(h->in_c) * h->in_h * h->in_w;
+    const size_t pooled_img = h->tensors[Lp.d.out_tensor].bytes_per_image();
+    for (int c0 = 0; c0 < n; c0 += h->front_chunk) {
+      const int nc = std::min(h->front_chunk, n - c0);
+      if (int rc = launch_quantize(h, static_cast<const float*>(x) + c0 * in_img, nc,
+                                   static_cast<uint8_t*>(tensor_ptr(h, 0)), s)) return rc;
+      if (int rc = launch_stem(h, Ls, tensor_ptr(h, 0), tensor_ptr(h, Ls.d.out_tensor), nc, s)) return rc;
+      if (int rc = launch_maxpool(h, Lp, tensor_ptr(h, Ls.d.out_tensor),
+                                  static_cast<uint8_t*>(tensor_ptr(h, Lp.d.out_tensor)) + c0 * pooled_img, nc, s)) return rc;
+    }
+    if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[2], s));
+    first_layer = 2;
+  } else {
+    if (i8)
+      if (int rc = launch_quantize(h, static_cast<const float*>(x), n, static_cast<uint8_t*>(tensor_ptr(h, 0)), s)) return rc;
+    if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
   }
-  if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
-  for (size_t li = 0; li < h->layers.size(); ++li) {
+  for (size_t li = first_layer; li < h->layers.size(); ++li) {
     const LayerPlan& L = h->layers[li];
     const ievm_layer_desc& d = L.d;
     if (prof && li > 0) CUDA_TRY(cudaEventRecord(h->prof_events[li + 1], s));
     if (d.op == IEVM_OP_CONV && L.is_stem) {
-      const long long m_total = static_cast<long long>(n) * L.ho * L.wo;
-      if (i8 && h->conv_impl == 0) {
-        if (int rc = launch_stem_tc(h, L, n, s, nullptr)) return rc;
-      } else if (i8) {
-        StemParams sp;
-        sp.n = n; sp.h = L.h; sp.w = L.w; sp.ho = L.ho; sp.wo = L.wo; sp.cpad = L.cout_pad; sp.in_zp = h->in_zp;
-        sp.w4 = static_cast<const uint32_t*>(L.w_stem); sp.wsum = L.wsum; sp.bdiv = L.ep0; sp.mult = L.ep1;
-        sp.out_zp = d.out_zp; sp.out_lo = d.relu ? d.out_zp : 0;
-        stem_conv7x7_simt_kernel<<<static_cast<unsigned>((m_total + 127) / 128), 128, 49 * L.cout_pad * 4, s>>>(
-            static_cast<const uint8_t*>(tensor_ptr(h, 0)), static_cast<uint8_t*>(tensor_ptr(h, d.out_tensor)), sp);
-      } else {
-        StemF16Params sp;
-        sp.n = n; sp.h = L.h; sp.w = L.w; sp.ho = L.ho; sp.wo = L.wo; sp.cpad = L.cout_pad;
-        sp.wt = static_cast<const __half*>(L.w_stem); sp.bias = L.ep0;
-        const long long total = m_total * (L.cout_pad / 8);
-        stem_conv7x7_f16_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 147 * L.cout_pad * 2, s>>>(
-            static_cast<const __half*>(x), static_cast<__half*>(tensor_ptr(h, d.out_tensor)), sp);
-      }
-      CUDA_TRY(cudaGetLastError());
+      if (int rc = launch_stem(h, L, i8 ? tensor_ptr(h, 0) : x, tensor_ptr(h, d.out_tensor), n, s)) return rc;
     } else if (d.op == IEVM_OP_CONV) {
       if (int rc = launch_conv(h, L, n, s, nullptr)) return rc;
     } else if (d.op == IEVM_OP_MAXPOOL) {
-      const TensorInfo& tin = h->tensors[d.in_tensor];
-      if (i8) {
-        const long long total = static_cast<long long>(n) * L.ho * L.wo * (tin.pitch / 16);
-        maxpool3x3s2_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
-            static_cast<const uint8_t*>(tensor_ptr(h, d.in_tensor)), static_cast<uint8_t*>(tensor_ptr(h, d.out_tensor)),
-            n, L.h, L.w, L.ho, L.wo, tin.pitch);
-      } else {
-        const long long total = static_cast<long long>(n) * L.ho * L.wo * (tin.pitch / 8);
-        maxpool3x3s2_f16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
-            static_cast<const __half*>(tensor_ptr(h, d.in_tensor)), static_cast<__half*>(tensor_ptr(h, d.out_tensor)),
-            n, L.h, L.w, L.ho, L.wo, tin.pitch);
-      }
-      CUDA_TRY(cudaGetLastError());
+      if (int rc = launch_maxpool(h, L, tensor_ptr(h, d.in_tensor), tensor_ptr(h, d.out_tensor), n, s)) return rc;
     } else {   // head
       const TensorInfo& tin = h->tensors[d.in_tensor];
       if (i8) {
@@ -861,6 +919,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   h->in_scale = nd->in_scale; h->in_zp = nd->in_zp;
   if (const char* e = getenv("IEVM_HALO")) h->opt_halo = atoi(e);
   if (const char* e = getenv("IEVM_HALO_RB128")) h->opt_halo_rb128 = atoi(e);
+  if (const char* e = getenv("IEVM_FRONT_CHUNK")) h->front_chunk = atoi(e);
   int rc = plan_shapes(h, nd);
   for (size_t i = 0; rc == IEVM_OK && i < h->layers.size(); ++i) {
     LayerPlan& L = h->layers[i];
@@ -1005,6 +1064,8 @@ int ievm_tensor_shape(const ievm_handle* h, int id, int32_t out6[6]) {
 
 int ievm_launches_per_forward(const ievm_handle* h) {
   if (!h) return 0;
+  const int n = h->last_n > 0 ? h->last_n : h->max_batch;
+  if (front_end_is_chunked(h)) return 3 * ((n + h->front_chunk - 1) / h->front_chunk) + static_cast<int>(h->layers.size()) - 2;
   return static_cast<int>(h->layers.size()) + (h->dtype == IEVM_DTYPE_I8 ? 1 : 0);
 }
 
@@ -1022,10 +1083,21 @@ int ievm_debug_read_tensor(ievm_handle* h, int id, void* host_out, uint64_t host
   if (!h || id < 0 || id >= static_cast<int>(h->tensors.size()) || !host_out) return fail(IEVM_ERR_BAD_ARG, "bad tensor id");
   const TensorInfo& t = h->tensors[id];
   if (t.buffer < 0) return fail(IEVM_ERR_BAD_ARG, "tensor %d has no engine-owned buffer", id);
-  const size_t bytes = t.bytes_per_image() * h->last_n;
+  const size_t row = static_cast<size_t>(t.w) * t.pitch * t.elem;
+  const size_t bytes = row * t.h * h->last_n;
   if (host_bytes < bytes) return fail(IEVM_ERR_BAD_ARG, "host buffer too small: need %zu bytes", bytes);
   CUDA_TRY(cudaSetDevice(h->device));
   if (int rc = check_stuck(h, cudaDeviceSynchronize(), "debug_read_tensor sync")) return rc;
+  if (t.hp > 0) {   // strip the border: one 2-D copy per image
+    const size_t src_row = static_cast<size_t>(t.wp) * t.pitch * t.elem;
+    for (int i = 0; i < h->last_n; ++i) {
+      const uint8_t* src = static_cast<const uint8_t*>(tensor_ptr(h, id)) + i * t.bytes_per_image() +
+                           t.pad_t * src_row + static_cast<size_t>(t.pad_l) * t.pitch * t.elem;
+      CUDA_TRY(cudaMemcpy2D(static_cast<uint8_t*>(host_out) + i * row * t.h, row, src, src_row, row, t.h,
+                            cudaMemcpyDeviceToHost));
+    }
+    return IEVM_OK;
+  }
   CUDA_TRY(cudaMemcpy(host_out, tensor_ptr(h, id), bytes, cudaMemcpyDeviceToHost));
   return IEVM_OK;
 }
@@ -1041,7 +1113,9 @@ int ievm_debug_conv_acc(ievm_handle* h, int layer, int n, int32_t* host_out, uin
   CUDA_TRY(cudaSetDevice(h->device));
   int32_t* dacc = nullptr;
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dacc), bytes));
-  int rc = L.is_stem ? launch_stem_tc(h, L, n, h->own_stream, dacc) : launch_conv(h, L, n, h->own_stream, dacc);
+  int rc = L.is_stem ? launch_stem_tc(h, L, static_cast<const uint8_t*>(tensor_ptr(h, 0)),
+                                      static_cast<uint8_t*>(tensor_ptr(h, L.d.out_tensor)), n, h->own_stream, dacc)
+                     : launch_conv(h, L, n, h->own_stream, dacc);
   if (rc == IEVM_OK) rc = check_stuck(h, cudaStreamSynchronize(h->own_stream), "debug_conv_acc");
   if (rc == IEVM_OK && cudaMemcpy(host_out, dacc, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
     rc = fail(IEVM_ERR_CUDA, "accumulator copy failed");

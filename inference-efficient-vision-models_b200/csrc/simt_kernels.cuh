@@ -10,23 +10,34 @@
 namespace ievm {
 
 // --------------------------------------------------------------------------------------------
-// quantize_per_tensor (graph node 1): f32 NCHW [n,3,h,w] -> u8 NHWC4 [n,h,w,4] (4th byte = zp).
-// One thread = 4 consecutive pixels: three coalesced float4 loads, one 16-byte store.
+// quantize_per_tensor (graph node 1): f32 NCHW [n,3,h,w] -> u8 NHWC4 (4th byte = zp) stored with a
+// constant border of zero-point pixels, [n][h + 6][w + 8][4] with the image at (row 3, column 4):
+// the 7x7/2 stem then reads every window without a single bounds check (the border is written once
+// at engine creation and never touched again).
+// One thread = 4 consecutive pixels of a row: three coalesced float4 loads, one 16-byte store.
 // --------------------------------------------------------------------------------------------
+constexpr int kInPadTop = 3;
+constexpr int kInPadLeft = 4;
+constexpr int kInPadH = 6;     // rows added (3 above, 3 below)
+constexpr int kInPadW = 8;     // columns added (4 left, 4 right)
+
 __device__ __forceinline__ uint32_t quant_u8(float x, float inv_scale, int zp) {
   const int q = __float2int_rn(__fmul_rn(x, inv_scale)) + zp;
   return static_cast<uint32_t>(min(max(q, 0), 255));
 }
 
 __global__ void __launch_bounds__(256)
-quantize_nchw3_to_nhwc4_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long n_quads,
-                               int plane /* h*w */, float inv_scale, int zp) {
+quantize_nchw3_to_nhwc4_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long n_quads, int h, int w,
+                               float inv_scale, int zp) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_quads) return;
-  const long long pix = i * 4;
-  const long long img = pix / plane;
-  const long long off = pix - img * plane;
-  const float* base = x + img * 3 * plane + off;
+  const int qpr = w >> 2;                         // quads per row
+  const long long rowid = i / qpr;                // img * h + y
+  const int xq = static_cast<int>(i - rowid * qpr);
+  const long long img = rowid / h;
+  const int y = static_cast<int>(rowid - img * h);
+  const long long plane = static_cast<long long>(h) * w;
+  const float* base = x + img * 3 * plane + static_cast<long long>(y) * w + 4 * xq;
   const float4 r = __ldg(reinterpret_cast<const float4*>(base));
   const float4 g = __ldg(reinterpret_cast<const float4*>(base + plane));
   const float4 b = __ldg(reinterpret_cast<const float4*>(base + 2 * plane));
@@ -36,7 +47,8 @@ quantize_nchw3_to_nhwc4_kernel(const float* __restrict__ x, uint8_t* __restrict_
   o.y = quant_u8(r.y, inv_scale, zp) | (quant_u8(g.y, inv_scale, zp) << 8) | (quant_u8(b.y, inv_scale, zp) << 16) | z;
   o.z = quant_u8(r.z, inv_scale, zp) | (quant_u8(g.z, inv_scale, zp) << 8) | (quant_u8(b.z, inv_scale, zp) << 16) | z;
   o.w = quant_u8(r.w, inv_scale, zp) | (quant_u8(g.w, inv_scale, zp) << 8) | (quant_u8(b.w, inv_scale, zp) << 16) | z;
-  reinterpret_cast<uint4*>(out)[i] = o;
+  const long long orow = (img * (h + kInPadH) + y + kInPadTop) * (w + kInPadW) + kInPadLeft + 4 * xq;
+  *reinterpret_cast<uint4*>(out + orow * 4) = o;
 }
 
 __device__ __forceinline__ int dp4a_u8s8(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
@@ -49,7 +61,7 @@ __device__ __forceinline__ int dp4a_u8s8(uint32_t a_u8x4, uint32_t b_s8x4, int c
 // Stem: 7x7 stride-2 pad-3 conv over u8 NHWC4 + requant + ReLU -> u8 NHWC(cpad).
 // One thread = one output pixel; the 49 input pixels sit in registers, weights are broadcast from
 // shared memory as [tap][cout] s8x4 words.  sum (xq - zp) w = sum xq w - zp * sum w because
-// out-of-image taps read the value zp.
+// out-of-image taps read the zero-point border of the padded input tensor.
 // --------------------------------------------------------------------------------------------
 struct StemParams {
   int n, h, w, ho, wo;
@@ -74,18 +86,14 @@ stem_conv7x7_simt_kernel(const uint8_t* __restrict__ xq, uint8_t* __restrict__ o
   const int img = static_cast<int>(m / hw);
   const int rem = static_cast<int>(m - static_cast<long long>(img) * hw);
   const int oy = rem / p.wo, ox = rem - (rem / p.wo) * p.wo;
-  const uint32_t zpix = static_cast<uint32_t>(p.in_zp) * 0x01010101u;
-  const uint32_t* in32 = reinterpret_cast<const uint32_t*>(xq) + static_cast<long long>(img) * p.h * p.w;
+  const int wp = p.w + kInPadW;
+  const uint32_t* in32 = reinterpret_cast<const uint32_t*>(xq) + static_cast<long long>(img) * (p.h + kInPadH) * wp;
   uint32_t px[49];
 #pragma unroll
   for (int ky = 0; ky < 7; ++ky) {
-    const int iy = oy * 2 - 3 + ky;
+    const int iy = oy * 2 + ky;                  // padded row of input row 2*oy - 3 + ky
 #pragma unroll
-    for (int kx = 0; kx < 7; ++kx) {
-      const int ix = ox * 2 - 3 + kx;
-      const bool ok = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-      px[ky * 7 + kx] = ok ? __ldg(in32 + iy * p.w + ix) : zpix;
-    }
+    for (int kx = 0; kx < 7; ++kx) px[ky * 7 + kx] = __ldg(in32 + iy * wp + ox * 2 + kx + 1);
   }
   uint8_t* orow = out + m * p.cpad;
   for (int c0 = 0; c0 < p.cpad; c0 += 16) {

@@ -1,6 +1,6 @@
 // INT8 stem (7x7 stride-2 pad-3 conv over the 3-channel quantised input + requant + ReLU) on tcgen05.
 //
-// The input tensor is u8 NHWC4 (4th byte = zero point).  One output pixel needs, for each of the 7
+// The input tensor is u8 NHWC4 (4th byte = zero point) with a zero-point border (simt_kernels.cuh).  One output pixel needs, for each of the 7
 // filter rows, the 7 input pixels ix = 2*ox-3 .. 2*ox+3; widening the window by one pixel on the left
 // (ix = 2*ox-4, weight 0) makes it 8 pixels * 4 B = one 8-byte-aligned 32-byte segment.  The GEMM is
 //
@@ -9,18 +9,21 @@
 //
 // The A operand is too narrow per pixel (4 B) for TMA im2col (16 B minimum), so four builder warps
 // gather it with 8-byte loads and write it to shared memory in the 128B-swizzled K-major layout that
-// tcgen05.mma expects; out-of-image pixels are written as the zero point, and the epilogue subtracts
+// tcgen05.mma expects; out-of-image pixels read the zero-point border, and the epilogue subtracts
 // zp * sum(w) (exact in int32) before the usual float requantisation.
 // Weights (cout_pad x 256 B) stay resident in shared memory; accumulators are double buffered in TMEM.
 //
-// Warp roles (416 threads): warp 0 = weights TMA + TMEM owner + MMA issuer, warps 1..4 = A builders
-// (one output pixel per thread), warps 5..12 = epilogue.
+// Warp roles (544 threads): warp 0 = weights TMA + TMEM owner + MMA issuer, warps 1..8 = A builders in
+// two groups of four that alternate tiles (one output pixel per thread, all 28 loads of a tile row in
+// flight at once), warps 9..16 = epilogue.
 #pragma once
 #include "conv_tc.cuh"
+#include "simt_kernels.cuh"
 
 namespace ievm {
 
-constexpr int kStemBuildWarps = 4;
+constexpr int kStemBuildGroups = 2;
+constexpr int kStemBuildWarps = 4 * kStemBuildGroups;
 constexpr int kStemThreads = 32 * (1 + kStemBuildWarps + kEpiWarps);
 constexpr int kStemKBytes = 256;          // 8 segments x 32 B
 constexpr int kStemStages = 4;
@@ -32,7 +35,7 @@ struct StemTcParams {
   int in_zp;
   int tmem_cols, acc_stride;
   uint32_t idesc;
-  const uint8_t* xq;        // [n][h][w][4]
+  const uint8_t* xq;        // [n][h + 6][w + 8][4], image at (3, 4), zero-point border
   uint8_t* out;             // [n][ho][wo][cpad]
   const float* bdiv;
   const float* mult;
@@ -75,7 +78,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemTcParams p)
     if (lane == 0) {
       tma_prefetch_desc(&tmap_w);
       for (int i = 0; i < kStemStages; ++i) {
-        mbar_init(&full_bar[i], kStemBuildWarps * 32);
+        mbar_init(&full_bar[i], 128);
         mbar_init(&empty_bar[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
@@ -134,51 +137,50 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemTcParams p)
     }
   } else if (warp <= kStemBuildWarps) {
     // ================================ A builders ================================
-    const int r = (warp - 1) * 32 + lane;                    // tile row == output pixel
+    const int group = (warp - 1) >> 2;                       // which builder group
+    const int r = ((warp - 1) & 3) * 32 + lane;              // tile row == output pixel
     const uint32_t sw = static_cast<uint32_t>(r & 7);         // 128B-swizzle phase of this row
-    const uint2 zp2 = make_uint2(static_cast<uint32_t>(p.in_zp) * 0x01010101u,
-                                 static_cast<uint32_t>(p.in_zp) * 0x01010101u);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-      const int m = tile * kTileM + r;
-      const bool valid = m < p.m_total;
-      const int img = valid ? m / hw : 0;
+    const uint2* in_pairs = reinterpret_cast<const uint2*>(p.xq);
+    const int hp = p.h + kInPadH;
+    const int wp2 = (p.w + kInPadW) >> 1;                    // pixel pairs per padded row
+    uint32_t chunk_off[8];                                   // swizzled 16-byte chunk offsets of this row
+#pragma unroll
+    for (int c = 0; c < 8; ++c) chunk_off[c] = ((static_cast<uint32_t>(c) ^ sw) << 4);
+    // Tile t (in this CTA's order) uses stage t % kStemStages; group g builds the tiles with t % 2 == g.
+    int t = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++t) {
+      if ((t & (kStemBuildGroups - 1)) != group) continue;
+      const int stage = t % kStemStages;
+      const uint32_t phase = static_cast<uint32_t>(t / kStemStages) & 1u;
+      const int m = min(tile * kTileM + r, p.m_total - 1);      // rows past the end rebuild the last pixel (discarded)
+      const int img = m / hw;
       const int rem = m - img * hw;
       const int oy = rem / p.wo;
       const int ox = rem - oy * p.wo;
-      const int ix0 = 2 * ox - 4;                              // window start (even, may be negative)
-      const uint8_t* img_base = p.xq + static_cast<size_t>(img) * p.h * p.w * 4;
+      // Padded input (see quantize kernel): filter row ky of this pixel starts at padded row 2*oy + ky,
+      // padded column 2*ox (= input column 2*ox - 4); 32 bytes = 4 aligned pixel pairs.
+      const uint2* src = in_pairs + (static_cast<size_t>(img) * hp + 2 * oy) * wp2 + ox;
+      uint2 q[7][4];
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[ky][j] = __ldg(src + ky * wp2 + j);
+      }
       wait_or_die(&empty_bar[stage], phase ^ 1u, 0x630u | stage, p.stuck_flag);
       uint8_t* a_row = sA + stage * kAStage + r * 128;
 #pragma unroll
-      for (int ky = 0; ky < 8; ++ky) {
-        uint2 q[4] = {zp2, zp2, zp2, zp2};
-        const int iy = 2 * oy - 3 + ky;
-        if (ky < 7 && valid && iy >= 0 && iy < p.h) {
-          const uint2* src = reinterpret_cast<const uint2*>(img_base + (static_cast<size_t>(iy) * p.w) * 4) ;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ix = ix0 + 2 * j;                        // pixel pair (ix, ix+1): both in or both out
-            if (ix >= 0 && ix < p.w) q[j] = __ldg(src + (ix >> 1));
-          }
-        }
+      for (int ky = 0; ky < 7; ++ky) {                         // segment 7 has zero weights: left unwritten
         uint8_t* blk = a_row + (ky >> 2) * kABlock;
-        const uint32_t c0 = static_cast<uint32_t>((ky & 3) * 2);
-        *reinterpret_cast<uint4*>(blk + ((c0 ^ sw) << 4)) = make_uint4(q[0].x, q[0].y, q[1].x, q[1].y);
-        *reinterpret_cast<uint4*>(blk + (((c0 + 1) ^ sw) << 4)) = make_uint4(q[2].x, q[2].y, q[3].x, q[3].y);
+        *reinterpret_cast<uint4*>(blk + chunk_off[(ky & 3) * 2]) = make_uint4(q[ky][0].x, q[ky][0].y, q[ky][1].x, q[ky][1].y);
+        *reinterpret_cast<uint4*>(blk + chunk_off[(ky & 3) * 2 + 1]) = make_uint4(q[ky][2].x, q[ky][2].y, q[ky][3].x, q[ky][3].y);
       }
       fence_proxy_async_smem();                                // generic-proxy writes -> visible to the MMA
       mbar_arrive(&full_bar[stage]);
-      if (++stage == kStemStages) {
-        stage = 0;
-        phase ^= 1u;
-      }
     }
   } else {
     // ================================ epilogue ================================
     const int quad = warp & 3;
-    const int half = (warp - 1 - kStemBuildWarps) >> 2;
+    const int half = (warp - 1 - kStemBuildWarps) >> 2;   // warps 9..16: quadrant = warp % 4, two warps each
     const int row = quad * 32 + lane;
     const int nchunks = p.cpad >> 4;
     int acc = 0;
