@@ -14,9 +14,10 @@
 // * The epilogue is fused: INT8 requantisation (+ReLU clamp) and, for a block's last conv, the whole
 //   quantized::add_relu with the residual; FP16 bias (+residual) (+ReLU).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4; the two warps of a quadrant interleave
-// 16-column chunks).
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..17 = epilogue (TMEM lane quadrant = warp % 4; the four warps of a quadrant interleave
+// 16-column chunks).  The epilogue is latency-bound (TMEM load -> LDS -> dependent float chain), so it
+// gets as many warps as the register file allows.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -25,7 +26,8 @@
 namespace ievm {
 
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiSub = kEpiWarps / 4;     // epilogue warps per TMEM lane quadrant; they interleave 16-column chunks
 constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 
 enum : int { kDtypeI8 = 0, kDtypeF16 = 1 };
@@ -315,51 +317,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      if (p.resident_b) {
-        mbar_expect_tx(bres_bar, static_cast<uint32_t>(num_kb * b_bytes));
-        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sB + kb * b_bytes, &tmap_b, bres_bar, kb * p.kc_elems, 0);
-      }
-      const uint32_t tx_bytes = static_cast<uint32_t>(p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        if (kMode == kModeHalo) {
-          const int img = tile / p.tiles_per_img;
-          const int p0 = (tile - img * p.tiles_per_img) * kTileM;
-          const int oy_first = p0 / p.wp;
-          wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
+    // The whole warp walks the schedule (so coordinates stay in uniform registers); one elected lane
+    // arms the barrier and issues the copies.
+    if (p.resident_b && elect_one()) {
+      mbar_expect_tx(bres_bar, static_cast<uint32_t>(num_kb * b_bytes));
+      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sB + kb * b_bytes, &tmap_b, bres_bar, kb * p.kc_elems, 0);
+    }
+    __syncwarp();
+    const uint32_t tx_bytes = static_cast<uint32_t>(p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (kMode == kModeHalo) {
+        const int img = tile / p.tiles_per_img;
+        const int p0 = (tile - img * p.tiles_per_img) * kTileM;
+        const int oy_first = p0 / p.wp;
+        wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], 0, -1, oy_first - 1, img);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-          continue;
         }
-        const int m_tile = tile / p.n_tiles;
-        const int n_tile = tile - m_tile * p.n_tiles;
-        const int m0 = m_tile * kTileM;
-        const int img = m0 / hw;
-        const int rem = m0 - img * hw;
-        const int oy = rem / p.wo;
-        const int ox = rem - oy * p.wo;
-        const int base_w = ox * p.stride - p.pad;
-        const int base_h = oy * p.stride - p.pad;
-        int kb = 0;
-        for (int ty = 0; ty < p.ksize; ++ty) {
-          for (int tx = 0; tx < p.ksize; ++tx) {
-            for (int ch = 0; ch < p.kchunks; ++ch, ++kb) {
-              wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        continue;
+      }
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const int m0 = m_tile * kTileM;
+      const int img = m0 / hw;
+      const int rem = m0 - img * hw;
+      const int oy = rem / p.wo;
+      const int ox = rem - oy * p.wo;
+      const int base_w = ox * p.stride - p.pad;
+      const int base_h = oy * p.stride - p.pad;
+      int kb = 0;
+      for (int ty = 0; ty < p.ksize; ++ty) {
+        for (int tx = 0; tx < p.ksize; ++tx) {
+          for (int ch = 0; ch < p.kchunks; ++ch, ++kb) {
+            wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
+            if (elect_one()) {
               mbar_expect_tx(&full_bar[stage], tx_bytes);
-              tma_load_im2col_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h,
-                                 img, static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
+              tma_load_im2col_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h, img,
+                                 static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
               if (!p.resident_b)
                 tma_load_2d(sB + stage * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems, n_tile * p.bn);
-              if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1u;
-              }
+            }
+            __syncwarp();
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
             }
           }
         }
@@ -408,8 +417,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int x0 = p0 - (p0 / p.wp) * p.wp;
         wait_or_die(&full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step + static_cast<uint32_t>(x0) * row16;
+        const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step + static_cast<uint32_t>(x0) * row16;
+        if (elect_one()) {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap)
             mma_kblock(d_tmem, a_lo + tap_off[tap], b_lo0 + static_cast<uint32_t>(tap) * b_step, tap != 0 ? 1u : 0u);
@@ -425,9 +434,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           wait_or_die(&full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step;
-            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(p.resident_b ? kb : stage) * b_step;
+          const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step;
+          const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(p.resident_b ? kb : stage) * b_step;
+          if (elect_one()) {
             mma_kblock(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
             umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
             if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
@@ -445,7 +454,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ================================ epilogue ================================
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;        // 0 or 1: which of the quadrant's two warps
+    const int half = (warp - 2) >> 2;        // 0 .. kEpiSub-1: which of the quadrant's warps
     const int row = quad * 32 + lane;
     const int nchunks = p.bn >> 4;
     AddReluConst k;
@@ -490,20 +499,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (c < nchunks) tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), va);
       while (c < nchunks) {
         tmem_ld_wait();
-        if (c + 2 < nchunks) {
-          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 2) * 16), vb);
-          if (kResI8) rb = load_res16_i8(p, m, valid, n0 + (c + 2) * 16);
+        if (c + kEpiSub < nchunks) {
+          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + kEpiSub) * 16), vb);
+          if (kResI8) rb = load_res16_i8(p, m, valid, n0 + (c + kEpiSub) * 16);
         }
         epilogue_chunk<kDtype, kHasRes>(p, va, ra, m, valid, n0 + c * 16, s_ep0, s_ep1, k);
-        c += 2;
+        c += kEpiSub;
         if (c >= nchunks) break;
         tmem_ld_wait();
-        if (c + 2 < nchunks) {
-          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 2) * 16), va);
-          if (kResI8) ra = load_res16_i8(p, m, valid, n0 + (c + 2) * 16);
+        if (c + kEpiSub < nchunks) {
+          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + kEpiSub) * 16), va);
+          if (kResI8) ra = load_res16_i8(p, m, valid, n0 + (c + kEpiSub) * 16);
         }
         epilogue_chunk<kDtype, kHasRes>(p, vb, rb, m, valid, n0 + c * 16, s_ep0, s_ep1, k);
-        c += 2;
+        c += kEpiSub;
       }
       tc_fence_before();
       __syncwarp();

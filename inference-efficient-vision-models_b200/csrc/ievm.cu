@@ -19,6 +19,7 @@
 #include "conv_tc.cuh"
 #include "simt_kernels.cuh"
 #include "stem_tc.cuh"
+#include "frontend_fused.cuh"
 
 namespace {
 
@@ -119,6 +120,9 @@ struct ievm_handle {
   int smem_optin = 0;
   int opt_halo = 1;        // IEVM_HALO=0 disables the halo-patch mode (all convs use per-tap im2col TMA)
   int opt_halo_rb128 = 0;
+  int opt_fused_front = 1; // IEVM_FUSED_FRONT=0: separate quantize / stem / maxpool kernels
+  size_t fe_smem = 0;
+  int opt_fixed_bn = 0;    // IEVM_FIXED_BN=1: one N tile per <=256 channels (disables the tile-width heuristic)
   int front_chunk = 0;     // IEVM_FRONT_CHUNK: images per front-end chunk (0 = whole batch at once, default)
   // IEVM_HALO_RB128=1: 64-byte pixels use 128-byte shared-memory rows in halo mode
   int in_c = 0, in_h = 0, in_w = 0, classes = 0;
@@ -282,6 +286,33 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
     L.kc_elems = L.kc_bytes / h->elem;
     L.kchunks = (d.cin * h->elem + L.kc_bytes - 1) / L.kc_bytes;
     L.cin_w = L.kchunks * L.kc_elems;
+    {
+      // N-tile width: the persistent grid runs ceil(tiles / #SMs) rounds of tiles, each costing about
+      // (#k-blocks x k-steps) MMAs of max(bn/2, issue floor) cycles.  Narrower tiles waste less of the
+      // last round (e.g. 7x7 layers: 98 M-tiles x 2 N-tiles on 148 SMs is 1.3 rounds, x 3 N-tiles is 2.0).
+      const int num_kb_ = d.ksize * d.ksize * L.kchunks;
+      const int ksteps = L.kc_bytes / 32;
+      const long long m_tiles = (static_cast<long long>(h->max_batch) * L.ho * L.wo + kTileM - 1) / kTileM;
+      long long best_cost = -1;
+      int best_bn = L.bn;
+      for (int bn = 16; bn <= 256; bn += 16) {
+        if (L.cout_pad % bn != 0) continue;
+        const long long tiles = m_tiles * (L.cout_pad / bn);
+        const long long rounds = (tiles + h->num_sms - 1) / h->num_sms;
+        const long long tile_cycles = static_cast<long long>(num_kb_) * ksteps * std::max(bn / 2, 24) + 600 + 6LL * bn;
+        const long long cost = rounds * tile_cycles;
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best_bn)) {
+          best_cost = cost;
+          best_bn = bn;
+        }
+      }
+      if (!h->opt_fixed_bn) {
+        L.bn = best_bn;
+        L.n_tiles = L.cout_pad / L.bn;
+        L.tmem_cols = 32;
+        while (L.tmem_cols < 2 * L.bn) L.tmem_cols *= 2;
+      }
+    }
     // shared-memory plan: [A stages][B stages | all B k-blocks][epilogue tables][barriers]
     const int a_bytes = kTileM * L.kc_bytes, b_bytes = L.bn * L.kc_bytes;
     const int num_kb = d.ksize * d.ksize * L.kchunks;
@@ -429,6 +460,7 @@ int upload_head_operands(ievm_handle* h, LayerPlan& L) {
 // Workspace: greedy buffer reuse by liveness (or one buffer per tensor with keep_tensors)
 // ----------------------------------------------------------------------------------------------
 bool front_end_is_chunked(const ievm_handle* h);
+bool front_end_is_fused(const ievm_handle* h);
 
 int assign_buffers(ievm_handle* h) {
   for (void* b : h->buffers) cudaFree(b);
@@ -716,6 +748,39 @@ int launch_maxpool(ievm_handle* h, const LayerPlan& L, const void* in, void* out
 // small reused buffers: the stem's 112x112xC output (the largest tensor of the net, 0.8 MB/image)
 // is produced and consumed inside L2 and, because every chunk overwrites the same lines, never has
 // to be written back to HBM.
+// quantize + stem + maxpool in one kernel (frontend_fused.cuh): INT8, tensor-core path, no parity hooks.
+bool front_end_is_fused(const ievm_handle* h) {
+  return h->dtype == IEVM_DTYPE_I8 && h->opt_fused_front && h->conv_impl == 0 && !h->keep_tensors &&
+         h->layers.size() >= 2 && h->layers[0].is_stem && h->layers[1].d.op == IEVM_OP_MAXPOOL &&
+         h->layers[1].d.in_tensor == h->layers[0].d.out_tensor && h->tensors[h->layers[0].d.out_tensor].last_use == 1 &&
+         (h->layers[0].cout_pad == 64 || h->layers[0].cout_pad == 128 || h->layers[0].cout_pad == 256);
+}
+
+int launch_frontend_fused(ievm_handle* h, const float* x, int n, cudaStream_t s) {
+  const LayerPlan& Ls = h->layers[0];
+  const LayerPlan& Lp = h->layers[1];
+  FrontendParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.n = n; fp.h = Ls.h; fp.w = Ls.w; fp.ho = Ls.ho; fp.wo = Ls.wo; fp.ph = Lp.ho; fp.pw = Lp.wo;
+  fp.strips = (fp.pw + 6) / 7;
+  fp.tiles_per_strip = (fp.ho + 7) / 8;
+  fp.cpad = Ls.cout_pad;
+  fp.in_zp = h->in_zp;
+  fp.inv_scale = 1.0f / h->in_scale;
+  fp.tmem_cols = Ls.tmem_cols;
+  fp.acc_stride = Ls.tmem_cols / 2;
+  fp.idesc = make_idesc_i8_u8s8(Ls.cout_pad);
+  fp.x = x;
+  fp.out = static_cast<uint8_t*>(tensor_ptr(h, Lp.d.out_tensor));
+  fp.bdiv = Ls.ep0; fp.mult = Ls.ep1; fp.zwsum = Ls.zwsum;
+  fp.out_zp = Ls.d.out_zp; fp.out_lo = Ls.d.relu ? Ls.d.out_zp : 0;
+  fp.stuck_flag = h->stuck_dev;
+  const int grid = std::min(n * fp.strips, h->num_sms);
+  frontend_fused_kernel<<<grid, kFeThreads, h->fe_smem, s>>>(Ls.tmap_b, fp);
+  CUDA_TRY(cudaGetLastError());
+  return IEVM_OK;
+}
+
 bool front_end_is_chunked(const ievm_handle* h) {
   return h->dtype == IEVM_DTYPE_I8 && h->front_chunk > 0 && !h->keep_tensors && h->layers.size() >= 2 &&
          h->layers[0].is_stem && h->layers[1].d.op == IEVM_OP_MAXPOOL &&
@@ -736,7 +801,13 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     CUDA_TRY(cudaEventRecord(h->prof_events[0], s));
   }
   size_t first_layer = 0;
-  if (front_end_is_chunked(h)) {
+  if (front_end_is_fused(h)) {
+    // profile slots: the fused kernel is attributed to the stem's slot (quantize and maxpool read 0)
+    if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
+    if (int rc = launch_frontend_fused(h, static_cast<const float*>(x), n, s)) return rc;
+    if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[2], s));
+    first_layer = 2;
+  } else if (front_end_is_chunked(h)) {
     // profile slots: the whole interleaved front end is attributed to the stem's slot
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
     const LayerPlan& Ls = h->layers[0];
@@ -919,6 +990,8 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   h->in_scale = nd->in_scale; h->in_zp = nd->in_zp;
   if (const char* e = getenv("IEVM_HALO")) h->opt_halo = atoi(e);
   if (const char* e = getenv("IEVM_HALO_RB128")) h->opt_halo_rb128 = atoi(e);
+  if (const char* e = getenv("IEVM_FIXED_BN")) h->opt_fixed_bn = atoi(e);
+  if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
   if (const char* e = getenv("IEVM_FRONT_CHUNK")) h->front_chunk = atoi(e);
   int rc = plan_shapes(h, nd);
   for (size_t i = 0; rc == IEVM_OK && i < h->layers.size(); ++i) {
@@ -927,6 +1000,15 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
     else if (L.d.op == IEVM_OP_HEAD) rc = upload_head_operands(h, L);
     // host pointers in the copied descriptor must not be used after create returns
     L.d.weight = nullptr; L.d.bias = nullptr; L.d.w_scale = nullptr;
+  }
+  if (rc == IEVM_OK && getenv("IEVM_VERBOSE")) {
+    for (size_t i = 0; i < h->layers.size(); ++i) {
+      const LayerPlan& L = h->layers[i];
+      if (L.d.op != IEVM_OP_CONV || L.is_stem) continue;
+      fprintf(stderr, "[ievm] layer %2zu %dx%d s%d %4d->%4d @%dx%d mode=%s kc=%d kchunks=%d bn=%d n_tiles=%d stages=%d residentB=%d smem=%zu\n",
+              i, L.d.ksize, L.d.ksize, L.d.stride, L.d.cin, L.d.cout, L.ho, L.wo, L.mode == kModeHalo ? "halo" : "im2col",
+              L.kc_bytes, L.kchunks, L.bn, L.n_tiles, L.stages, L.resident_b, L.smem_bytes);
+    }
   }
   if (rc == IEVM_OK) rc = assign_buffers(h);
   if (rc == IEVM_OK) rc = encode_maps(h);
@@ -946,6 +1028,16 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
 #undef IEVM_ATTR
       if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
+  }
+  if (rc == IEVM_OK && h->dtype == IEVM_DTYPE_I8 && h->layers[0].is_stem && h->layers[0].cout_pad % 64 == 0) {
+    const int cp = h->layers[0].cout_pad;
+    h->fe_smem = 1024 + static_cast<size_t>(kFeStages) * 2 * kTileM * 128 + 2 * static_cast<size_t>(cp) * 128 +
+                 static_cast<size_t>(kFeRing) * kFeRowBytes + static_cast<size_t>(kFeDepth) * kFeRawBytes +
+                 (2 * 9 + 1) * 16 * static_cast<size_t>(cp) * 4 + 3 * static_cast<size_t>(cp) * 4 +
+                 (2 * kFeStages + 5) * 8 + 16;
+    if (h->fe_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) h->opt_fused_front = 0;
+    else if (cudaFuncSetAttribute(frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fe_smem) != cudaSuccess)
+      rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend_fused_kernel) failed");
   }
   if (rc == IEVM_OK) {
     for (const LayerPlan& L : h->layers)
@@ -1065,6 +1157,7 @@ int ievm_tensor_shape(const ievm_handle* h, int id, int32_t out6[6]) {
 int ievm_launches_per_forward(const ievm_handle* h) {
   if (!h) return 0;
   const int n = h->last_n > 0 ? h->last_n : h->max_batch;
+  if (front_end_is_fused(h)) return static_cast<int>(h->layers.size()) - 1;
   if (front_end_is_chunked(h)) return 3 * ((n + h->front_chunk - 1) / h->front_chunk) + static_cast<int>(h->layers.size()) - 2;
   return static_cast<int>(h->layers.size()) + (h->dtype == IEVM_DTYPE_I8 ? 1 : 0);
 }

@@ -13,17 +13,15 @@
 // zp * sum(w) (exact in int32) before the usual float requantisation.
 // Weights (cout_pad x 256 B) stay resident in shared memory; accumulators are double buffered in TMEM.
 //
-// Warp roles (544 threads): warp 0 = weights TMA + TMEM owner + MMA issuer, warps 1..8 = A builders in
-// two groups of four that alternate tiles (one output pixel per thread, all 28 loads of a tile row in
-// flight at once), warps 9..16 = epilogue.
+// Warp roles (800 threads): warp 0 = weights TMA + TMEM owner + MMA issuer, warps 1..8 = A builders
+// (thread = output pixel x k-block half, all its loads in flight at once), warps 9..24 = epilogue.
 #pragma once
 #include "conv_tc.cuh"
 #include "simt_kernels.cuh"
 
 namespace ievm {
 
-constexpr int kStemBuildGroups = 2;
-constexpr int kStemBuildWarps = 4 * kStemBuildGroups;
+constexpr int kStemBuildWarps = 8;          // 256 threads: thread = (tile row, k-block half)
 constexpr int kStemThreads = 32 * (1 + kStemBuildWarps + kEpiWarps);
 constexpr int kStemKBytes = 256;          // 8 segments x 32 B
 constexpr int kStemStages = 4;
@@ -78,7 +76,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemTcParams p)
     if (lane == 0) {
       tma_prefetch_desc(&tmap_w);
       for (int i = 0; i < kStemStages; ++i) {
-        mbar_init(&full_bar[i], 128);
+        mbar_init(&full_bar[i], kStemBuildWarps * 32);
         mbar_init(&empty_bar[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
@@ -112,11 +110,11 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemTcParams p)
       wait_or_die(&tempty_bar[acc], acc_phase ^ 1u, 0x610u | acc, p.stuck_flag);
       wait_or_die(&full_bar[stage], phase, 0x620u | stage, p.stuck_flag);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
-        const uint32_t hi = smem_desc_hi(128);
-        const uint32_t a_lo = smem_desc_lo(smem_u32(sA)) + static_cast<uint32_t>(stage) * (kAStage >> 4);
-        const uint32_t b_lo = smem_desc_lo(smem_u32(sB));
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
+      const uint32_t hi = smem_desc_hi(128);
+      const uint32_t a_lo = smem_desc_lo(smem_u32(sA)) + static_cast<uint32_t>(stage) * (kAStage >> 4);
+      const uint32_t b_lo = smem_desc_lo(smem_u32(sB));
+      if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
@@ -137,8 +135,12 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemTcParams p)
     }
   } else if (warp <= kStemBuildWarps) {
     // ================================ A builders ================================
-    const int group = (warp - 1) >> 2;                       // which builder group
-    const int r = ((warp - 1) & 3) * 32 + lane;              // tile row == output pixel
+    // 256 threads per tile: thread = (output pixel r, k-block kbh).  k-block 0 holds filter rows 0..3,
+    // k-block 1 rows 4..6 (+ the zero-weight segment, left unwritten).
+    const int bt = (warp - 1) * 32 + lane;
+    const int r = bt & 127;
+    const int kbh = bt >> 7;
+    const int nseg = kbh == 0 ? 4 : 3;
     const uint32_t sw = static_cast<uint32_t>(r & 7);         // 128B-swizzle phase of this row
     const uint2* in_pairs = reinterpret_cast<const uint2*>(p.xq);
     const int hp = p.h + kInPadH;
@@ -146,12 +148,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemTcParams p)
     uint32_t chunk_off[8];                                   // swizzled 16-byte chunk offsets of this row
 #pragma unroll
     for (int c = 0; c < 8; ++c) chunk_off[c] = ((static_cast<uint32_t>(c) ^ sw) << 4);
-    // Tile t (in this CTA's order) uses stage t % kStemStages; group g builds the tiles with t % 2 == g.
-    int t = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++t) {
-      if ((t & (kStemBuildGroups - 1)) != group) continue;
-      const int stage = t % kStemStages;
-      const uint32_t phase = static_cast<uint32_t>(t / kStemStages) & 1u;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
       const int m = min(tile * kTileM + r, p.m_total - 1);      // rows past the end rebuild the last pixel (discarded)
       const int img = m / hw;
       const int rem = m - img * hw;
@@ -159,28 +158,35 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemTcParams p)
       const int ox = rem - oy * p.wo;
       // Padded input (see quantize kernel): filter row ky of this pixel starts at padded row 2*oy + ky,
       // padded column 2*ox (= input column 2*ox - 4); 32 bytes = 4 aligned pixel pairs.
-      const uint2* src = in_pairs + (static_cast<size_t>(img) * hp + 2 * oy) * wp2 + ox;
-      uint2 q[7][4];
+      const uint2* src = in_pairs + (static_cast<size_t>(img) * hp + 2 * oy + 4 * kbh) * wp2 + ox;
+      uint2 q[4][4];
 #pragma unroll
-      for (int ky = 0; ky < 7; ++ky) {
+      for (int sg = 0; sg < 4; ++sg) {
+        if (sg < nseg) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) q[ky][j] = __ldg(src + ky * wp2 + j);
+          for (int j = 0; j < 4; ++j) q[sg][j] = __ldg(src + sg * wp2 + j);
+        }
       }
       wait_or_die(&empty_bar[stage], phase ^ 1u, 0x630u | stage, p.stuck_flag);
-      uint8_t* a_row = sA + stage * kAStage + r * 128;
+      uint8_t* blk = sA + stage * kAStage + kbh * kABlock + r * 128;
 #pragma unroll
-      for (int ky = 0; ky < 7; ++ky) {                         // segment 7 has zero weights: left unwritten
-        uint8_t* blk = a_row + (ky >> 2) * kABlock;
-        *reinterpret_cast<uint4*>(blk + chunk_off[(ky & 3) * 2]) = make_uint4(q[ky][0].x, q[ky][0].y, q[ky][1].x, q[ky][1].y);
-        *reinterpret_cast<uint4*>(blk + chunk_off[(ky & 3) * 2 + 1]) = make_uint4(q[ky][2].x, q[ky][2].y, q[ky][3].x, q[ky][3].y);
+      for (int sg = 0; sg < 4; ++sg) {
+        if (sg < nseg) {
+          *reinterpret_cast<uint4*>(blk + chunk_off[sg * 2]) = make_uint4(q[sg][0].x, q[sg][0].y, q[sg][1].x, q[sg][1].y);
+          *reinterpret_cast<uint4*>(blk + chunk_off[sg * 2 + 1]) = make_uint4(q[sg][2].x, q[sg][2].y, q[sg][3].x, q[sg][3].y);
+        }
       }
       fence_proxy_async_smem();                                // generic-proxy writes -> visible to the MMA
       mbar_arrive(&full_bar[stage]);
+      if (++stage == kStemStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
     }
   } else {
     // ================================ epilogue ================================
     const int quad = warp & 3;
-    const int half = (warp - 1 - kStemBuildWarps) >> 2;   // warps 9..16: quadrant = warp % 4, two warps each
+    const int half = (warp - 1 - kStemBuildWarps) >> 2;   // quadrant = warp % 4, kEpiSub warps each
     const int row = quad * 32 + lane;
     const int nchunks = p.cpad >> 4;
     int acc = 0;
@@ -192,7 +198,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemTcParams p)
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * p.acc_stride);
-      for (int c = half; c < nchunks; c += 2) {
+      for (int c = half; c < nchunks; c += kEpiSub) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), v);
         tmem_ld_wait();
