@@ -69,46 +69,68 @@ def max_over_ranks(value: float, device) -> float:
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled DURING the timed region (NVML poll every ~2 ms on a thread;
+    falls back to `nvidia-smi -lms` when NVML is unavailable)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop, self._thread, self._proc, self._rows = threading.Event(), None, None, []
+
+    def _poll_nvml(self, nv, handle):
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll_nvml, args=(nv, handle), daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._thread = None
+        try:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            self._proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                           "--format=csv,noheader,nounits", "-lms", "20"],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self._rows.append(l.strip()) for l in self._proc.stdout], daemon=True).start()
         except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self._proc = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            f = [c.strip() for c in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        busy = [v for v in sm if mx and v > 0.3 * mx] or sm
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        elif self._proc is not None:
+            time.sleep(0.05)
+            self._proc.terminate()
+            for r in self._rows:
+                f = [c.strip() for c in r.split(",")]
+                try:
+                    self.sm.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                except (ValueError, IndexError):
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(sm)}
 
 
@@ -283,6 +305,33 @@ def run_b200(args, rank, world, local_rank):
            "d2h_bytes_per_step": y_host.numel() * y_host.element_size(), "steps": e2e_steps,
            "how": "B200*ResNet.forward(cpu_tensor) -> ievm_forward_*_host: pinned H2D + forward + D2H per step"}
 
+    # ---- bs-1 latency (BASELINE.json: "p50 bs1 latency ms"; protocol of engines.py:26-34, synchronised) ----
+    latency = None
+    if rank == 0 and not args.no_latency:
+        cls = ievm_b200.B200QuantizedResNet if i8 else ievm_b200.B200HalfResNet
+        eng1 = (cls.from_converted if i8 else cls.from_half_module)(ref_mod, device=local_rank, max_batch=1)
+        eng1.set_option("use_graph", 1)
+        x1 = x[:1].contiguous()
+        for _ in range(10):
+            eng1(x1)
+        torch.cuda.synchronize(dev)
+        wall, devt = [], []
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(args.latency_runs):
+            t0 = time.perf_counter()
+            a.record()
+            eng1(x1)
+            b.record()
+            torch.cuda.synchronize(dev)
+            wall.append(1e3 * (time.perf_counter() - t0))
+            devt.append(a.elapsed_time(b))
+        wall.sort()
+        devt.sort()
+        latency = {"p50_ms": wall[len(wall) // 2], "mean_ms": sum(wall) / len(wall), "p99_ms": wall[int(len(wall) * 0.99)],
+                   "device_p50_ms": devt[len(devt) // 2], "runs": len(wall), "warmup": 10, "batch": 1,
+                   "how": "host wall clock around model(x1) + synchronize, input resident on device, CUDA graph replay"}
+        eng1.close()
+
     # logits gathered over NVLink for reporting only (not in the timed region)
     gathered = gather_logits(y.float(), world * n, rank, world)
 
@@ -326,7 +375,7 @@ def run_b200(args, rank, world, local_rank):
                                     "input batch 77 MB f16; activations stream through L2",
                        "cuda_graph": bool(args.graph)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": eng.launches_per_forward * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "latency_bs1": latency,
             "logits_checksum": float(gathered.double().sum().item()),
         }
     barrier()
@@ -348,6 +397,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=64, help="reference arm: images per CPU step (bounded sample)")
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--latency-runs", type=int, default=300)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

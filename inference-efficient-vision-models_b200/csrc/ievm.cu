@@ -140,6 +140,9 @@ struct ievm_handle {
   unsigned int* stuck_host = nullptr;  // mapped pinned word
   unsigned int* stuck_dev = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D copies of the *_host entry points
+  std::vector<cudaEvent_t> copy_events;
+  int host_chunk = 64;                  // IEVM_HOST_CHUNK: images per H2D/compute pipeline chunk (0 = no chunking)
   void* stage_in = nullptr;            // device staging for the *_host entry points
   void* stage_out = nullptr;
   void* pin_in = nullptr;              // pinned host staging
@@ -991,6 +994,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (const char* e = getenv("IEVM_HALO")) h->opt_halo = atoi(e);
   if (const char* e = getenv("IEVM_HALO_RB128")) h->opt_halo_rb128 = atoi(e);
   if (const char* e = getenv("IEVM_FIXED_BN")) h->opt_fixed_bn = atoi(e);
+  if (const char* e = getenv("IEVM_HOST_CHUNK")) h->host_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
   if (const char* e = getenv("IEVM_FRONT_CHUNK")) h->front_chunk = atoi(e);
   int rc = plan_shapes(h, nd);
@@ -1018,7 +1022,9 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
     if (max_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) rc = fail(IEVM_ERR_UNSUPPORTED, "smem plan exceeds device limit");
     if (rc == IEVM_OK && max_smem > 0) {
       cudaError_t e = cudaSuccess;
-      const int ms = static_cast<int>(max_smem);
+      // function attributes are process-wide: always raise the limit to the device maximum so that several
+      // engines with different plans can coexist
+      const int ms = static_cast<int>(prop.sharedMemPerBlockOptin);
 #define IEVM_ATTR(DT, RES, MODE) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<DT, RES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms)
       IEVM_ATTR(kDtypeI8, false, kModeIm2col); IEVM_ATTR(kDtypeI8, true, kModeIm2col);
@@ -1036,14 +1042,14 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
                  (2 * 9 + 1) * 16 * static_cast<size_t>(cp) * 4 + 3 * static_cast<size_t>(cp) * 4 +
                  (2 * kFeStages + 5) * 8 + 16;
     if (h->fe_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) h->opt_fused_front = 0;
-    else if (cudaFuncSetAttribute(frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fe_smem) != cudaSuccess)
+    else if (cudaFuncSetAttribute(frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) != cudaSuccess)
       rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend_fused_kernel) failed");
   }
   if (rc == IEVM_OK) {
     for (const LayerPlan& L : h->layers)
       if (L.stem_smem > 0) {
         if (L.stem_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) rc = fail(IEVM_ERR_UNSUPPORTED, "stem smem plan exceeds device limit");
-        else if (cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.stem_smem) != cudaSuccess)
+        else if (cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) != cudaSuccess)
           rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(stem_tc_kernel) failed");
       }
   }
@@ -1054,6 +1060,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
       e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->stuck_dev), h->stuck_host, 0);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "runtime setup: %s", cudaGetErrorString(e));
   }
   if (rc != IEVM_OK) {
@@ -1079,6 +1086,8 @@ void ievm_destroy(ievm_handle* h) {
   if (h->pin_out) cudaFreeHost(h->pin_out);
   if (h->stuck_host) cudaFreeHost(h->stuck_host);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
   delete h;
 }
 
@@ -1101,9 +1110,29 @@ static int forward_host_common(ievm_handle* h, int dtype, const void* x_host, in
     CUDA_TRY(cudaMalloc(&h->stage_in, per_img * h->max_batch));
     CUDA_TRY(cudaMalloc(&h->stage_out, out_elem * h->classes * h->max_batch));
   }
+  // Chunked pipeline: the H2D copy of chunk i+1 (copy stream) overlaps the forward of chunk i (compute
+  // stream); PCIe, not the GPU, bounds this entry point, so the chunk size only has to be large enough
+  // to keep the kernels efficient.
   cudaStream_t s = h->own_stream;
-  CUDA_TRY(cudaMemcpyAsync(h->stage_in, x_host, per_img * n, cudaMemcpyHostToDevice, s));
-  if (int rc = forward_common(h, dtype, h->stage_in, n, h->stage_out, s)) return rc;
+  const int chunk = (h->host_chunk > 0 && n > h->host_chunk) ? h->host_chunk : n;
+  const int nchunks = (n + chunk - 1) / chunk;
+  while (static_cast<int>(h->copy_events.size()) < nchunks) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->copy_events.push_back(e);
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    const int c0 = c * chunk, nc = std::min(chunk, n - c0);
+    CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(h->stage_in) + c0 * per_img,
+                             static_cast<const uint8_t*>(x_host) + c0 * per_img, per_img * nc, cudaMemcpyHostToDevice,
+                             nchunks > 1 ? h->copy_stream : s));
+    if (nchunks > 1) {
+      CUDA_TRY(cudaEventRecord(h->copy_events[c], h->copy_stream));
+      CUDA_TRY(cudaStreamWaitEvent(s, h->copy_events[c], 0));
+    }
+    if (int rc = forward_common(h, dtype, static_cast<uint8_t*>(h->stage_in) + c0 * per_img, nc,
+                                static_cast<uint8_t*>(h->stage_out) + c0 * out_elem * h->classes, s)) return rc;
+  }
   CUDA_TRY(cudaMemcpyAsync(logits_host, h->stage_out, out_elem * h->classes * n, cudaMemcpyDeviceToHost, s));
   return check_stuck(h, cudaStreamSynchronize(s), "forward (host buffers)");
 }
