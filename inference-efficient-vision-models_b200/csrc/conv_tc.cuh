@@ -58,6 +58,7 @@ struct ConvTcParams {
   // halo mode
   int h_in, w_in, wp;  // input height / width, wp = w_in + 2
   int tiles_per_img;
+  uint32_t tpi_magic, wp_magic, hw_magic, wo_magic;   // ceil(2^32 / d), or 0 = divide normally: see fast_div
   int tmem_cols;       // power of two >= 32 covering two accumulator buffers
   int acc_stride;      // column offset of the second accumulator buffer
   int cout_pad;        // n_tiles * bn
@@ -80,6 +81,12 @@ struct ConvTcParams {
   int dump_pitch;
   unsigned int* stuck_flag;   // mapped host word; written before a bounded wait gives up
 };
+
+// n / d.  magic = ceil(2^32 / d) is exact while n * d < 2^32; the host passes magic = 0 (plain division) when
+// the largest n of the launch could violate that, or when d == 1.
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
+  return magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), magic)) : n / d;
+}
 
 __device__ __forceinline__ void wait_or_die(uint64_t* bar, uint32_t parity, uint32_t code, unsigned int* flag) {
   if (mbar_try_wait(bar, parity)) return;
@@ -311,6 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  griddep_launch_dependents();          // the next kernel may begin its prologue as SMs free up
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int hw = p.ho * p.wo;
@@ -324,14 +332,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sB + kb * b_bytes, &tmap_b, bres_bar, kb * p.kc_elems, 0);
     }
     __syncwarp();
+    griddep_wait();                     // weights were loadable early; activations need the previous kernel done
     const uint32_t tx_bytes = static_cast<uint32_t>(p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       if (kMode == kModeHalo) {
-        const int img = tile / p.tiles_per_img;
+        const int img = fast_div(tile, p.tiles_per_img, p.tpi_magic);
         const int p0 = (tile - img * p.tiles_per_img) * kTileM;
-        const int oy_first = p0 / p.wp;
+        const int oy_first = fast_div(p0, p.wp, p.wp_magic);
         wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
         if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], tx_bytes);
@@ -347,9 +356,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
       const int m0 = m_tile * kTileM;
-      const int img = m0 / hw;
+      const int img = fast_div(m0, hw, p.hw_magic);
       const int rem = m0 - img * hw;
-      const int oy = rem / p.wo;
+      const int oy = fast_div(rem, p.wo, p.wo_magic);
       const int ox = rem - oy * p.wo;
       const int base_w = ox * p.stride - p.pad;
       const int base_h = oy * p.stride - p.pad;
@@ -413,8 +422,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
       if (kMode == kModeHalo) {
-        const int p0 = (tile % p.tiles_per_img) * kTileM;
-        const int x0 = p0 - (p0 / p.wp) * p.wp;
+        const int p0 = (tile - fast_div(tile, p.tiles_per_img, p.tpi_magic) * p.tiles_per_img) * kTileM;
+        const int x0 = p0 - fast_div(p0, p.wp, p.wp_magic) * p.wp;
         wait_or_die(&full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step + static_cast<uint32_t>(x0) * row16;
@@ -457,6 +466,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int half = (warp - 2) >> 2;        // 0 .. kEpiSub-1: which of the quadrant's warps
     const int row = quad * 32 + lane;
     const int nchunks = p.bn >> 4;
+    griddep_wait();                     // before the first residual read / output store
     AddReluConst k;
     k.lo_f = static_cast<float>(p.out_lo - p.out_zp);
     k.hi_f = static_cast<float>(255 - p.out_zp);
@@ -471,9 +481,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int m, n0;
       bool valid;
       if (kMode == kModeHalo) {
-        const int img = tile / p.tiles_per_img;
+        // warp-uniform divisions for the tile's first position, then a short walk to this thread's row
+        const int img = fast_div(tile, p.tiles_per_img, p.tpi_magic);
         const int pos = (tile - img * p.tiles_per_img) * kTileM + row;
-        const int oy = pos / p.wp;
+        const int oy = fast_div(pos, p.wp, p.wp_magic);
         const int x = pos - oy * p.wp;
         valid = x < p.w_in && oy < p.h_in;
         m = (img * p.h_in + oy) * p.w_in + x;

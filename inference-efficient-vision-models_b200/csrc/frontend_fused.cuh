@@ -123,6 +123,7 @@ frontend_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const Frontend
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  griddep_launch_dependents();
 
   const int units = p.n * p.strips;
   const int tps = p.tiles_per_strip;

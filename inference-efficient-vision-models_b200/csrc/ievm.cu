@@ -14,6 +14,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "conv_tc.cuh"
@@ -73,6 +74,25 @@ int load_driver_entry_points() {
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its
+// predecessor in the stream drains; it calls griddepcontrol.wait before touching the predecessor's output.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 struct TensorInfo {
   int h = 0, w = 0, c = 0, pitch = 0;   // pitch in elements
   int elem = 1;
@@ -122,6 +142,7 @@ struct ievm_handle {
   int opt_halo_rb128 = 0;
   int opt_fused_front = 1; // IEVM_FUSED_FRONT=0: separate quantize / stem / maxpool kernels
   size_t fe_smem = 0;
+  int opt_pdl = 1;         // IEVM_PDL=0: no programmatic dependent launch
   int opt_fixed_bn = 0;    // IEVM_FIXED_BN=1: one N tile per <=256 channels (disables the tile-width heuristic)
   int front_chunk = 0;     // IEVM_FRONT_CHUNK: images per front-end chunk (0 = whole batch at once, default)
   // IEVM_HALO_RB128=1: 64-byte pixels use 128-byte shared-memory rows in halo mode
@@ -302,7 +323,11 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
         if (L.cout_pad % bn != 0) continue;
         const long long tiles = m_tiles * (L.cout_pad / bn);
         const long long rounds = (tiles + h->num_sms - 1) / h->num_sms;
-        const long long tile_cycles = static_cast<long long>(num_kb_) * ksteps * std::max(bn / 2, 24) + 600 + 6LL * bn;
+        // a tile costs the slower of its MMAs (128 x bn x 32 B per instruction = bn/2 cycles) and the delivery of
+        // its operands from L2 (measured ~40 B/clk/SM when every SM streams: layers 3-4 sit on this bound)
+        const long long mma_cycles = static_cast<long long>(num_kb_) * ksteps * std::max(bn / 2, 24);
+        const long long load_cycles = static_cast<long long>(num_kb_) * (kTileM + bn) * L.kc_bytes / 40;
+        const long long tile_cycles = std::max(mma_cycles, load_cycles) + 600 + 6LL * bn;
         const long long cost = rounds * tile_cycles;
         if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best_bn)) {
           best_cost = cost;
@@ -615,6 +640,15 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   p.w_in = L.w;
   p.wp = L.wp;
   p.tiles_per_img = L.tiles_per_img;
+  // magic(d, n_max): ceil(2^32 / d) when every dividend n <= n_max satisfies n * d < 2^32, else 0 (plain division)
+  auto magic = [](long long d, long long n_max) {
+    return (d > 1 && n_max * d < 0x100000000ll) ? static_cast<uint32_t>((0x100000000ull + d - 1) / d) : 0u;
+  };
+  const long long tiles_max = L.mode == kModeHalo ? static_cast<long long>(n) * L.tiles_per_img : 0;
+  p.tpi_magic = magic(L.tiles_per_img, tiles_max);
+  p.wp_magic = magic(L.wp, static_cast<long long>(L.tiles_per_img) * kTileM + kTileM);
+  p.hw_magic = magic(static_cast<long long>(L.ho) * L.wo, static_cast<long long>(p.m_total) + kTileM);
+  p.wo_magic = magic(L.wo, static_cast<long long>(L.ho) * L.wo);
   p.cout_pad = L.cout_pad;
   p.tmem_cols = L.tmem_cols;
   p.acc_stride = L.tmem_cols / 2;
@@ -661,7 +695,7 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
   const int grid = std::min(p.m_tiles * p.n_tiles, h->num_sms);
   const bool has_res = p.res != nullptr;
 #define IEVM_LAUNCH(DT, RES, MODE) \
-  conv_tc_kernel<DT, RES, MODE><<<grid, kConvThreads, L.smem_bytes, s>>>(L.tmap_a, L.tmap_b, p)
+  CUDA_TRY(launch_kernel(conv_tc_kernel<DT, RES, MODE>, grid, kConvThreads, L.smem_bytes, s, h->opt_pdl != 0, L.tmap_a, L.tmap_b, p))
 #define IEVM_LAUNCH_MODE(DT, RES) \
   do { if (L.mode == kModeHalo) IEVM_LAUNCH(DT, RES, kModeHalo); else IEVM_LAUNCH(DT, RES, kModeIm2col); } while (0)
   if (h->dtype == IEVM_DTYPE_I8) {
@@ -849,14 +883,15 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
         hp.hw = tin.h * tin.w; hp.c = tin.c; hp.cpad = tin.pitch; hp.classes = d.cout; hp.in_zp = d.in_zp;
         hp.w = static_cast<const int8_t*>(L.w_packed); hp.bdiv = L.ep0; hp.mult = L.ep1;
         hp.fc_zp = d.out_zp; hp.fc_scale = d.out_scale;
-        head_i8_kernel<<<n, kHeadThreads, 0, s>>>(static_cast<const uint8_t*>(tensor_ptr(h, d.in_tensor)),
-                                                  static_cast<float*>(logits), nullptr, hp);
+        CUDA_TRY(launch_kernel(head_i8_kernel, n, kHeadThreads, 0, s, h->opt_pdl != 0,
+                               static_cast<const uint8_t*>(tensor_ptr(h, d.in_tensor)), static_cast<float*>(logits),
+                               static_cast<uint8_t*>(nullptr), hp));
       } else {
         HeadF16Params hp;
         hp.hw = tin.h * tin.w; hp.c = tin.c; hp.cpad = tin.pitch; hp.classes = d.cout;
         hp.w = static_cast<const __half*>(L.w_packed); hp.bias = L.ep0;
-        head_f16_kernel<<<n, kHeadThreads, 0, s>>>(static_cast<const __half*>(tensor_ptr(h, d.in_tensor)),
-                                                   static_cast<__half*>(logits), hp);
+        CUDA_TRY(launch_kernel(head_f16_kernel, n, kHeadThreads, 0, s, h->opt_pdl != 0,
+                               static_cast<const __half*>(tensor_ptr(h, d.in_tensor)), static_cast<__half*>(logits), hp));
       }
       CUDA_TRY(cudaGetLastError());
     }
@@ -994,6 +1029,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (const char* e = getenv("IEVM_HALO")) h->opt_halo = atoi(e);
   if (const char* e = getenv("IEVM_HALO_RB128")) h->opt_halo_rb128 = atoi(e);
   if (const char* e = getenv("IEVM_FIXED_BN")) h->opt_fixed_bn = atoi(e);
+  if (const char* e = getenv("IEVM_PDL")) h->opt_pdl = atoi(e);
   if (const char* e = getenv("IEVM_HOST_CHUNK")) h->host_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
   if (const char* e = getenv("IEVM_FRONT_CHUNK")) h->front_chunk = atoi(e);

@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(kHeadThreads)
 head_i8_kernel(const uint8_t* __restrict__ in, float* __restrict__ logits, uint8_t* __restrict__ pooled_dbg,
                const HeadParams p) {
   __shared__ int s_part[kHeadThreads / 32][kMaxClasses];
+  griddep_launch_dependents();
+  griddep_wait();
   const int img = blockIdx.x;
   const uint8_t* base = in + static_cast<long long>(img) * p.hw * p.cpad;
   int acc[kMaxClasses];
@@ -276,6 +278,8 @@ struct HeadF16Params {
 __global__ void __launch_bounds__(kHeadThreads)
 head_f16_kernel(const __half* __restrict__ in, __half* __restrict__ logits, const HeadF16Params p) {
   __shared__ float s_part[kHeadThreads / 32][kMaxClasses];
+  griddep_launch_dependents();
+  griddep_wait();
   const int img = blockIdx.x;
   const __half* base = in + static_cast<long long>(img) * p.hw * p.cpad;
   float acc[kMaxClasses];
