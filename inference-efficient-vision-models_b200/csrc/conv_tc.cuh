@@ -265,7 +265,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
   }
 }
 
-template <int kDtype, bool kHasRes, int kMode>
+// kCluster > 1 (im2col mode, streamed weights): kCluster CTAs take consecutive M tiles of the same N tile and
+// each loads 1/kCluster of every weight k-block, multicast into all of them -- the layers with deep K
+// (layers 3-4) are bound by L2->SM operand delivery, and this removes (kCluster-1)/kCluster of the B traffic.
+template <int kDtype, bool kHasRes, int kMode, int kCluster>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const ConvTcParams p) {
@@ -296,12 +299,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     s_ep0[i] = p.ep0[i];
     s_ep1[i] = p.ep1[i];
   }
+  const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << kCluster) - 1u);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], kCluster);    // every CTA that reads the multicast stage releases it everywhere
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -316,11 +321,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();     // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   griddep_launch_dependents();          // the next kernel may begin its prologue as SMs free up
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // Tile schedule.  Work item `tile` of stride `tile_step` starting at `tile_first`:
+  //   single CTA : tile -> (m_tile = tile / n_tiles, n_tile = tile % n_tiles)
+  //   cluster    : tile is a cluster tile -> (m_tile = (tile / n_tiles) * kCluster + rank, n_tile = tile % n_tiles)
+  const int total_tiles = kCluster > 1 ? ((p.m_tiles + kCluster - 1) / kCluster) * p.n_tiles : p.m_tiles * p.n_tiles;
+  const int tile_first = kCluster > 1 ? static_cast<int>(blockIdx.x) / kCluster : static_cast<int>(blockIdx.x);
+  const int tile_step = kCluster > 1 ? static_cast<int>(gridDim.x) / kCluster : static_cast<int>(gridDim.x);
   const int hw = p.ho * p.wo;
 
   if (warp == 0) {
@@ -336,7 +347,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t tx_bytes = static_cast<uint32_t>(p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       if (kMode == kModeHalo) {
         const int img = fast_div(tile, p.tiles_per_img, p.tpi_magic);
         const int p0 = (tile - img * p.tiles_per_img) * kTileM;
@@ -353,8 +364,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         continue;
       }
-      const int m_tile = tile / p.n_tiles;
-      const int n_tile = tile - m_tile * p.n_tiles;
+      const int m_group = tile / p.n_tiles;
+      const int n_tile = tile - m_group * p.n_tiles;
+      const int m_tile = kCluster > 1 ? m_group * kCluster + static_cast<int>(crank) : m_group;
       const int m0 = m_tile * kTileM;
       const int img = fast_div(m0, hw, p.hw_magic);
       const int rem = m0 - img * hw;
@@ -371,8 +383,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               mbar_expect_tx(&full_bar[stage], tx_bytes);
               tma_load_im2col_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h, img,
                                  static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
-              if (!p.resident_b)
+              if (kCluster > 1) {
+                const int slice = p.bn / kCluster;          // rows of the weight tile this CTA fetches for everyone
+                tma_load_2d_multicast(sB + stage * b_bytes + static_cast<int>(crank) * slice * p.kc_bytes, &tmap_b,
+                                      &full_bar[stage], kb * p.kc_elems, n_tile * p.bn + static_cast<int>(crank) * slice,
+                                      kClusterMask);
+              } else if (!p.resident_b) {
                 tma_load_2d(sB + stage * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems, n_tile * p.bn);
+              }
             }
             __syncwarp();
             if (++stage == p.stages) {
@@ -417,7 +435,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>((tap / 3) * p.wp + (tap % 3)) * row16;
     if (p.resident_b) wait_or_die(bres_bar, 0, 0x500u, p.stuck_flag);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       wait_or_die(&tempty_bar[acc], acc_phase ^ 1u, 0x200u | acc, p.stuck_flag);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
@@ -447,7 +465,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(p.resident_b ? kb : stage) * b_step;
           if (elect_one()) {
             mma_kblock(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
-            umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
+            if (kCluster > 1) umma_commit_multicast(&empty_bar[stage], kClusterMask);
+            else umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
             if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
           }
           __syncwarp();
@@ -477,7 +496,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     k.add_zp = p.add_zp;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       int m, n0;
       bool valid;
       if (kMode == kModeHalo) {
@@ -490,8 +509,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         m = (img * p.h_in + oy) * p.w_in + x;
         n0 = 0;
       } else {
-        const int m_tile = tile / p.n_tiles;
-        const int n_tile = tile - m_tile * p.n_tiles;
+        const int m_group = tile / p.n_tiles;
+        const int n_tile = tile - m_group * p.n_tiles;
+        const int m_tile = kCluster > 1 ? m_group * kCluster + static_cast<int>(crank) : m_group;
         m = m_tile * kTileM + row;
         valid = m < p.m_total;
         n0 = n_tile * p.bn;
@@ -535,6 +555,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();     // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));

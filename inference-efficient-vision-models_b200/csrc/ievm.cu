@@ -77,20 +77,36 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may begin while its
 // predecessor in the stream drains; it calls griddepcontrol.wait before touching the predecessor's output.
 template <typename... KArgs, typename... Args>
-cudaError_t launch_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl,
-                          Args&&... args) {
+cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s,
+                                  bool pdl, unsigned cluster, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl,
+                          Args&&... args) {
+  return launch_kernel_cluster(kernel, grid, block, smem, s, pdl, 1u, std::forward<Args>(args)...);
 }
 
 struct TensorInfo {
@@ -115,6 +131,8 @@ struct LayerPlan {
   int kc_bytes = 0, kc_elems = 0, kchunks = 0, cin_w = 0;
   int stages = 0, tmem_cols = 0, resident_b = 0;
   int mode = 0;                 // kModeIm2col | kModeHalo
+  int cluster = 1;              // CTAs per cluster sharing the weight tile by TMA multicast
+  int max_clusters = 0;         // co-resident clusters the device can hold (cluster > 1)
   int wp = 0, patch_rows = 0, tiles_per_img = 0, a_stage_bytes = 0, a_tx_bytes = 0;
   size_t smem_bytes = 0;
   // device operands
@@ -142,6 +160,7 @@ struct ievm_handle {
   int opt_halo_rb128 = 0;
   int opt_fused_front = 1; // IEVM_FUSED_FRONT=0: separate quantize / stem / maxpool kernels
   size_t fe_smem = 0;
+  int opt_cluster = 1;     // IEVM_CLUSTER=0: no 2-CTA clusters / weight multicast
   int opt_pdl = 1;         // IEVM_PDL=0: no programmatic dependent launch
   int opt_fixed_bn = 0;    // IEVM_FIXED_BN=1: one N tile per <=256 channels (disables the tile-width heuristic)
   int front_chunk = 0;     // IEVM_FRONT_CHUNK: images per front-end chunk (0 = whole batch at once, default)
@@ -318,24 +337,33 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
       const int ksteps = L.kc_bytes / 32;
       const long long m_tiles = (static_cast<long long>(h->max_batch) * L.ho * L.wo + kTileM - 1) / kTileM;
       long long best_cost = -1;
-      int best_bn = L.bn;
+      int best_bn = L.bn, best_cluster = 1;
       for (int bn = 16; bn <= 256; bn += 16) {
         if (L.cout_pad % bn != 0) continue;
-        const long long tiles = m_tiles * (L.cout_pad / bn);
-        const long long rounds = (tiles + h->num_sms - 1) / h->num_sms;
-        // a tile costs the slower of its MMAs (128 x bn x 32 B per instruction = bn/2 cycles) and the delivery of
-        // its operands from L2 (measured ~40 B/clk/SM when every SM streams: layers 3-4 sit on this bound)
-        const long long mma_cycles = static_cast<long long>(num_kb_) * ksteps * std::max(bn / 2, 24);
-        const long long load_cycles = static_cast<long long>(num_kb_) * (kTileM + bn) * L.kc_bytes / 40;
-        const long long tile_cycles = std::max(mma_cycles, load_cycles) + 600 + 6LL * bn;
-        const long long cost = rounds * tile_cycles;
-        if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best_bn)) {
-          best_cost = cost;
-          best_bn = bn;
+        const int ntl = L.cout_pad / bn;
+        const bool resident = ntl == 1 && num_kb_ * bn * L.kc_bytes + 4 * kTileM * L.kc_bytes <= avail;
+        for (int cl = 1; cl <= (h->opt_cluster && !resident ? 2 : 1); ++cl) {
+          if (cl > 1 && ((bn / cl) % 8 != 0 || m_tiles < 2 * cl)) continue;
+          const long long tiles = ((m_tiles + cl - 1) / cl) * ntl;              // cluster tiles
+          const long long rounds = (tiles + h->num_sms / cl - 1) / (h->num_sms / cl);
+          // a tile costs the slower of its MMAs (128 x bn x 32 B per instruction = bn/2 cycles) and the delivery of
+          // its operands from L2 (measured ~40 B/clk/SM when every SM streams: layers 3-4 sit on this bound);
+          // resident weights are loaded once, multicast splits the weight tile over the cluster
+          const long long mma_cycles = static_cast<long long>(num_kb_) * ksteps * std::max(bn / 2, 24);
+          const long long b_rows = resident ? 0 : bn / cl;
+          const long long load_cycles = static_cast<long long>(num_kb_) * (kTileM + b_rows) * L.kc_bytes / 40;
+          const long long tile_cycles = std::max(mma_cycles, load_cycles) + 600 + 6LL * bn;
+          const long long cost = rounds * tile_cycles;
+          if (best_cost < 0 || cost < best_cost || (cost == best_cost && bn > best_bn)) {
+            best_cost = cost;
+            best_bn = bn;
+            best_cluster = cl;
+          }
         }
       }
       if (!h->opt_fixed_bn) {
         L.bn = best_bn;
+        L.cluster = best_cluster;
         L.n_tiles = L.cout_pad / L.bn;
         L.tmem_cols = 32;
         while (L.tmem_cols < 2 * L.bn) L.tmem_cols *= 2;
@@ -346,6 +374,7 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
     const int num_kb = d.ksize * d.ksize * L.kchunks;
     L.a_stage_bytes = L.a_tx_bytes = a_bytes;
     L.resident_b = (L.n_tiles == 1 && num_kb * b_bytes + 4 * a_bytes <= avail) ? 1 : 0;
+    if (L.resident_b) L.cluster = 1;
     if (L.resident_b) L.stages = std::min(kMaxStages, (avail - num_kb * b_bytes) / a_bytes);
     else L.stages = std::min(kMaxStages, avail / (a_bytes + b_bytes));
     if (L.stages < 2) return fail(IEVM_ERR_UNSUPPORTED, "layer %d: tile does not fit in shared memory", i);
@@ -602,7 +631,7 @@ int encode_maps(ievm_handle* h) {
       const size_t k_total = static_cast<size_t>(L.d.ksize) * L.d.ksize * L.cin_w;
       cuuint64_t dims[2] = {k_total, static_cast<cuuint64_t>(L.cout_pad)};
       cuuint64_t strides[1] = {k_total * e};
-      cuuint32_t box[2] = {static_cast<cuuint32_t>(L.kc_elems), static_cast<cuuint32_t>(L.bn)};
+      cuuint32_t box[2] = {static_cast<cuuint32_t>(L.kc_elems), static_cast<cuuint32_t>(L.bn / L.cluster)};
       cuuint32_t estr[2] = {1, 1};
       const CUresult r = g_encode_tiled(&L.tmap_b, dt, 2, L.w_packed, dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -647,7 +676,7 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   const long long tiles_max = L.mode == kModeHalo ? static_cast<long long>(n) * L.tiles_per_img : 0;
   p.tpi_magic = magic(L.tiles_per_img, tiles_max);
   p.wp_magic = magic(L.wp, static_cast<long long>(L.tiles_per_img) * kTileM + kTileM);
-  p.hw_magic = magic(static_cast<long long>(L.ho) * L.wo, static_cast<long long>(p.m_total) + kTileM);
+  p.hw_magic = magic(static_cast<long long>(L.ho) * L.wo, static_cast<long long>(p.m_total) + 4 * kTileM);
   p.wo_magic = magic(L.wo, static_cast<long long>(L.ho) * L.wo);
   p.cout_pad = L.cout_pad;
   p.tmem_cols = L.tmem_cols;
@@ -692,12 +721,22 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
     CUDA_TRY(cudaGetLastError());
     return IEVM_OK;
   }
-  const int grid = std::min(p.m_tiles * p.n_tiles, h->num_sms);
   const bool has_res = p.res != nullptr;
-#define IEVM_LAUNCH(DT, RES, MODE) \
-  CUDA_TRY(launch_kernel(conv_tc_kernel<DT, RES, MODE>, grid, kConvThreads, L.smem_bytes, s, h->opt_pdl != 0, L.tmap_a, L.tmap_b, p))
-#define IEVM_LAUNCH_MODE(DT, RES) \
-  do { if (L.mode == kModeHalo) IEVM_LAUNCH(DT, RES, kModeHalo); else IEVM_LAUNCH(DT, RES, kModeIm2col); } while (0)
+  const unsigned cl = static_cast<unsigned>(L.cluster);
+  int grid = std::min(p.m_tiles * p.n_tiles, h->num_sms);
+  if (cl > 1) {
+    const int cluster_tiles = ((p.m_tiles + L.cluster - 1) / L.cluster) * p.n_tiles;
+    grid = std::min(cluster_tiles, L.max_clusters > 0 ? L.max_clusters : h->num_sms / L.cluster) * L.cluster;
+  }
+#define IEVM_LAUNCH(DT, RES, MODE, CL) \
+  CUDA_TRY(launch_kernel_cluster(conv_tc_kernel<DT, RES, MODE, CL>, grid, kConvThreads, L.smem_bytes, s, h->opt_pdl != 0, \
+                                 static_cast<unsigned>(CL), L.tmap_a, L.tmap_b, p))
+#define IEVM_LAUNCH_MODE(DT, RES)                                        \
+  do {                                                                   \
+    if (L.mode == kModeHalo) IEVM_LAUNCH(DT, RES, kModeHalo, 1);         \
+    else if (cl == 2) IEVM_LAUNCH(DT, RES, kModeIm2col, 2);              \
+    else IEVM_LAUNCH(DT, RES, kModeIm2col, 1);                           \
+  } while (0)
   if (h->dtype == IEVM_DTYPE_I8) {
     if (has_res) IEVM_LAUNCH_MODE(kDtypeI8, true); else IEVM_LAUNCH_MODE(kDtypeI8, false);
   } else {
@@ -1030,6 +1069,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (const char* e = getenv("IEVM_HALO_RB128")) h->opt_halo_rb128 = atoi(e);
   if (const char* e = getenv("IEVM_FIXED_BN")) h->opt_fixed_bn = atoi(e);
   if (const char* e = getenv("IEVM_PDL")) h->opt_pdl = atoi(e);
+  if (const char* e = getenv("IEVM_CLUSTER")) h->opt_cluster = atoi(e);
   if (const char* e = getenv("IEVM_HOST_CHUNK")) h->host_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
   if (const char* e = getenv("IEVM_FRONT_CHUNK")) h->front_chunk = atoi(e);
@@ -1045,9 +1085,9 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
     for (size_t i = 0; i < h->layers.size(); ++i) {
       const LayerPlan& L = h->layers[i];
       if (L.d.op != IEVM_OP_CONV || L.is_stem) continue;
-      fprintf(stderr, "[ievm] layer %2zu %dx%d s%d %4d->%4d @%dx%d mode=%s kc=%d kchunks=%d bn=%d n_tiles=%d stages=%d residentB=%d smem=%zu\n",
+      fprintf(stderr, "[ievm] layer %2zu %dx%d s%d %4d->%4d @%dx%d mode=%s kc=%d kchunks=%d bn=%d n_tiles=%d cluster=%d stages=%d residentB=%d smem=%zu\n",
               i, L.d.ksize, L.d.ksize, L.d.stride, L.d.cin, L.d.cout, L.ho, L.wo, L.mode == kModeHalo ? "halo" : "im2col",
-              L.kc_bytes, L.kchunks, L.bn, L.n_tiles, L.stages, L.resident_b, L.smem_bytes);
+              L.kc_bytes, L.kchunks, L.bn, L.n_tiles, L.cluster, L.stages, L.resident_b, L.smem_bytes);
     }
   }
   if (rc == IEVM_OK) rc = assign_buffers(h);
@@ -1061,14 +1101,36 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
       // function attributes are process-wide: always raise the limit to the device maximum so that several
       // engines with different plans can coexist
       const int ms = static_cast<int>(prop.sharedMemPerBlockOptin);
-#define IEVM_ATTR(DT, RES, MODE) \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<DT, RES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms)
-      IEVM_ATTR(kDtypeI8, false, kModeIm2col); IEVM_ATTR(kDtypeI8, true, kModeIm2col);
-      IEVM_ATTR(kDtypeI8, false, kModeHalo);   IEVM_ATTR(kDtypeI8, true, kModeHalo);
-      IEVM_ATTR(kDtypeF16, false, kModeIm2col); IEVM_ATTR(kDtypeF16, true, kModeIm2col);
-      IEVM_ATTR(kDtypeF16, false, kModeHalo);   IEVM_ATTR(kDtypeF16, true, kModeHalo);
+#define IEVM_ATTR(DT, RES, MODE, CL) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<DT, RES, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms)
+      IEVM_ATTR(kDtypeI8, false, kModeIm2col, 1); IEVM_ATTR(kDtypeI8, true, kModeIm2col, 1);
+      IEVM_ATTR(kDtypeI8, false, kModeIm2col, 2); IEVM_ATTR(kDtypeI8, true, kModeIm2col, 2);
+      IEVM_ATTR(kDtypeI8, false, kModeHalo, 1);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1);
+      IEVM_ATTR(kDtypeF16, false, kModeIm2col, 1); IEVM_ATTR(kDtypeF16, true, kModeIm2col, 1);
+      IEVM_ATTR(kDtypeF16, false, kModeIm2col, 2); IEVM_ATTR(kDtypeF16, true, kModeIm2col, 2);
+      IEVM_ATTR(kDtypeF16, false, kModeHalo, 1);   IEVM_ATTR(kDtypeF16, true, kModeHalo, 1);
 #undef IEVM_ATTR
       if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      // how many 2-CTA clusters of the heaviest configuration can be co-resident (GPC packing may strand SMs)
+      for (LayerPlan& L : h->layers) {
+        if (rc != IEVM_OK || L.cluster <= 1) continue;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(h->num_sms / L.cluster * L.cluster);
+        cfg.blockDim = dim3(kConvThreads);
+        cfg.dynamicSmemBytes = L.smem_bytes;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = L.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int nc = 0;
+        const cudaError_t qe = h->dtype == IEVM_DTYPE_I8
+            ? cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<kDtypeI8, false, kModeIm2col, 2>, &cfg)
+            : cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<kDtypeF16, false, kModeIm2col, 2>, &cfg);
+        L.max_clusters = (qe == cudaSuccess && nc > 0) ? std::min(nc, h->num_sms / L.cluster) : h->num_sms / L.cluster;
+        if (qe != cudaSuccess) cudaGetLastError();
+      }
     }
   }
   if (rc == IEVM_OK && h->dtype == IEVM_DTYPE_I8 && h->layers[0].is_stem && h->layers[0].cout_pad % 64 == 0) {

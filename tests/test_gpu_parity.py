@@ -46,6 +46,18 @@ def _swizzle(tile, kc):
     return out.reshape(rows, kc)
 
 
+def _swizzle_rows(rows, kc):
+    """Same XOR pattern for an arbitrary number of rows (swizzle follows the row's address bits)."""
+    n, chunks = rows.shape[0], kc // 16
+    t = rows.reshape(n, chunks, 16)
+    out = np.empty_like(t)
+    for r in range(n):
+        x = (r % 8) if kc == 128 else ((r // 2) % 4)
+        for j in range(chunks):
+            out[r, j ^ x] = t[r, j]
+    return out.reshape(n, kc)
+
+
 def _expected_im2col(x, ksize, stride, pad, kc, m0, tx, ty, c0):
     n, h, w, cp = x.shape
     ho, wo = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
@@ -193,6 +205,49 @@ def test_batch_sharding_is_bitwise_invariant():
     parts = torch.cat([eng(x[i:i + 8]).clone() for i in range(0, 32, 8)])
     assert torch.equal(whole, parts)
     eng.close()
+
+
+def test_int8_batch_size_invariance_up_to_1024():
+    """Size-independent property at full batch sizes: an image's logits do not depend on the batch it rides in
+    (ragged M tiles, tile-width heuristic, fused front-end strips, halo tiles all change with N)."""
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=1024)
+    x = mf.synthetic_images(1024, seed=99).cuda()
+    full = eng(x).clone()
+    for n in (1, 3, 64, 255, 256, 777):
+        assert torch.equal(eng(x[:n]), full[:n]), f"batch {n} differs from batch 1024"
+    # and against the CPU fbgemm module on a slice
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    torch.backends.quantized.engine = "fbgemm"
+    with torch.no_grad():
+        ref = gm(x[1000:1024].cpu())
+    assert torch.equal(full[1000:1024].cpu(), ref)
+    eng.close()
+
+
+@pytest.mark.parametrize("case", [
+    dict(h=56, w=56, cp=64, rb=64, bw=58, bh=6, w0=-1, h0=-1),
+    dict(h=28, w=28, cp=128, rb=128, bw=30, bh=8, w0=-1, h0=3),
+    dict(h=56, w=56, cp=64, rb=128, bw=58, bh=6, w0=-1, h0=53),      # channel over-read + past the bottom edge
+])
+def test_tma_halo_patch_layout(case):
+    """The halo-mode convolution relies on a tiled 4-D TMA box landing as a swizzled *linear* run of pixels with
+    zero-filled borders (ievm_probe_patch)."""
+    from ievm_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    h, w, cp, rb, bw, bh, w0, h0 = (case[k] for k in ("h", "w", "cp", "rb", "bw", "bh", "w0", "h0"))
+    x = rng.integers(1, 255, size=(2, h, w, cp), dtype=np.uint8)
+    xd = torch.from_numpy(x).cuda()
+    out = torch.zeros(bw * bh * rb, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.ievm_probe_patch(xd.data_ptr(), 2, h, w, cp, rb, 1, w0, h0, bw, bh, out.data_ptr()), "probe_patch")
+    got = out.cpu().numpy().reshape(bh * bw, rb)
+    exp = np.zeros((bh, bw, rb), np.uint8)
+    for r in range(bh):
+        for c in range(bw):
+            iy, ix = h0 + r, w0 + c
+            if 0 <= iy < h and 0 <= ix < w:
+                exp[r, c, :min(cp, rb)] = x[1, iy, ix, :rb]
+    assert np.array_equal(got, _swizzle_rows(exp.reshape(bh * bw, rb), rb))
 
 
 # ------------------------------------------------------------------------------------------ FP16 parity
