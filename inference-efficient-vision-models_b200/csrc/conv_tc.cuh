@@ -265,9 +265,12 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
   }
 }
 
-// kCluster > 1 (im2col mode, streamed weights): kCluster CTAs take consecutive M tiles of the same N tile and
-// each loads 1/kCluster of every weight k-block, multicast into all of them -- the layers with deep K
-// (layers 3-4) are bound by L2->SM operand delivery, and this removes (kCluster-1)/kCluster of the B traffic.
+// kCluster == 2 (im2col mode, streamed weights): a CTA PAIR runs one tcgen05.mma.cta_group::2 per k-step over
+// M = 256 (two consecutive M tiles) x N = bn.  Each CTA loads its own 128 A rows and only HALF of the weight
+// k-block (bn/2 rows) into its own shared memory; the tensor cores of both SMs read both halves.  The layers with
+// deep K (layers 3-4) are bound by how fast an SM can ingest operands (~40 B/clk), and the pair ingests
+// (128 + bn/2) instead of (128 + bn) rows per k-block for the same MMA work.  Only the leader (even) CTA issues
+// MMAs; full barriers live in the leader, empty / tmem-full barriers are signalled in both CTAs by the commit.
 template <int kDtype, bool kHasRes, int kMode, int kCluster>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -279,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int num_kb = p.ksize * p.ksize * p.kchunks;
   const int a_bytes = p.a_stage_bytes;
-  const int b_bytes = p.bn * p.kc_bytes;
+  const int b_bytes = (p.bn / kCluster) * p.kc_bytes;      // a pair CTA holds half of the weight k-block
   const int b_slots = p.resident_b ? num_kb : p.stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * a_bytes;
@@ -300,28 +303,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     s_ep1[i] = p.ep1[i];
   }
   const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
-  constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << kCluster) - 1u);
+  const bool leader = crank == 0;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], kCluster);    // every CTA that reads the multicast stage releases it everywhere
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);   // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], kCluster * kEpiWarps);   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
-    tmem_relinquish();
+    if (kCluster > 1) {
+      tmem_alloc_pair(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();     // peers' barriers are initialised before anyone signals them
+  if (kCluster > 1) cluster_sync_all();     // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   griddep_launch_dependents();          // the next kernel may begin its prologue as SMs free up
@@ -380,16 +388,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int ch = 0; ch < p.kchunks; ++ch, ++kb) {
             wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
             if (elect_one()) {
-              mbar_expect_tx(&full_bar[stage], tx_bytes);
-              tma_load_im2col_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h, img,
-                                 static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
               if (kCluster > 1) {
-                const int slice = p.bn / kCluster;          // rows of the weight tile this CTA fetches for everyone
-                tma_load_2d_multicast(sB + stage * b_bytes + static_cast<int>(crank) * slice * p.kc_bytes, &tmap_b,
-                                      &full_bar[stage], kb * p.kc_elems, n_tile * p.bn + static_cast<int>(crank) * slice,
-                                      kClusterMask);
-              } else if (!p.resident_b) {
-                tma_load_2d(sB + stage * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems, n_tile * p.bn);
+                // both CTAs fill their own stage and complete bytes on the leader's barrier; the leader arms it
+                // for the pair's total
+                if (leader) mbar_expect_tx(&full_bar[stage], 2u * tx_bytes);
+                tma_load_im2col_4d_pair(sA + stage * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h,
+                                        img, static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
+                tma_load_2d_pair(sB + stage * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems,
+                                 n_tile * p.bn + static_cast<int>(crank) * (p.bn / kCluster));
+              } else {
+                mbar_expect_tx(&full_bar[stage], tx_bytes);
+                tma_load_im2col_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h, img,
+                                   static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
+                if (!p.resident_b)
+                  tma_load_2d(sB + stage * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems, n_tile * p.bn);
               }
             }
             __syncwarp();
@@ -420,8 +432,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t row16 = static_cast<uint32_t>(p.kc_bytes) >> 4;      // one pixel row in 16-byte units
     const uint32_t idesc = p.idesc;
     auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t accum) {
-      if (kDtype == kDtypeI8) umma_i8_lohi(d, a_lo, b_lo, hi, idesc, accum);
-      else umma_f16_lohi(d, a_lo, b_lo, hi, idesc, accum);
+      if (kCluster > 1) {
+        if (kDtype == kDtypeI8) umma_i8_lohi_pair(d, a_lo, b_lo, hi, idesc, accum);
+        else umma_f16_lohi_pair(d, a_lo, b_lo, hi, idesc, accum);
+      } else {
+        if (kDtype == kDtypeI8) umma_i8_lohi(d, a_lo, b_lo, hi, idesc, accum);
+        else umma_f16_lohi(d, a_lo, b_lo, hi, idesc, accum);
+      }
     };
     auto mma_kblock = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t first_accum) {
       mma(d, a_lo, b_lo, first_accum);
@@ -435,7 +452,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>((tap / 3) * p.wp + (tap % 3)) * row16;
     if (p.resident_b) wait_or_die(bres_bar, 0, 0x500u, p.stuck_flag);
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+    for (int tile = tile_first; leader && tile < total_tiles; tile += tile_step) {   // the peer CTA issues no MMAs
       wait_or_die(&tempty_bar[acc], acc_phase ^ 1u, 0x200u | acc, p.stuck_flag);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
@@ -465,9 +482,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(p.resident_b ? kb : stage) * b_step;
           if (elect_one()) {
             mma_kblock(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
-            if (kCluster > 1) umma_commit_multicast(&empty_bar[stage], kClusterMask);
-            else umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
-            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+            if (kCluster > 1) {
+              umma_commit_pair(&empty_bar[stage]);          // frees the stage in both CTAs
+              if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[acc]);
+            } else {
+              umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
+              if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+            }
           }
           __syncwarp();
           if (++stage == p.stages) {
@@ -547,7 +568,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (kCluster > 1 && !leader) mbar_arrive_remote(&tempty_bar[acc], 0u);   // the leader's MMA warp waits for both
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -555,10 +579,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();     // no CTA leaves while a peer may still signal its barriers
+  if (kCluster > 1) cluster_sync_all();     // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    if (kCluster > 1) tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    else tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
 }
 

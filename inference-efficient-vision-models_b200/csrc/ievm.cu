@@ -370,11 +370,12 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
       }
     }
     // shared-memory plan: [A stages][B stages | all B k-blocks][epilogue tables][barriers]
-    const int a_bytes = kTileM * L.kc_bytes, b_bytes = L.bn * L.kc_bytes;
+    const int a_bytes = kTileM * L.kc_bytes;
     const int num_kb = d.ksize * d.ksize * L.kchunks;
     L.a_stage_bytes = L.a_tx_bytes = a_bytes;
-    L.resident_b = (L.n_tiles == 1 && num_kb * b_bytes + 4 * a_bytes <= avail) ? 1 : 0;
+    L.resident_b = (L.n_tiles == 1 && num_kb * L.bn * L.kc_bytes + 4 * a_bytes <= avail) ? 1 : 0;
     if (L.resident_b) L.cluster = 1;
+    const int b_bytes = (L.bn / L.cluster) * L.kc_bytes;      // a pair CTA holds half of each weight k-block
     if (L.resident_b) L.stages = std::min(kMaxStages, (avail - num_kb * b_bytes) / a_bytes);
     else L.stages = std::min(kMaxStages, avail / (a_bytes + b_bytes));
     if (L.stages < 2) return fail(IEVM_ERR_UNSUPPORTED, "layer %d: tile does not fit in shared memory", i);
@@ -681,7 +682,8 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   p.cout_pad = L.cout_pad;
   p.tmem_cols = L.tmem_cols;
   p.acc_stride = L.tmem_cols / 2;
-  p.idesc = h->dtype == IEVM_DTYPE_I8 ? make_idesc_i8_u8s8(L.bn) : make_idesc_f16(L.bn);
+  const int mma_m = L.cluster > 1 ? 256 : 128;             // a CTA pair issues M = 256 instructions
+  p.idesc = h->dtype == IEVM_DTYPE_I8 ? make_idesc_i8_u8s8(L.bn, mma_m) : make_idesc_f16(L.bn, mma_m);
   p.out = tensor_ptr(h, d.out_tensor);
   p.out_pitch = L.cout_pad;
   p.res = d.res_tensor >= 0 ? tensor_ptr(h, d.res_tensor) : nullptr;
