@@ -129,6 +129,12 @@ int ievm_debug_read_tensor(ievm_handle* h, int id, void* host_out, uint64_t host
  * raw accumulators (int32 for I8, fp32 bits for F16) as [n*ho*wo][c_pitch] to the host. */
 int ievm_debug_conv_acc(ievm_handle* h, int layer, int n, int32_t* host_out, uint64_t host_bytes);
 
+/* Runs ONLY the fused front end (quantize + stem + ReLU + max-pool, frontend_v2.cuh) on the device batch
+ * x_dev and copies the pooled tensor [n][ph][pw][c_pitch] (u8 / f16) to pooled_host; when acc_host is not
+ * NULL also the stem's zero-point-corrected accumulators [n][ho][wo][c_pitch] (int32; fp32 bits for F16). */
+int ievm_debug_frontend(ievm_handle* h, const void* x_dev, int n, void* pooled_host, uint64_t pooled_bytes,
+                        int32_t* acc_host, uint64_t acc_bytes);
+
 /* Diagnostic: issue ONE im2col-mode TMA load (128 pixels x kc_bytes channels of a u8 NHWC tensor
  * with channel pitch c_pitch) for the tile that starts at output pixel m0, filter tap
  * (tap_x, tap_y), channel offset c0, and copy the raw (swizzled) shared-memory image, 128*kc_bytes

@@ -25,6 +25,7 @@ EXPORTS = [
     "ievm_forward_f16_host", "ievm_set_option", "ievm_num_tensors", "ievm_tensor_shape",
     "ievm_launches_per_forward", "ievm_debug_read_tensor", "ievm_debug_conv_acc", "ievm_kd_loss",
     "ievm_last_error", "ievm_build_info", "ievm_probe_im2col", "ievm_profile_read", "ievm_probe_patch",
+    "ievm_debug_frontend",
 ]
 
 
@@ -110,6 +111,8 @@ def load():
     lib.ievm_probe_im2col.restype = C.c_int
     lib.ievm_probe_patch.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_void_p]
     lib.ievm_probe_patch.restype = C.c_int
+    lib.ievm_debug_frontend.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.ievm_debug_frontend.restype = C.c_int
     lib.ievm_profile_read.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
     lib.ievm_profile_read.restype = C.c_int
     for name in ("ievm_forward_i8", "ievm_forward_f16", "ievm_forward_i8_host", "ievm_forward_f16_host",

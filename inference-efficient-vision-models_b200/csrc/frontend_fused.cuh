@@ -61,10 +61,6 @@ struct FrontendParams {
   unsigned int* stuck_flag;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
 __global__ void __launch_bounds__(kFeThreads, 1)
 frontend_fused_kernel(const __grid_constant__ CUtensorMap tmap_w, const FrontendParams p) {
   extern __shared__ uint8_t smem_raw[];

@@ -1,0 +1,460 @@
+// Fused front end, second generation: [quantize_per_tensor ->] 7x7/2 stem conv (+folded BN) -> requant/bias + ReLU
+// -> MaxPool2d(3,2,1) in one kernel, for 224-wide inputs and stems of <= 64 channels (INT8 and FP16).
+//
+// Three ideas carry it:
+//
+// 1. No im2col build.  The (quantised) input is written to shared memory exactly once, as 16-byte RECORDS:
+//      INT8: record (Y, p) = input rows 2Y, 2Y+1 x columns 2p, 2p+1 x 3 channels (12 bytes + 4 zero-weight bytes)
+//      FP16: record (y, p) = input row y x columns 2p, 2p+1 x 3 channels        (6 halves + 2 zero halves)
+//    A LINE is one row (pair) of 116 records (p = -2 .. 113, out-of-image records hold the zero point / 0).
+//    The stem window of output column ox is the four consecutive records ox .. ox+3 of a line, and the window
+//    of ox+1 is the same run shifted by ONE record.  That is precisely the no-swizzle K-major UMMA operand
+//    layout -- rows 16 bytes apart, eight-row groups 128 bytes apart (SBO), the second 16-byte K chunk at
+//    LBO -- with LBO = 16 bytes: the K chunks of neighbouring rows overlap in memory, which a read-only
+//    operand does not mind.  One tcgen05.mma therefore reads a line in place as a [112 pixels x 32 B] operand.
+//
+// 2. Channels are the M dimension, pixels the N dimension: D[m][ox], m = channel.  TMEM lane = channel,
+//    TMEM column = stem column, so one epilogue thread holds a whole stem row of ONE channel: the 3-wide
+//    horizontal max of the pool runs on registers, per-channel requantisation constants are scalars, and
+//    nothing about the pool goes through shared memory except one 28-value exchange (below).
+//
+// 3. M = 128 holds TWO stem rows: rows 0..63 of the weight operand compute stem row 2T, rows 64..127 hold the
+//    same filters shifted down by one row pair (two input rows) and compute stem row 2T+1 from the same
+//    B operand.  A tile = pooled row T = 5 (INT8) / 9 (FP16) lines x 2 k-steps = 10 / 18 MMAs of
+//    M128 x N112.  Pooled row T needs stem rows 2T-1, 2T, 2T+1: thread (lane 64+c) keeps the horizontal maxima of
+//    row 2T-1 in registers from the previous tile, thread (lane c) has row 2T; the two exchange half of
+//    their maxima through shared memory and each finishes half of the pooled columns.
+//
+// requant(x) is non-decreasing in x (and so is half(relu(x + b))), hence pooling the raw accumulators first is
+// bit-exact and only the pooled values are requantised.
+//
+// Pipeline (persistent CTA, 14 warps): TMA producer (raw f32/f16 rows, zero-filled outside the image: q(0.0) is
+// the zero point) -> 4 quantiser warps (raw -> records) -> MMA warp -> 8 epilogue warps (two warpgroups, one per
+// half of the pooled columns).  Work unit = (image, range of pooled rows); a unit starts with one warm-up tile
+// whose only purpose is stem row 2*T0-1.
+#pragma once
+#include <cuda_fp16.h>
+
+#include <climits>
+
+#include "conv_tc.cuh"
+
+namespace ievm {
+
+constexpr int kF2W = 224;                        // input width this kernel is specialised for
+constexpr int kF2Wo = 112;                       // stem columns == UMMA N
+constexpr int kF2Pw = 56;                        // pooled columns
+constexpr int kF2PxPerWg = 28;                   // pooled columns per epilogue warpgroup
+constexpr int kF2Rec = 116;                      // records per line (column pairs -2 .. 113)
+constexpr int kF2LinePitch = kF2Rec * 16;        // 1856 B
+constexpr int kF2RawSlots = 6;
+constexpr int kF2ChunkSlots = 8;                 // chunk slots in the line ring
+constexpr int kF2TmemSlots = 4;
+constexpr int kF2TmemSlotCols = 128;
+constexpr int kF2EpiWarps = 8;
+constexpr int kF2QuantWarps = 4;
+constexpr int kF2QuantThreads = 32 * kF2QuantWarps;
+constexpr int kF2MmaWarp = kF2EpiWarps;
+constexpr int kF2TmaWarp = kF2EpiWarps + 1;
+constexpr int kF2FirstQuantWarp = kF2EpiWarps + 2;
+constexpr int kF2Threads = 32 * (kF2EpiWarps + 2 + kF2QuantWarps);
+constexpr int kF2LowerPx = 16;                   // of a warpgroup's 28 pooled columns, the lane-c thread finishes 16
+constexpr int kF2XRows = 7;                      // uint4 rows of one exchange buffer (4 upper->lower, 3 lower->upper)
+
+template <int kDtype>
+struct F2Cfg {
+  static constexpr int kLpc = kDtype == kDtypeI8 ? 2 : 4;             // lines per chunk (a chunk = 4 input rows)
+  static constexpr int kSegs = 2 * kLpc + 1;                          // lines one tile reads
+  static constexpr int kRowOff = kDtype == kDtypeI8 ? 4 : 3;          // chunk ci = input rows 4ci - kRowOff ..
+  static constexpr int kABytes = kSegs * 64 * 128;                    // weight operand: 128 rows x kSegs x 64 B
+  static constexpr int kInElem = kDtype == kDtypeI8 ? 4 : 2;          // f32 / f16 input
+  // raw rows start kBoxX0 columns left of the image so that the box begins on a 16-byte boundary of the row
+  // (TMA faults on an 8-byte-aligned box start); they cover the 232 columns -4 .. 227 the records need
+  static constexpr int kBoxX0 = kDtype == kDtypeI8 ? 4 : 8;
+  static constexpr int kBoxW = 2 * kF2Rec + (kBoxX0 - 4) + (kDtype == kDtypeI8 ? 0 : 4);   // 232 / 240
+  static constexpr int kRawTx = 3 * 4 * kBoxW * kInElem;              // bytes one chunk's TMA delivers
+  static constexpr int kRawStride = (kRawTx + 127) / 128 * 128;
+  static constexpr int kLines = kF2ChunkSlots * kLpc;                 // power of two
+  static constexpr int kRecsPerChunk = kLpc * kF2Rec;
+  static constexpr size_t kSmemBytes = 1024 + kABytes + static_cast<size_t>(kLines) * kF2LinePitch +
+                                       static_cast<size_t>(kF2RawSlots) * kRawStride +
+                                       2 * 2 * kF2XRows * 64 * 16 + 64 * 8 + 16;
+};
+
+struct Frontend2Params {
+  int n, h;                  // images, input height (multiple of 4); the width is kF2W
+  int ho, ph;                // stem rows (h / 2), pooled rows (h / 4)
+  int tpu, upi;              // pooled rows per work unit, units per image
+  int in_zp;
+  float inv_scale;
+  uint32_t idesc;
+  const uint8_t* wpack;      // weight operand image (F2Cfg::kABytes), see pack_front2_weights
+  void* out;                 // [n][ph][56][64] u8 / f16
+  const float* bdiv;         // i8: bias / (x_s * w_s[c]);  f16: folded bias
+  const float* mult;         // i8: (x_s * w_s[c]) / out_s
+  const int* zwsum;          // i8: in_zp * sum(w[c])
+  int out_zp, out_lo;
+  int32_t* dump_acc;         // debug: corrected stem accumulators [n][ho][112][64] (f16: float bit patterns)
+  unsigned int* stuck_flag;
+};
+
+struct F2Unit {
+  int img, t0, nt;
+};
+__device__ __forceinline__ F2Unit f2_unit(const Frontend2Params& p, int u) {
+  F2Unit r;
+  r.img = u / p.upi;
+  r.t0 = (u - r.img * p.upi) * p.tpu;
+  r.nt = min(p.tpu, p.ph - r.t0);
+  return r;
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Accumulator words are int32 (INT8) or float bit patterns (FP16); "lowest" is the pool's padding value.
+template <int kDtype>
+__device__ __forceinline__ uint32_t f2_lowest() {
+  return kDtype == kDtypeI8 ? 0x80000000u : 0xFF800000u;   // INT_MIN / -inf
+}
+template <int kDtype>
+__device__ __forceinline__ uint32_t f2_max(uint32_t a, uint32_t b) {
+  if (kDtype == kDtypeI8) return static_cast<uint32_t>(max(static_cast<int>(a), static_cast<int>(b)));
+  return __float_as_uint(fmaxf(__uint_as_float(a), __uint_as_float(b)));
+}
+template <int kDtype>
+__device__ __forceinline__ uint32_t f2_max3(uint32_t a, uint32_t b, uint32_t c) {
+  if (kDtype == kDtypeI8)
+    return static_cast<uint32_t>(__vimax3_s32(static_cast<int>(a), static_cast<int>(b), static_cast<int>(c)));
+  return __float_as_uint(fmaxf(fmaxf(__uint_as_float(a), __uint_as_float(b)), __uint_as_float(c)));
+}
+
+// Epilogue of one warpgroup (kWg = 0: pooled columns 0..27, kWg = 1: 28..55).
+template <int kDtype, int kWg>
+__device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t tmem_base, uint64_t* tmem_full,
+                                            uint64_t* tmem_empty, uint4* s_x, int units) {
+  constexpr int kOff = kWg == 0 ? -1 : 7;        // register index of a pooled column's first stem column: 2k + kOff
+  constexpr int kCol0 = kWg == 0 ? 0 : 48;       // first TMEM column this warpgroup loads
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = warp & 3;
+  const bool upper = quad >= 2;                  // lanes 64..127: stem row 2T+1
+  const int c = (quad & 1) * 32 + lane;          // channel
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + kCol0;
+  const uint32_t kLow = f2_lowest<kDtype>();
+  const float bd = p.bdiv[c];
+  const float mu = kDtype == kDtypeI8 ? p.mult[c] : 0.f;
+  const int zw = kDtype == kDtypeI8 ? p.zwsum[c] : 0;
+  const int out_elem = kDtype == kDtypeI8 ? 1 : 2;
+  uint4* xs = s_x + kWg * 2 * kF2XRows * 64;
+
+  uint32_t prev[kF2PxPerWg];                     // upper threads: horizontal maxima of the previous tile's row
+#pragma unroll
+  for (int k = 0; k < kF2PxPerWg; ++k) prev[k] = kLow;
+  int t = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const F2Unit un = f2_unit(p, u);
+    for (int i = 0; i <= un.nt; ++i, ++t) {
+      const int T = un.t0 - 1 + i;               // pooled row of this tile (the warm-up tile i == 0 only feeds `prev`)
+      const int ts = t & (kF2TmemSlots - 1);
+      wait_or_die(&tmem_full[ts], (t >> 2) & 1u, 0x840u | ts, p.stuck_flag);
+      tc_fence_after();
+      const uint32_t taddr = lane_addr + static_cast<uint32_t>(ts * kF2TmemSlotCols);
+      const bool real = i > 0;
+      uint32_t hm[kF2PxPerWg];
+      if (real || upper) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        if (p.dump_acc != nullptr && T >= 0) {
+          const int oy = 2 * T + (upper ? 1 : 0);
+          int32_t* d = p.dump_acc + ((static_cast<size_t>(un.img) * p.ho + oy) * kF2Wo + kCol0) * 64 + c;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) d[j * 64] = static_cast<int32_t>(v[j]) - zw;
+        }
+#pragma unroll
+        for (int k = 0; k < kF2PxPerWg; ++k) {
+          const int i0 = 2 * k + kOff;
+          if (i0 + 2 <= 31) hm[k] = f2_max3<kDtype>(i0 < 0 ? kLow : v[i0 < 0 ? 0 : i0], v[i0 + 1], v[i0 + 2]);
+        }
+        const uint32_t c30 = v[30], c31 = v[31];
+        tmem_ld_32x32b_x32(taddr + 32, v);
+        tmem_ld_wait();
+        if (p.dump_acc != nullptr && T >= 0) {
+          const int oy = 2 * T + (upper ? 1 : 0);
+          int32_t* d = p.dump_acc + ((static_cast<size_t>(un.img) * p.ho + oy) * kF2Wo + kCol0 + 32) * 64 + c;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) d[j * 64] = static_cast<int32_t>(v[j]) - zw;
+        }
+#pragma unroll
+        for (int k = 0; k < kF2PxPerWg; ++k) {
+          const int i0 = 2 * k + kOff;
+          if (i0 + 2 >= 32) {
+            const uint32_t a = i0 >= 32 ? v[i0 >= 32 ? i0 - 32 : 0] : (i0 == 30 ? c30 : c31);
+            const uint32_t b = i0 + 1 >= 32 ? v[i0 + 1 >= 32 ? i0 + 1 - 32 : 0] : c31;
+            hm[k] = f2_max3<kDtype>(a, b, v[i0 + 2 - 32]);
+          }
+        }
+      }
+      tc_fence_before();
+      uint4* xb = xs + (t & 1) * kF2XRows * 64;
+      if (upper) {
+        // stem row 2T+1 joins the row 2T-1 kept from the previous tile; rows above the image do not exist
+#pragma unroll
+        for (int k = 0; k < kF2PxPerWg; ++k) {
+          const uint32_t cur = T < 0 ? kLow : hm[k];
+          hm[k] = f2_max<kDtype>(prev[k], cur);
+          prev[k] = cur;
+        }
+        if (real) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) xb[j * 64 + c] = make_uint4(hm[4 * j], hm[4 * j + 1], hm[4 * j + 2], hm[4 * j + 3]);
+        }
+      } else if (real) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          xb[(4 + j) * 64 + c] = make_uint4(hm[kF2LowerPx + 4 * j], hm[kF2LowerPx + 4 * j + 1], hm[kF2LowerPx + 4 * j + 2],
+                                            hm[kF2LowerPx + 4 * j + 3]);
+      }
+      named_bar_sync(1 + kWg, 128);
+      if ((threadIdx.x & 127) == 0) mbar_arrive(&tmem_empty[ts]);       // this warpgroup's TMEM reads of the slot are done
+      if (!real) continue;
+      uint8_t* orow = static_cast<uint8_t*>(p.out) +
+                      (((static_cast<size_t>(un.img) * p.ph + T) * kF2Pw + kWg * kF2PxPerWg) * 64 + c) * out_elem;
+      auto finish = [&](int k, uint32_t m) {
+        if (kDtype == kDtypeI8) {
+          orow[k * 64] = static_cast<uint8_t>(requant_i8(static_cast<int>(m) - zw, bd, mu, p.out_zp, p.out_lo));
+        } else {
+          reinterpret_cast<__half*>(orow)[k * 64] = __float2half_rn(fmaxf(__uint_as_float(m) + bd, 0.f));
+        }
+      };
+      if (!upper) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 o = xb[j * 64 + c];
+          finish(4 * j + 0, f2_max<kDtype>(hm[4 * j + 0], o.x));
+          finish(4 * j + 1, f2_max<kDtype>(hm[4 * j + 1], o.y));
+          finish(4 * j + 2, f2_max<kDtype>(hm[4 * j + 2], o.z));
+          finish(4 * j + 3, f2_max<kDtype>(hm[4 * j + 3], o.w));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const uint4 o = xb[(4 + j) * 64 + c];
+          finish(kF2LowerPx + 4 * j + 0, f2_max<kDtype>(hm[kF2LowerPx + 4 * j + 0], o.x));
+          finish(kF2LowerPx + 4 * j + 1, f2_max<kDtype>(hm[kF2LowerPx + 4 * j + 1], o.y));
+          finish(kF2LowerPx + 4 * j + 2, f2_max<kDtype>(hm[kF2LowerPx + 4 * j + 2], o.z));
+          finish(kF2LowerPx + 4 * j + 3, f2_max<kDtype>(hm[kF2LowerPx + 4 * j + 3], o.w));
+        }
+      }
+    }
+  }
+}
+
+template <int kDtype>
+__global__ void __launch_bounds__(kF2Threads, 1)
+frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Params p) {
+  using Cfg = F2Cfg<kDtype>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sW = smem;
+  uint8_t* sLines = sW + Cfg::kABytes;
+  uint8_t* sRaw = sLines + Cfg::kLines * kF2LinePitch;
+  uint4* sX = reinterpret_cast<uint4*>(sRaw + kF2RawSlots * Cfg::kRawStride);
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(sX + 2 * 2 * kF2XRows * 64);
+  uint64_t* raw_empty = raw_full + kF2RawSlots;
+  uint64_t* line_full = raw_empty + kF2RawSlots;
+  uint64_t* line_empty = line_full + kF2ChunkSlots;
+  uint64_t* tmem_full = line_empty + kF2ChunkSlots;
+  uint64_t* tmem_empty = tmem_full + kF2TmemSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kF2TmemSlots);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // weight operand image: plain copy (it is already in the UMMA core-matrix order)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wpack);
+    uint4* dst = reinterpret_cast<uint4*>(sW);
+    for (int i = threadIdx.x; i < Cfg::kABytes / 16; i += kF2Threads) dst[i] = __ldg(src + i);
+    fence_proxy_async_smem();
+  }
+  if (warp == kF2TmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    for (int i = 0; i < kF2RawSlots; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], kF2QuantThreads);
+    }
+    for (int i = 0; i < kF2ChunkSlots; ++i) {
+      mbar_init(&line_full[i], kF2QuantThreads);
+      mbar_init(&line_empty[i], 1);
+    }
+    for (int i = 0; i < kF2TmemSlots; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2);              // one arrival per epilogue warpgroup
+    }
+    fence_barrier_init();
+  }
+  if (warp == kF2MmaWarp) {
+    tmem_alloc(tmem_slot, 512u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  griddep_launch_dependents();
+
+  const int units = p.n * p.upi;
+
+  if (warp < kF2EpiWarps) {
+    if (warp < 4) f2_epilogue<kDtype, 0>(p, tmem_base, tmem_full, tmem_empty, sX, units);
+    else f2_epilogue<kDtype, 1>(p, tmem_base, tmem_full, tmem_empty, sX, units);
+  } else if (warp == kF2MmaWarp) {
+    // ================================ MMA issuer ================================
+    const uint32_t hi = (128u >> 4) | (1u << 14);                                  // SBO = 128 B, version 1, no swizzle
+    const uint32_t a_lo0 = ((smem_u32(sW) & 0x3FFFFu) >> 4) | ((2048u >> 4) << 16);     // LBO = 2048 B (next K chunk)
+    const uint32_t b_lo0 = ((smem_u32(sLines) & 0x3FFFFu) >> 4) | (1u << 16);          // LBO = 16 B (next record)
+    int q0 = 0, t = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const F2Unit un = f2_unit(p, u);
+      for (int i = 0; i <= un.nt; ++i, ++t) {
+        const int qn = q0 + i + 2;               // newest chunk this tile reads (chunks complete in order)
+        wait_or_die(&line_full[qn % kF2ChunkSlots], (qn / kF2ChunkSlots) & 1u, 0x820u | (qn % kF2ChunkSlots), p.stuck_flag);
+        const int ts = t & (kF2TmemSlots - 1);
+        wait_or_die(&tmem_empty[ts], ((t >> 2) & 1u) ^ 1u, 0x830u | ts, p.stuck_flag);
+        tc_fence_after();
+        fence_proxy_async_smem();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * kF2TmemSlotCols);
+        const int line0 = (q0 + i) * Cfg::kLpc;
+        if (elect_one()) {
+#pragma unroll
+          for (int s = 0; s < Cfg::kSegs; ++s) {
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>((line0 + s) & (Cfg::kLines - 1)) * (kF2LinePitch >> 4);
+#pragma unroll
+            for (int jh = 0; jh < 2; ++jh) {
+              const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(2 * s + jh) * (4096u >> 4);
+              if (kDtype == kDtypeI8) umma_i8_lohi(d_tmem, a_lo, b_lo + 2u * jh, hi, p.idesc, (s | jh) != 0 ? 1u : 0u);
+              else umma_f16_lohi(d_tmem, a_lo, b_lo + 2u * jh, hi, p.idesc, (s | jh) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&tmem_full[ts]);
+          umma_commit(&line_empty[(q0 + i) % kF2ChunkSlots]);      // tile i is the last reader of chunk i
+          if (i == un.nt) {
+            umma_commit(&line_empty[(q0 + i + 1) % kF2ChunkSlots]);
+            umma_commit(&line_empty[(q0 + i + 2) % kF2ChunkSlots]);
+          }
+        }
+        __syncwarp();
+      }
+      q0 += un.nt + 3;
+    }
+  } else if (warp == kF2TmaWarp) {
+    // ================================ TMA producer: raw input rows ================================
+    int q = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const F2Unit un = f2_unit(p, u);
+      for (int j = 0; j < un.nt + 3; ++j, ++q) {
+        const int slot = q % kF2RawSlots;
+        wait_or_die(&raw_empty[slot], ((q / kF2RawSlots) & 1u) ^ 1u, 0x800u | slot, p.stuck_flag);
+        if (elect_one()) {
+          mbar_expect_tx(&raw_full[slot], static_cast<uint32_t>(Cfg::kRawTx));
+          tma_load_3d(sRaw + slot * Cfg::kRawStride, &tmap_x, &raw_full[slot], -Cfg::kBoxX0, 4 * (un.t0 - 1 + j) - Cfg::kRowOff,
+                      3 * un.img);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ quantisers: raw rows -> records ================================
+    const int qt = threadIdx.x - 32 * kF2FirstQuantWarp;
+    int q = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const F2Unit un = f2_unit(p, u);
+      for (int j = 0; j < un.nt + 3; ++j, ++q) {
+        const int slot = q % kF2RawSlots, cs = q % kF2ChunkSlots;
+        wait_or_die(&raw_full[slot], (q / kF2RawSlots) & 1u, 0x810u | slot, p.stuck_flag);
+        wait_or_die(&line_empty[cs], ((q / kF2ChunkSlots) & 1u) ^ 1u, 0x818u | cs, p.stuck_flag);
+        const uint8_t* raw = sRaw + slot * Cfg::kRawStride;
+        uint8_t* lines = sLines + cs * Cfg::kLpc * kF2LinePitch;
+        if (kDtype == kDtypeI8) {
+          // record (l, ri): rows 2l, 2l+1 of the chunk, raw columns 2ri, 2ri+1; byte = rp*6 + cp*3 + c
+          const float* rf = reinterpret_cast<const float*>(raw);
+#pragma unroll
+          for (int it = 0; it < (Cfg::kRecsPerChunk + kF2QuantThreads - 1) / kF2QuantThreads; ++it) {
+            const int idx = qt + it * kF2QuantThreads;
+            if (idx < Cfg::kRecsPerChunk) {
+              const int l = idx >= kF2Rec ? 1 : 0;
+              const int ri = idx - l * kF2Rec;
+              int qv[3][2][2];                   // [c][rp][cp]
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                for (int rp = 0; rp < 2; ++rp) {
+                  const float2 f = *reinterpret_cast<const float2*>(rf + (ch * 4 + 2 * l + rp) * Cfg::kBoxW + 2 * ri);
+                  qv[ch][rp][0] = __float2int_rn(__fmul_rn(f.x, p.inv_scale)) + p.in_zp;
+                  qv[ch][rp][1] = __float2int_rn(__fmul_rn(f.y, p.inv_scale)) + p.in_zp;
+                }
+              uint4 o;
+              o.x = pack4_sat_u8(qv[0][0][0], qv[1][0][0], qv[2][0][0], qv[0][0][1]);
+              o.y = pack4_sat_u8(qv[1][0][1], qv[2][0][1], qv[0][1][0], qv[1][1][0]);
+              o.z = pack4_sat_u8(qv[2][1][0], qv[0][1][1], qv[1][1][1], qv[2][1][1]);
+              o.w = 0u;
+              *reinterpret_cast<uint4*>(lines + l * kF2LinePitch + ri * 16) = o;
+            }
+          }
+        } else {
+          // record (l, ri): row l of the chunk, raw columns 2ri, 2ri+1; half e = cp*3 + c
+          const uint32_t* rh = reinterpret_cast<const uint32_t*>(raw);
+#pragma unroll
+          for (int it = 0; it < (Cfg::kRecsPerChunk + kF2QuantThreads - 1) / kF2QuantThreads; ++it) {
+            const int idx = qt + it * kF2QuantThreads;
+            if (idx < Cfg::kRecsPerChunk) {
+              const int l = idx / kF2Rec;
+              const int ri = idx - l * kF2Rec;
+              constexpr int kSkip = (Cfg::kBoxX0 - 4) / 2;      // column pairs between the box start and record 0
+              const uint32_t p0 = rh[((0 * 4 + l) * Cfg::kBoxW >> 1) + ri + kSkip];
+              const uint32_t p1 = rh[((1 * 4 + l) * Cfg::kBoxW >> 1) + ri + kSkip];
+              const uint32_t p2 = rh[((2 * 4 + l) * Cfg::kBoxW >> 1) + ri + kSkip];
+              uint4 o;
+              o.x = __byte_perm(p0, p1, 0x5410);   // (cp0,c0) (cp0,c1)
+              o.y = __byte_perm(p2, p0, 0x7610);   // (cp0,c2) (cp1,c0)
+              o.z = __byte_perm(p1, p2, 0x7632);   // (cp1,c1) (cp1,c2)
+              o.w = 0u;
+              *reinterpret_cast<uint4*>(lines + l * kF2LinePitch + ri * 16) = o;
+            }
+          }
+        }
+        mbar_arrive(&raw_empty[slot]);           // after the reads above (release)
+        fence_proxy_async_smem();                // records visible to the tensor core's async-proxy reads
+        mbar_arrive(&line_full[cs]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kF2MmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+}  // namespace ievm

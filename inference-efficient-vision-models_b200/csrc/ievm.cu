@@ -21,6 +21,7 @@
 #include "simt_kernels.cuh"
 #include "stem_tc.cuh"
 #include "frontend_fused.cuh"
+#include "frontend_v2.cuh"
 
 namespace {
 
@@ -139,6 +140,7 @@ struct LayerPlan {
   void* w_packed = nullptr;     // tensor-core layout [cout_pad][taps][cin_w]
   void* w_stem = nullptr;       // stem layout (CUDA-core kernels)
   void* w_stem_tc = nullptr;    // stem layout for the tensor-core kernel: [cout_pad][8 segments x 32 B]
+  void* w_front2 = nullptr;     // frontend_v2.cuh weight operand image (two stem rows stacked in M)
   int* wsum = nullptr;
   int* zwsum = nullptr;         // in_zp * wsum
   size_t stem_smem = 0;
@@ -159,6 +161,9 @@ struct ievm_handle {
   int opt_halo = 1;        // IEVM_HALO=0 disables the halo-patch mode (all convs use per-tap im2col TMA)
   int opt_halo_rb128 = 0;
   int opt_fused_front = 1; // IEVM_FUSED_FRONT=0: separate quantize / stem / maxpool kernels
+  int opt_front_v2 = 1;    // IEVM_FRONT_V2=0: first-generation fused front end (INT8) / separate kernels (FP16)
+  int front2_ok = 0;       // the network's front end fits frontend_v2.cuh (224-wide input, <= 64 stem channels)
+  int front_tpu = 0;       // IEVM_FRONT_TPU: pooled rows per work unit (0 = heuristic)
   size_t fe_smem = 0;
   int opt_cluster = 1;     // IEVM_CLUSTER=0: no 2-CTA clusters / weight multicast
   int opt_pdl = 1;         // IEVM_PDL=0: no programmatic dependent launch
@@ -388,6 +393,8 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
 // ----------------------------------------------------------------------------------------------
 // Weights and epilogue tables
 // ----------------------------------------------------------------------------------------------
+int upload_front2_weights(ievm_handle* h, LayerPlan& L);
+
 int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
   const ievm_layer_desc& d = L.d;
   const int taps = d.ksize * d.ksize;
@@ -405,6 +412,10 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
   if (int rc = dev_upload(h, ep1, &L.ep1)) return rc;
 
   if (L.is_stem) {
+    if (L.cout_pad == 64 && h->in_w == kF2W && h->in_h % 4 == 0 && h->in_h >= 8) {
+      if (int rc = upload_front2_weights(h, L)) return rc;
+      h->front2_ok = 1;
+    }
     if (h->dtype == IEVM_DTYPE_I8) {
       const int8_t* w = static_cast<const int8_t*>(d.weight);     // [cout][3][7][7]
       std::vector<uint32_t> w4(static_cast<size_t>(49) * L.cout_pad, 0u);
@@ -483,6 +494,48 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
   return IEVM_OK;
 }
 
+// Weight operand of frontend_v2.cuh: A[m][k], m = 64 * r + cout (r = which of the tile's two stem rows),
+// K bytes = line s (0 .. kSegs-1) x 64: record j (0..3) x 16 bytes.  Stored as UMMA no-swizzle K-major core
+// matrices: byte (m, kb) at ((kb / 16) * 16 + m / 8) * 128 + (m % 8) * 16 + kb % 16  (SBO = 128, LBO = 2048).
+//   INT8: record byte = rp * 6 + cp * 3 + c, line s = input row pair: ky = 2 * (s - r) + rp - 1, kx = 2 * j + cp - 1
+//   FP16: record half = cp * 3 + c,          line s = input row:      ky = s - 2 * r,             kx = 2 * j + cp - 1
+int upload_front2_weights(ievm_handle* h, LayerPlan& L) {
+  const ievm_layer_desc& d = L.d;
+  const bool i8 = h->dtype == IEVM_DTYPE_I8;
+  const int segs = i8 ? F2Cfg<kDtypeI8>::kSegs : F2Cfg<kDtypeF16>::kSegs;
+  const int abytes = i8 ? F2Cfg<kDtypeI8>::kABytes : F2Cfg<kDtypeF16>::kABytes;
+  std::vector<uint8_t> img(abytes, 0);
+  auto at = [&](int m, int kb) -> uint8_t* { return &img[(static_cast<size_t>(kb / 16) * 16 + m / 8) * 128 + (m % 8) * 16 + kb % 16]; };
+  for (int r = 0; r < 2; ++r)
+    for (int co = 0; co < d.cout; ++co)
+      for (int s = 0; s < segs; ++s)
+        for (int j = 0; j < 4; ++j)
+          for (int cp = 0; cp < 2; ++cp)
+            for (int c = 0; c < 3; ++c) {
+              const int kx = 2 * j + cp - 1;
+              if (kx < 0 || kx > 6) continue;
+              if (i8) {
+                for (int rp = 0; rp < 2; ++rp) {
+                  const int ky = 2 * (s - r) + rp - 1;
+                  if (ky < 0 || ky > 6) continue;
+                  const int8_t v = static_cast<const int8_t*>(d.weight)[(static_cast<size_t>(co) * 3 + c) * 49 + ky * 7 + kx];
+                  *at(64 * r + co, s * 64 + j * 16 + rp * 6 + cp * 3 + c) = static_cast<uint8_t>(v);
+                }
+              } else {
+                const int ky = s - 2 * r;
+                if (ky < 0 || ky > 6) continue;
+                const uint16_t v = static_cast<const uint16_t*>(d.weight)[(static_cast<size_t>(co) * 3 + c) * 49 + ky * 7 + kx];
+                uint8_t* dst = at(64 * r + co, s * 64 + j * 16 + (cp * 3 + c) * 2);
+                dst[0] = static_cast<uint8_t>(v & 0xff);
+                dst[1] = static_cast<uint8_t>(v >> 8);
+              }
+            }
+  uint8_t* dw = nullptr;
+  if (int rc = dev_upload(h, img, &dw)) return rc;
+  L.w_front2 = dw;
+  return IEVM_OK;
+}
+
 int upload_head_operands(ievm_handle* h, LayerPlan& L) {
   const ievm_layer_desc& d = L.d;
   std::vector<float> ep0(kMaxClasses, 0.f), ep1(kMaxClasses, 0.f);
@@ -519,6 +572,7 @@ int upload_head_operands(ievm_handle* h, LayerPlan& L) {
 // ----------------------------------------------------------------------------------------------
 bool front_end_is_chunked(const ievm_handle* h);
 bool front_end_is_fused(const ievm_handle* h);
+bool front_end_is_v2(const ievm_handle* h);
 
 int assign_buffers(ievm_handle* h) {
   for (void* b : h->buffers) cudaFree(b);
@@ -827,6 +881,76 @@ int launch_maxpool(ievm_handle* h, const LayerPlan& L, const void* in, void* out
 // is produced and consumed inside L2 and, because every chunk overwrites the same lines, never has
 // to be written back to HBM.
 // quantize + stem + maxpool in one kernel (frontend_fused.cuh): INT8, tensor-core path, no parity hooks.
+// Second-generation fused front end (frontend_v2.cuh): INT8 and FP16, 224-wide inputs, <= 64 stem channels.
+bool front_end_is_v2(const ievm_handle* h) {
+  return h->front2_ok && h->opt_front_v2 && h->opt_fused_front && h->conv_impl == 0 && !h->keep_tensors &&
+         h->layers.size() >= 2 && h->layers[0].is_stem && h->layers[0].w_front2 != nullptr &&
+         h->layers[1].d.op == IEVM_OP_MAXPOOL && h->layers[1].d.in_tensor == h->layers[0].d.out_tensor &&
+         h->tensors[h->layers[0].d.out_tensor].last_use == 1;
+}
+
+// Pooled rows per work unit: the persistent grid runs ceil(units / #SMs) rounds of (tpu + 1 warm-up) tiles.
+int front2_tiles_per_unit(const ievm_handle* h, int n, int ph) {
+  if (h->front_tpu > 0) return std::min(h->front_tpu, ph);
+  int best = ph;
+  double best_cost = 1e30;
+  for (int tpu = 1; tpu <= ph; ++tpu) {
+    const long long units = static_cast<long long>(n) * ((ph + tpu - 1) / tpu);
+    const long long rounds = (units + h->num_sms - 1) / h->num_sms;
+    const double cost = static_cast<double>(rounds) * (tpu + 2.5);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = tpu;
+    }
+  }
+  return best;
+}
+
+int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32_t* dump_acc) {
+  const LayerPlan& Ls = h->layers[0];
+  const LayerPlan& Lp = h->layers[1];
+  const bool i8 = h->dtype == IEVM_DTYPE_I8;
+  // the input batch as (W, H, 3 * n) planes; boxes start 4 columns left of the image and are zero-filled outside
+  CUtensorMap tmap;
+  {
+    const size_t es = i8 ? 4 : 2;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(h->in_w), static_cast<cuuint64_t>(h->in_h), static_cast<cuuint64_t>(3) * n};
+    cuuint64_t strides[2] = {h->in_w * es, static_cast<cuuint64_t>(h->in_w) * h->in_h * es};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(i8 ? F2Cfg<kDtypeI8>::kBoxW : F2Cfg<kDtypeF16>::kBoxW), 4, 3};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = g_encode_tiled(&tmap, i8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                                      const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled (front end input) failed: CUresult %d", (int)r);
+  }
+  Frontend2Params fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.n = n;
+  fp.h = h->in_h;
+  fp.ho = Ls.ho;
+  fp.ph = Lp.ho;
+  fp.tpu = front2_tiles_per_unit(h, n, fp.ph);
+  fp.upi = (fp.ph + fp.tpu - 1) / fp.tpu;
+  fp.in_zp = h->in_zp;
+  fp.inv_scale = i8 ? 1.0f / h->in_scale : 1.0f;
+  fp.idesc = i8 ? make_idesc_i8_s8u8(kF2Wo) : make_idesc_f16(kF2Wo);
+  fp.wpack = static_cast<const uint8_t*>(Ls.w_front2);
+  fp.out = tensor_ptr(h, Lp.d.out_tensor);
+  fp.bdiv = Ls.ep0;
+  fp.mult = Ls.ep1;
+  fp.zwsum = Ls.zwsum;
+  fp.out_zp = Ls.d.out_zp;
+  fp.out_lo = Ls.d.relu ? Ls.d.out_zp : 0;
+  fp.dump_acc = dump_acc;
+  fp.stuck_flag = h->stuck_dev;
+  const int grid = std::min(n * fp.upi, h->num_sms);
+  if (i8) frontend2_kernel<kDtypeI8><<<grid, kF2Threads, F2Cfg<kDtypeI8>::kSmemBytes, s>>>(tmap, fp);
+  else frontend2_kernel<kDtypeF16><<<grid, kF2Threads, F2Cfg<kDtypeF16>::kSmemBytes, s>>>(tmap, fp);
+  CUDA_TRY(cudaGetLastError());
+  return IEVM_OK;
+}
+
 bool front_end_is_fused(const ievm_handle* h) {
   return h->dtype == IEVM_DTYPE_I8 && h->opt_fused_front && h->conv_impl == 0 && !h->keep_tensors &&
          h->layers.size() >= 2 && h->layers[0].is_stem && h->layers[1].d.op == IEVM_OP_MAXPOOL &&
@@ -879,7 +1003,13 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     CUDA_TRY(cudaEventRecord(h->prof_events[0], s));
   }
   size_t first_layer = 0;
-  if (front_end_is_fused(h)) {
+  if (front_end_is_v2(h)) {
+    // profile slots: the fused kernel is attributed to the stem's slot (quantize and maxpool read 0)
+    if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
+    if (int rc = launch_frontend2(h, x, n, s, nullptr)) return rc;
+    if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[2], s));
+    first_layer = 2;
+  } else if (front_end_is_fused(h)) {
     // profile slots: the fused kernel is attributed to the stem's slot (quantize and maxpool read 0)
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
     if (int rc = launch_frontend_fused(h, static_cast<const float*>(x), n, s)) return rc;
@@ -1075,6 +1205,8 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (const char* e = getenv("IEVM_HOST_CHUNK")) h->host_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
   if (const char* e = getenv("IEVM_FRONT_CHUNK")) h->front_chunk = atoi(e);
+  if (const char* e = getenv("IEVM_FRONT_V2")) h->opt_front_v2 = atoi(e);
+  if (const char* e = getenv("IEVM_FRONT_TPU")) h->front_tpu = atoi(e);
   int rc = plan_shapes(h, nd);
   for (size_t i = 0; rc == IEVM_OK && i < h->layers.size(); ++i) {
     LayerPlan& L = h->layers[i];
@@ -1144,6 +1276,12 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
     if (h->fe_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) h->opt_fused_front = 0;
     else if (cudaFuncSetAttribute(frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) != cudaSuccess)
       rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend_fused_kernel) failed");
+  }
+  if (rc == IEVM_OK && h->front2_ok) {
+    const cudaError_t e = h->dtype == IEVM_DTYPE_I8
+        ? cudaFuncSetAttribute(frontend2_kernel<kDtypeI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2Cfg<kDtypeI8>::kSmemBytes)
+        : cudaFuncSetAttribute(frontend2_kernel<kDtypeF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2Cfg<kDtypeF16>::kSmemBytes);
+    if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend2_kernel): %s", cudaGetErrorString(e));
   }
   if (rc == IEVM_OK) {
     for (const LayerPlan& L : h->layers)
@@ -1286,7 +1424,7 @@ int ievm_tensor_shape(const ievm_handle* h, int id, int32_t out6[6]) {
 int ievm_launches_per_forward(const ievm_handle* h) {
   if (!h) return 0;
   const int n = h->last_n > 0 ? h->last_n : h->max_batch;
-  if (front_end_is_fused(h)) return static_cast<int>(h->layers.size()) - 1;
+  if (front_end_is_v2(h) || front_end_is_fused(h)) return static_cast<int>(h->layers.size()) - 1;
   if (front_end_is_chunked(h)) return 3 * ((n + h->front_chunk - 1) / h->front_chunk) + static_cast<int>(h->layers.size()) - 2;
   return static_cast<int>(h->layers.size()) + (h->dtype == IEVM_DTYPE_I8 ? 1 : 0);
 }
@@ -1342,6 +1480,29 @@ int ievm_debug_conv_acc(ievm_handle* h, int layer, int n, int32_t* host_out, uin
   if (rc == IEVM_OK && cudaMemcpy(host_out, dacc, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
     rc = fail(IEVM_ERR_CUDA, "accumulator copy failed");
   cudaFree(dacc);
+  return rc;
+}
+
+int ievm_debug_frontend(ievm_handle* h, const void* x_dev, int n, void* pooled_host, uint64_t pooled_bytes,
+                        int32_t* acc_host, uint64_t acc_bytes) {
+  if (!h || !x_dev || !pooled_host || n <= 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "debug_frontend: bad arguments");
+  if (!h->front2_ok) return fail(IEVM_ERR_UNSUPPORTED, "this network's front end does not fit the fused v2 kernel");
+  const LayerPlan& Ls = h->layers[0];
+  const LayerPlan& Lp = h->layers[1];
+  const size_t pooled = static_cast<size_t>(n) * Lp.ho * Lp.wo * Ls.cout_pad * h->elem;
+  const size_t acc = static_cast<size_t>(n) * Ls.ho * Ls.wo * Ls.cout_pad * sizeof(int32_t);
+  if (pooled_bytes < pooled || (acc_host && acc_bytes < acc)) return fail(IEVM_ERR_BAD_ARG, "debug_frontend: host buffer too small");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int32_t* dacc = nullptr;
+  if (acc_host) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dacc), acc));
+  int rc = launch_frontend2(h, x_dev, n, h->own_stream, dacc);
+  if (rc == IEVM_OK) rc = check_stuck(h, cudaStreamSynchronize(h->own_stream), "debug_frontend");
+  if (rc == IEVM_OK && cudaMemcpy(pooled_host, tensor_ptr(h, Lp.d.out_tensor), pooled, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = fail(IEVM_ERR_CUDA, "pooled tensor copy failed");
+  if (rc == IEVM_OK && acc_host && cudaMemcpy(acc_host, dacc, acc, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = fail(IEVM_ERR_CUDA, "accumulator copy failed");
+  if (dacc) cudaFree(dacc);
+  h->last_n = n;
   return rc;
 }
 

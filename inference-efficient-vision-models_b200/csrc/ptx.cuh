@@ -32,6 +32,11 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Named barrier among `threads` threads of the CTA (ids 1..15; 0 is __syncthreads).
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start
 // (prologue: barrier init, TMEM allocation, weight preload) while its predecessor drains; griddep_wait()
@@ -353,6 +358,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 //   n_dim [17,23) = N >> 3;  m_dim [24,29) = M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_i8_u8s8(int n, int m = 128) {
   return (2u << 4) | (0u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+// Same with A = S8 (weights as the M operand) and B = U8 (activations as the N operand).
+__host__ __device__ constexpr uint32_t make_idesc_i8_s8u8(int n, int m = 128) {
+  return (2u << 4) | (1u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 __host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);

@@ -165,6 +165,26 @@ class _B200Engine(nn.Module):
                 return acc if self.net.dtype == DTYPE_I8 else acc.view(np.float32)
         raise KeyError(layer_name)
 
+    def debug_frontend(self, images: torch.Tensor, want_acc: bool = True):
+        """Run only the fused front end (quantize + stem + ReLU + max-pool) on a CUDA batch.  Returns
+        (pooled NCHW over real channels, stem accumulators NCHW or None)."""
+        stem, pool = self.net.layers[0], self.net.layers[1]
+        n = int(images.shape[0])
+        _, ho, wo, c, pitch, elem = self.tensor_shape(stem.out_tensor)
+        _, ph, pw, _, _, _ = self.tensor_shape(pool.out_tensor)
+        dt = np.uint8 if elem == 1 else np.float16
+        pooled = np.empty((n, ph, pw, pitch), dtype=dt)
+        acc = np.empty((n, ho, wo, pitch), dtype=np.int32) if want_acc else None
+        x = images.contiguous()
+        _lib.check(self._lib.ievm_debug_frontend(self._handle, x.data_ptr(), n, pooled.ctypes.data, pooled.nbytes,
+                                                 acc.ctypes.data if want_acc else None, acc.nbytes if want_acc else 0),
+                   "debug_frontend")
+        pooled = np.ascontiguousarray(pooled[..., :c].transpose(0, 3, 1, 2))
+        if want_acc:
+            acc = np.ascontiguousarray(acc[..., :c].transpose(0, 3, 1, 2))
+            acc = acc if self.net.dtype == DTYPE_I8 else acc.view(np.float32)
+        return pooled, acc
+
     def close(self) -> None:
         if getattr(self, "_handle", None) is not None and self._handle.value:
             self._lib.ievm_destroy(self._handle)

@@ -137,6 +137,28 @@ def test_int8_every_tensor_and_accumulator_bit_exact():
     eng.close()
 
 
+@pytest.mark.parametrize("n,tpu", [(3, 0), (2, 5), (1, 56), (5, 1)])
+def test_int8_fused_front_end_accumulators_and_pooled_tensor(n, tpu, monkeypatch):
+    """frontend_v2.cuh alone (quantize + record build + stacked-row tcgen05 stem + pool in registers): stem
+    accumulators and the pooled tensor bit-identical to the oracle, for several work-unit sizes (tpu = pooled
+    rows per unit: exercises the warm-up tile, ragged last units and whole-image units)."""
+    if tpu:
+        monkeypatch.setenv("IEVM_FRONT_TPU", str(tpu))
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    net = O.extract_qnet(gm)
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=8)
+    x = mf.synthetic_images(n, seed=40 + n)
+    x[0, :, :5, :7] = 1e4       # saturating inputs in a corner
+    x[-1, :, -3:, -9:] = -1e4
+    pooled, acc = eng.debug_frontend(x.cuda())
+    O.forward(net, x.numpy(), keep=True)
+    assert np.array_equal(acc, net.trace["conv1:acc"]), \
+        f"stem accumulators: {(acc != net.trace['conv1:acc']).mean():.3%} differ"
+    assert np.array_equal(pooled, net.trace["maxpool"]), \
+        f"pooled tensor: {(pooled != net.trace['maxpool']).mean():.3%} bytes differ"
+    eng.close()
+
+
 @pytest.mark.parametrize("n", [1, 2, 5, 13])
 def test_int8_ragged_batches(n):
     gm = cached_quantized(mf.PRUNED_WIDTHS)
@@ -269,6 +291,21 @@ def test_fp16_student_matches_reference_half_path(golden_dir):
     eng.set_option("conv_impl", 1)
     y_direct = eng(x.cuda()).float().cpu().numpy()
     assert _row_rel(y, y_direct) < 2e-3
+    eng.close()
+
+
+def test_fp16_fused_front_end_matches_torch():
+    """frontend_v2.cuh, FP16 flavour: conv1 + folded bn1 + ReLU + maxpool against the same modules in fp32."""
+    import ievm_b200
+    m16 = mf.cast_fp16(mf.make_student(mf.PRUNED_WIDTHS))
+    eng = ievm_b200.B200HalfResNet.from_half_module(m16, max_batch=4)
+    x = mf.synthetic_images(3, seed=11).half()
+    pooled, _ = eng.debug_frontend(x.cuda(), want_acc=False)
+    m32 = mf.cast_fp16(mf.make_student(mf.PRUNED_WIDTHS)).float()
+    with torch.no_grad():
+        ref = m32.maxpool(m32.relu(m32.bn1(m32.conv1(x.float())))).numpy()
+    err = np.abs(pooled.astype(np.float32) - ref).max() / max(np.abs(ref).max(), 1.0)
+    assert err < 5e-3, f"fp16 front end off by {err}"
     eng.close()
 
 
