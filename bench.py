@@ -154,6 +154,23 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
+    (profiles/r01_ncu_full_<workload>.json, written by scripts/ncu_traffic.py); None when no capture exists."""
+    path = os.path.join(ROOT, "profiles", f"r01_ncu_full_{workload}.json")
+    if not os.path.exists(path):
+        return None, None
+    d = json.load(open(path))
+    return d.get("conv_tc_dram_bytes_per_launch"), os.path.relpath(path, ROOT)
+
+
+def network_roofline_ms(table, pk, i8):
+    """sum over launches of max(2*MAC / tensor peak, compulsory bytes / HBM peak)."""
+    tensor = (2 * pk["bf16_tflops_sustained"] if i8 else pk["bf16_tflops_sustained"]) * 1e12
+    hbm = pk["hbm_gbs"] * 1e9
+    return 1e3 * sum(max(2 * macs / tensor, byt / hbm) for macs, byt in table.values())
+
+
 def layer_table(net, n):
     """Per launch: algorithmic MACs and compulsory HBM bytes (real channels, each tensor read/written once)."""
     shape = {0: (net.in_h, net.in_w, net.in_c)}
@@ -355,10 +372,15 @@ def run_b200(args, rank, world, local_rank):
         tc_macs = sum(table[nm][0] for nm, _ in tc)
         tensor_peak = 2 * pk["bf16_tflops_sustained"] if i8 else pk["bf16_tflops_sustained"]
         achieved = 2 * tc_macs / (tc_ms / 1e3) / 1e12 if tc_ms else 0.0
+        traffic, traffic_src = ncu_traffic(args.workload)
+        roof_ms = network_roofline_ms(table, pk, i8)
         roofline = {
             "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, %d launches/step)" % len(tc),
             "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-            "frac": achieved / tensor_peak if tensor_peak else None, "traffic": None,
+            "frac": achieved / tensor_peak if tensor_peak else None, "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_flops_per_launch": 2 * tc_macs / max(len(tc), 1),
+            "algorithmic_bytes_per_launch": sum(table[nm][1] for nm, _ in tc) / max(len(tc), 1),
+            "network_roofline_ms": roof_ms, "network_roofline_frac": roof_ms / (ms / args.steps),
             "peak_source": ("2 x " if i8 else "") + f"{pk['source']} sustained cuBLAS bf16 (MEASURED_PEAKS.json)",
             "share_of_step": tc_ms / tot_ms if tot_ms else None,
             "per_launch_ms": {nm: round(t / c, 5) for nm, t, c in prof if c},

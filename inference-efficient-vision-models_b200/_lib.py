@@ -12,7 +12,7 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "libievm_b200.so")
+LIB_PATH = os.environ.get("IEVM_LIB_PATH") or os.path.join(PKG_DIR, "libievm_b200.so")   # override: A/B builds
 CSRC = os.path.join(PKG_DIR, "csrc")
 
 NVCC_FLAGS = [
@@ -63,19 +63,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/ievm.cu for sm_100a into libievm_b200.so (in-tree, so it travels to the GPU box)."""
-    if not force and not needs_build():
-        return LIB_PATH
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """Compile csrc/ievm.cu for sm_100a into libievm_b200.so (in-tree, so it travels to the GPU box).
+    ``defines`` / ``out`` build an experimental variant (-DNAME=VALUE ...) to another path."""
+    out = out or LIB_PATH
+    if not force and not defines and not needs_build():
+        return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH, os.path.join(CSRC, "ievm.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
+        ["-o", out, os.path.join(CSRC, "ievm.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out
 
 
 _lib = None

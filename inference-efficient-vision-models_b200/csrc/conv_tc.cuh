@@ -15,9 +15,12 @@
 //   quantized::add_relu with the residual; FP16 bias (+residual) (+ReLU).
 //
 // Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..17 = epilogue (TMEM lane quadrant = warp % 4; the four warps of a quadrant interleave
-// 16-column chunks).  The epilogue is latency-bound (TMEM load -> LDS -> dependent float chain), so it
-// gets as many warps as the register file allows.
+// warps 2..17 = epilogue, organised as FOUR GROUPS of four warps (one per TMEM lane quadrant, = warp % 4).
+// A group owns whole tiles (tile sequence number % 4 == group) and walks all of the tile's 16-column chunks;
+// accumulators sit in a ring of up to eight TMEM buffers.  The groups therefore run out of phase with one
+// another and with the MMA warp: the conversion / float / integer pipes see a steady mix instead of sixteen
+// warps hitting the same pipe at the same moment, a group's TMEM-load and residual-fetch latency hides behind
+// the other groups' arithmetic, and the per-tile bookkeeping is paid once per 128 x bn outputs per warp.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -27,7 +30,9 @@ namespace ievm {
 
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 16;
-constexpr int kEpiSub = kEpiWarps / 4;     // epilogue warps per TMEM lane quadrant; they interleave 16-column chunks
+constexpr int kEpiSub = kEpiWarps / 4;     // epilogue warps per TMEM lane quadrant (stem_tc.cuh: they interleave chunks)
+constexpr int kEpiGroups = kEpiWarps / 4;  // conv_tc_kernel: groups of four warps, each owning every 4th tile
+constexpr int kMaxAcc = 8;                 // accumulator buffers in TMEM (512 columns / 64)
 constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 
 enum : int { kDtypeI8 = 0, kDtypeF16 = 1 };
@@ -59,8 +64,11 @@ struct ConvTcParams {
   int h_in, w_in, wp;  // input height / width, wp = w_in + 2
   int tiles_per_img;
   uint32_t tpi_magic, wp_magic, hw_magic, wo_magic;   // ceil(2^32 / d), or 0 = divide normally: see fast_div
-  int tmem_cols;       // power of two >= 32 covering two accumulator buffers
-  int acc_stride;      // column offset of the second accumulator buffer
+  int tmem_cols;       // power of two >= 32 covering the accumulator ring
+  int acc_stride;      // column distance between accumulator buffers (power of two >= bn)
+  int nacc;            // accumulator buffers in the ring (2 .. kMaxAcc)
+  int fast_round;      // i8: |requantised value| < 2^21 for every possible input (checked at engine creation), so
+                       // round-to-nearest-even may use the 1.5*2^23 magic add instead of F2I (8 cycles/warp on B200)
   int cout_pad;        // n_tiles * bn
   uint32_t idesc;
   // epilogue
@@ -139,22 +147,33 @@ struct AddReluConst {
   int add_zp;
 };
 
+// rne(x) + zp as an integer.  kFast: (x + 1.5*2^23) rounds to an integer with ties to even (the magic constant is
+// even), and its bit pattern minus the constant's is that integer -- one FADD + one IADD instead of F2I.
+constexpr int kRoundMagicBits = 0x4B400000;
+template <bool kFast>
+__device__ __forceinline__ int round_add(float x, int zp) {
+  if (kFast) return __float_as_int(__fadd_rn(x, 12582912.0f)) + (zp - kRoundMagicBits);
+  return __float2int_rn(x) + zp;
+}
+
 // 16 accumulators -> 16 requantised bytes (no residual).
+template <bool kFast>
 __device__ __forceinline__ uint4 epilogue16_i8(const uint32_t (&v)[16], const float* s_bd, const float* s_mu, int zp,
                                                int lo) {
   int q[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
+#ifdef IEVM_EXP_NOTABLE
+    const float4 b4 = make_float4(s_bd[0], s_bd[0], s_bd[0], s_bd[0]);   // timing experiment: one broadcast load
+    const float4 m4 = make_float4(s_mu[0], s_mu[0], s_mu[0], s_mu[0]);
+#else
     const float4 b4 = *reinterpret_cast<const float4*>(s_bd + 4 * j);
     const float4 m4 = *reinterpret_cast<const float4*>(s_mu + 4 * j);
-    q[4 * j + 0] = __float2int_rn(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 0])), b4.x), m4.x)) + zp;
-    q[4 * j + 1] = __float2int_rn(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 1])), b4.y), m4.y)) + zp;
-    q[4 * j + 2] = __float2int_rn(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 2])), b4.z), m4.z)) + zp;
-    q[4 * j + 3] = __float2int_rn(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 3])), b4.w), m4.w)) + zp;
-  }
-  if (lo > 0) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) q[i] = max(q[i], lo);
+#endif
+    q[4 * j + 0] = max(round_add<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 0])), b4.x), m4.x), zp), lo);
+    q[4 * j + 1] = max(round_add<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 1])), b4.y), m4.y), zp), lo);
+    q[4 * j + 2] = max(round_add<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 2])), b4.z), m4.z), zp), lo);
+    q[4 * j + 3] = max(round_add<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 3])), b4.w), m4.w), zp), lo);
   }
   return make_uint4(pack4_sat_u8(q[0], q[1], q[2], q[3]), pack4_sat_u8(q[4], q[5], q[6], q[7]),
                     pack4_sat_u8(q[8], q[9], q[10], q[11]), pack4_sat_u8(q[12], q[13], q[14], q[15]));
@@ -163,6 +182,7 @@ __device__ __forceinline__ uint4 epilogue16_i8(const uint32_t (&v)[16], const fl
 // 16 accumulators + 16 residual bytes -> 16 bytes of quantized::add_relu(requant(acc), residual).
 // All float steps reproduce the scalar definition exactly: clamping before rounding commutes with
 // RNE because the clamp bounds are integers, and (x + M) - M is RNE for |x| <= 256.
+template <bool kFast>
 __device__ __forceinline__ uint4 epilogue16_i8_res(const uint32_t (&v)[16], const uint4 r4, const float* s_bd,
                                                    const float* s_mu, const AddReluConst& k) {
   const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
@@ -182,7 +202,7 @@ __device__ __forceinline__ uint4 epilogue16_i8_res(const uint32_t (&v)[16], cons
       const float a = __fmul_rn(t, k.a_scale);
       const float rb = __fadd_rn(__uint_as_float(__byte_perm(rw[j], 0x4B400000u, 0x7650 + b)), -k.r_bias);
       const float s = fmaxf(__fadd_rn(a, __fmul_rn(rb, k.r_scale)), 0.0f);
-      q[i] = __float2int_rn(__fmul_rn(s, k.inv_scale)) + k.add_zp;
+      q[i] = round_add<kFast>(__fmul_rn(s, k.inv_scale), k.add_zp);
     }
   }
   return make_uint4(pack4_sat_u8(q[0], q[1], q[2], q[3]), pack4_sat_u8(q[4], q[5], q[6], q[7]),
@@ -241,6 +261,14 @@ template <int kDtype, bool kHasRes>
 __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint32_t (&v)[16], const uint4 r4, int m,
                                                bool valid, int ch, const float* s_ep0, const float* s_ep1,
                                                const AddReluConst& k) {
+#ifdef IEVM_EXP_EPI_LDTM
+  // timing experiment: TMEM loads only -- fold the words so that the loads stay, store never happens
+  uint32_t x = v[0];
+#pragma unroll
+  for (int j = 1; j < 16; ++j) x ^= v[j];
+  if (x == 0x12345679u && m < 0) *(static_cast<uint32_t*>(p.out) + ch) = x;
+  return;
+#endif
   if (valid && p.dump_acc != nullptr) {
     int4* d = reinterpret_cast<int4*>(p.dump_acc + static_cast<size_t>(m) * p.dump_pitch + ch);
 #pragma unroll
@@ -252,11 +280,17 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
     uint8_t* op = static_cast<uint8_t*>(p.out) + static_cast<size_t>(m) * p.out_pitch + ch;
     uint4 o;
     if (kHasRes) {
-      o = epilogue16_i8_res(v, r4, s_ep0 + ch, s_ep1 + ch, k);
+      o = p.fast_round ? epilogue16_i8_res<true>(v, r4, s_ep0 + ch, s_ep1 + ch, k)
+                       : epilogue16_i8_res<false>(v, r4, s_ep0 + ch, s_ep1 + ch, k);
     } else {
-      o = epilogue16_i8(v, s_ep0 + ch, s_ep1 + ch, p.out_zp, p.out_lo);
+      o = p.fast_round ? epilogue16_i8<true>(v, s_ep0 + ch, s_ep1 + ch, p.out_zp, p.out_lo)
+                       : epilogue16_i8<false>(v, s_ep0 + ch, s_ep1 + ch, p.out_zp, p.out_lo);
     }
+#ifdef IEVM_EXP_NOSTORE
+    if (valid && m < 0) *reinterpret_cast<uint4*>(op) = o;      // timing experiment: keep the math, drop the store
+#else
     if (valid) *reinterpret_cast<uint4*>(op) = o;
+#endif
   } else {
     __half* op = static_cast<__half*>(p.out) + static_cast<size_t>(m) * p.out_pitch + ch;
     const __half* rp = static_cast<const __half*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch;
@@ -291,8 +325,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ep1 + p.cout_pad);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* bres_bar = tempty_bar + 2;
+  uint64_t* tempty_bar = tfull_bar + kMaxAcc;
+  uint64_t* bres_bar = tempty_bar + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;       // warp-uniform
@@ -311,9 +345,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < p.nacc; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kCluster * kEpiWarps);   // one arrival per epilogue warp (of both CTAs of a pair)
+      // one arrival per warp of the owning group (of both CTAs of a pair); groups = min(4, nacc), see the epilogue
+      mbar_init(&tempty_bar[i], kCluster * kEpiWarps / (p.nacc < kEpiGroups ? p.nacc : kEpiGroups));
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -362,8 +397,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int oy_first = fast_div(p0, p.wp, p.wp_magic);
         wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
         if (elect_one()) {
+#ifdef IEVM_EXP_NOTMA
+          mbar_arrive(&full_bar[stage]);                         // timing experiment: no activation loads
+#else
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], 0, -1, oy_first - 1, img);
+#endif
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -463,9 +502,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step + static_cast<uint32_t>(x0) * row16;
         if (elect_one()) {
+#ifndef IEVM_EXP_NOMMA
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap)
             mma_kblock(d_tmem, a_lo + tap_off[tap], b_lo0 + static_cast<uint32_t>(tap) * b_step, tap != 0 ? 1u : 0u);
+#endif
           umma_commit(&empty_bar[stage]);
           umma_commit(&tfull_bar[acc]);
         }
@@ -497,13 +538,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == p.nacc) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
     }
   } else {
     // ================================ epilogue ================================
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;        // 0 .. kEpiSub-1: which of the quadrant's warps
+    // groups = min(4, nacc) so that a TMEM buffer is always drained by the same group: a waiter can tell only
+    // adjacent mbarrier phases apart, so it has to see every phase of the barriers it waits on.  With two
+    // buffers (bn > 128) there are two groups of eight warps, two per quadrant, which interleave chunks.
+    const int groups = p.nacc < kEpiGroups ? p.nacc : kEpiGroups;      // 2 or 4
+    const int group = ((warp - 2) >> 2) & (groups - 1);
+    const int sub = ((warp - 2) >> 2) / groups;                        // which of the group's warps of this quadrant
+    const int csub = kEpiGroups / groups;                              // warps per quadrant in a group
     const int row = quad * 32 + lane;
     const int nchunks = p.bn >> 4;
     griddep_wait();                     // before the first residual read / output store
@@ -515,9 +564,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     k.inv_scale = p.inv_add_scale;
     k.r_bias = kRoundMagic + static_cast<float>(p.res_zp);
     k.add_zp = p.add_zp;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+    int acc_next = 0, seq = 0;
+    uint32_t acc_phase_next = 0;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++seq) {
+      const int acc = acc_next;
+      const uint32_t acc_phase = acc_phase_next;
+      if (++acc_next == p.nacc) {
+        acc_next = 0;
+        acc_phase_next ^= 1u;
+      }
+      if ((seq & (groups - 1)) != group) continue;
       int m, n0;
       bool valid;
       if (kMode == kModeHalo) {
@@ -539,7 +595,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       constexpr bool kResI8 = kHasRes && kDtype == kDtypeI8;
       uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
-      int c = half;
+      int c = sub;
       if (kResI8 && c < nchunks) ra = load_res16_i8(p, m, valid, n0 + c * 16);   // does not depend on the MMA
       wait_or_die(&tfull_bar[acc], acc_phase, 0x400u | acc, p.stuck_flag);
       tc_fence_after();
@@ -548,23 +604,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // two register buffers: the TMEM load (and residual fetch) of the next chunk is in flight while this
       // one is processed
       uint32_t va[16], vb[16];
+#ifdef IEVM_EXP_EPI_NONE
+      c = nchunks;                                               // timing experiment: epilogue does nothing
+#endif
       if (c < nchunks) tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), va);
       while (c < nchunks) {
         tmem_ld_wait();
-        if (c + kEpiSub < nchunks) {
-          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + kEpiSub) * 16), vb);
-          if (kResI8) rb = load_res16_i8(p, m, valid, n0 + (c + kEpiSub) * 16);
+        if (c + csub < nchunks) {
+          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + csub) * 16), vb);
+          if (kResI8) rb = load_res16_i8(p, m, valid, n0 + (c + csub) * 16);
         }
         epilogue_chunk<kDtype, kHasRes>(p, va, ra, m, valid, n0 + c * 16, s_ep0, s_ep1, k);
-        c += kEpiSub;
+        c += csub;
         if (c >= nchunks) break;
         tmem_ld_wait();
-        if (c + kEpiSub < nchunks) {
-          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + kEpiSub) * 16), va);
-          if (kResI8) ra = load_res16_i8(p, m, valid, n0 + (c + kEpiSub) * 16);
+        if (c + csub < nchunks) {
+          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + csub) * 16), va);
+          if (kResI8) ra = load_res16_i8(p, m, valid, n0 + (c + csub) * 16);
         }
         epilogue_chunk<kDtype, kHasRes>(p, vb, rb, m, valid, n0 + c * 16, s_ep0, s_ep1, k);
-        c += kEpiSub;
+        c += csub;
       }
       tc_fence_before();
       __syncwarp();
@@ -572,8 +631,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (kCluster > 1 && !leader) mbar_arrive_remote(&tempty_bar[acc], 0u);   // the leader's MMA warp waits for both
         else mbar_arrive(&tempty_bar[acc]);
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
     }
   }
 

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -132,6 +133,7 @@ struct LayerPlan {
   int kc_bytes = 0, kc_elems = 0, kchunks = 0, cin_w = 0;
   int stages = 0, tmem_cols = 0, resident_b = 0;
   int mode = 0;                 // kModeIm2col | kModeHalo
+  int fast_round = 0;           // see ConvTcParams::fast_round
   int cluster = 1;              // CTAs per cluster sharing the weight tile by TMA multicast
   int max_clusters = 0;         // co-resident clusters the device can hold (cluster > 1)
   int wp = 0, patch_rows = 0, tiles_per_img = 0, a_stage_bytes = 0, a_tx_bytes = 0;
@@ -299,7 +301,7 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
     }
     const int row_bytes = L.cin_pitch * h->elem;
     constexpr int kMaxStages = 16;
-    const int fixed = 1024 /*alignment slack*/ + 2 * L.cout_pad * 4 + (2 * kMaxStages + 5) * 8 + 16;
+    const int fixed = 1024 /*alignment slack*/ + 2 * L.cout_pad * 4 + (2 * kMaxStages + 2 * kMaxAcc + 1) * 8 + 16;
     const int avail = h->smem_optin - fixed;
     L.tmem_cols = 32;
     while (L.tmem_cols < 2 * L.bn) L.tmem_cols *= 2;
@@ -405,6 +407,19 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
       ep0[c] = d.bias[c] / atw;
       ep1[c] = atw / d.out_scale;
     }
+    // Magic-number rounding is exact while the value being rounded stays below 2^22 in magnitude.  Bound it over
+    // every possible input: |acc| <= 255 * sum|w| (activations are u8, zero point 0 or a border of zero points).
+    double vmax = 0.0;
+    const int8_t* w = static_cast<const int8_t*>(d.weight);
+    const size_t per_out = static_cast<size_t>(d.cin) * taps;
+    for (int c = 0; c < d.cout; ++c) {
+      double sw = 0.0;
+      for (size_t i = 0; i < per_out; ++i) sw += std::abs(static_cast<int>(w[c * per_out + i]));
+      vmax = std::max(vmax, (255.0 * sw + std::fabs(static_cast<double>(ep0[c]))) * std::fabs(static_cast<double>(ep1[c])));
+    }
+    if (d.res_tensor >= 0) vmax = std::max(vmax, 256.0 * (static_cast<double>(d.out_scale) + d.res_scale) / d.add_scale);
+    L.fast_round = vmax < 2097152.0 ? 1 : 0;       // 2^21: a factor two of margin
+    if (const char* e = getenv("IEVM_FAST_ROUND")) L.fast_round = L.fast_round && atoi(e);
   } else {
     for (int c = 0; c < d.cout; ++c) ep0[c] = d.bias[c];
   }
@@ -734,8 +749,12 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   p.hw_magic = magic(static_cast<long long>(L.ho) * L.wo, static_cast<long long>(p.m_total) + 4 * kTileM);
   p.wo_magic = magic(L.wo, static_cast<long long>(L.ho) * L.wo);
   p.cout_pad = L.cout_pad;
-  p.tmem_cols = L.tmem_cols;
-  p.acc_stride = L.tmem_cols / 2;
+  // accumulator ring: buffers a power-of-two number of columns apart, as many as TMEM's 512 columns hold (<= 8)
+  p.acc_stride = 32;
+  while (p.acc_stride < L.bn) p.acc_stride *= 2;
+  p.nacc = std::max(2, std::min(kMaxAcc, 512 / p.acc_stride));
+  p.tmem_cols = p.nacc * p.acc_stride;
+  p.fast_round = L.fast_round;
   const int mma_m = L.cluster > 1 ? 256 : 128;             // a CTA pair issues M = 256 instructions
   p.idesc = h->dtype == IEVM_DTYPE_I8 ? make_idesc_i8_u8s8(L.bn, mma_m) : make_idesc_f16(L.bn, mma_m);
   p.out = tensor_ptr(h, d.out_tensor);
@@ -1219,9 +1238,9 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
     for (size_t i = 0; i < h->layers.size(); ++i) {
       const LayerPlan& L = h->layers[i];
       if (L.d.op != IEVM_OP_CONV || L.is_stem) continue;
-      fprintf(stderr, "[ievm] layer %2zu %dx%d s%d %4d->%4d @%dx%d mode=%s kc=%d kchunks=%d bn=%d n_tiles=%d cluster=%d stages=%d residentB=%d smem=%zu\n",
+      fprintf(stderr, "[ievm] layer %2zu %dx%d s%d %4d->%4d @%dx%d mode=%s kc=%d kchunks=%d bn=%d n_tiles=%d cluster=%d stages=%d residentB=%d fast_round=%d smem=%zu\n",
               i, L.d.ksize, L.d.ksize, L.d.stride, L.d.cin, L.d.cout, L.ho, L.wo, L.mode == kModeHalo ? "halo" : "im2col",
-              L.kc_bytes, L.kchunks, L.bn, L.n_tiles, L.cluster, L.stages, L.resident_b, L.smem_bytes);
+              L.kc_bytes, L.kchunks, L.bn, L.n_tiles, L.cluster, L.stages, L.resident_b, L.fast_round, L.smem_bytes);
     }
   }
   if (rc == IEVM_OK) rc = assign_buffers(h);

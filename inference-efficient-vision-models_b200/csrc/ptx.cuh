@@ -71,6 +71,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if IEVM_TRYWAIT_HINT_NS > 0
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -80,6 +81,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(IEVM_TRYWAIT_HINT_NS))
       : "memory");
+#else
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 

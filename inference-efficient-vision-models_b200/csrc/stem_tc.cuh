@@ -218,7 +218,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemTcParams p)
             d[j] = make_int4(static_cast<int>(v[4 * j]), static_cast<int>(v[4 * j + 1]),
                              static_cast<int>(v[4 * j + 2]), static_cast<int>(v[4 * j + 3]));
         }
-        const uint4 o = epilogue16_i8(v, s_bd + ch, s_mu + ch, p.out_zp, p.out_lo);
+        const uint4 o = epilogue16_i8<false>(v, s_bd + ch, s_mu + ch, p.out_zp, p.out_lo);
         if (valid) *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.cpad + ch) = o;
       }
       tc_fence_before();
