@@ -145,6 +145,10 @@ struct AddReluConst {
   float a_scale, r_scale, inv_scale;
   float r_bias;            // kRoundMagic + res_zp: subtracting it turns (magic | byte) into (byte - res_zp)
   int add_zp;
+  // fast form (magic-number rounding allowed): integer clamps done by one VIADDMNMX.RELU each
+  int c1_add, c1_max;      // clamp(rne(v), lo, hi) - lo == max(min(bits(v + M) + c1_add, c1_max), 0)
+  int c2_add, c2_max;      // q - add_zp          == max(min(bits(u + M) + c2_add, c2_max), 0)
+  uint32_t zp4;            // add_zp in every byte
 };
 
 // rne(x) + zp as an integer.  kFast: (x + 1.5*2^23) rounds to an integer with ties to even (the magic constant is
@@ -197,16 +201,33 @@ __device__ __forceinline__ uint4 epilogue16_i8_res(const uint32_t (&v)[16], cons
     for (int b = 0; b < 4; ++b) {
       const int i = 4 * j + b;
       float t = __fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[i])), bd[b]), mu[b]);
-      t = fminf(fmaxf(t, k.lo_f), k.hi_f);
-      t = __fadd_rn(__fadd_rn(t, kRoundMagic), -kRoundMagic);          // == float(q2 - zp2)
-      const float a = __fmul_rn(t, k.a_scale);
       const float rb = __fadd_rn(__uint_as_float(__byte_perm(rw[j], 0x4B400000u, 0x7650 + b)), -k.r_bias);
-      const float s = fmaxf(__fadd_rn(a, __fmul_rn(rb, k.r_scale)), 0.0f);
-      q[i] = round_add<kFast>(__fmul_rn(s, k.inv_scale), k.add_zp);
+      if (kFast) {
+        // Integer clamps after the magic-number rounding: rne commutes with clamping to integer bounds, and
+        // max(s, 0) before the final scaling equals clamping the rounded value at 0 (the scale is positive), so
+        // each clamp pair is ONE add-min-relu instruction instead of two FMNMX (the ALU pipe issues at half rate).
+        const int tq = __viaddmin_s32_relu(__float_as_int(__fadd_rn(t, kRoundMagic)), k.c1_add, k.c1_max);   // q2 - lo
+        const float a = __fmul_rn(__fadd_rn(__int2float_rn(tq), k.lo_f), k.a_scale);                        // (q2 - zp2) * s2
+        const float u = __fmul_rn(__fadd_rn(a, __fmul_rn(rb, k.r_scale)), k.inv_scale);
+        q[i] = __viaddmin_s32_relu(__float_as_int(__fadd_rn(u, kRoundMagic)), k.c2_add, k.c2_max);          // q - add_zp
+      } else {
+        t = fminf(fmaxf(t, k.lo_f), k.hi_f);
+        t = __fadd_rn(__fadd_rn(t, kRoundMagic), -kRoundMagic);          // == float(q2 - zp2)
+        const float a = __fmul_rn(t, k.a_scale);
+        const float s = fmaxf(__fadd_rn(a, __fmul_rn(rb, k.r_scale)), 0.0f);
+        q[i] = __float2int_rn(__fmul_rn(s, k.inv_scale)) + k.add_zp;
+      }
     }
   }
-  return make_uint4(pack4_sat_u8(q[0], q[1], q[2], q[3]), pack4_sat_u8(q[4], q[5], q[6], q[7]),
-                    pack4_sat_u8(q[8], q[9], q[10], q[11]), pack4_sat_u8(q[12], q[13], q[14], q[15]));
+  uint4 o = make_uint4(pack4_sat_u8(q[0], q[1], q[2], q[3]), pack4_sat_u8(q[4], q[5], q[6], q[7]),
+                       pack4_sat_u8(q[8], q[9], q[10], q[11]), pack4_sat_u8(q[12], q[13], q[14], q[15]));
+  if (kFast) {     // bytes hold q - add_zp <= 255 - add_zp: the per-byte add cannot carry
+    o.x += k.zp4;
+    o.y += k.zp4;
+    o.z += k.zp4;
+    o.w += k.zp4;
+  }
+  return o;
 }
 
 template <bool kHasRes, bool kRelu>
@@ -564,6 +585,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     k.inv_scale = p.inv_add_scale;
     k.r_bias = kRoundMagic + static_cast<float>(p.res_zp);
     k.add_zp = p.add_zp;
+    k.c1_add = -kRoundMagicBits - (p.out_lo - p.out_zp);
+    k.c1_max = 255 - p.out_lo;
+    k.c2_add = -kRoundMagicBits;
+    k.c2_max = 255 - p.add_zp;
+    k.zp4 = static_cast<uint32_t>(p.add_zp) * 0x01010101u;
     int acc_next = 0, seq = 0;
     uint32_t acc_phase_next = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++seq) {
