@@ -324,6 +324,25 @@ def run_b200(args, rank, world, local_rank):
            "d2h_bytes_per_step": y_host.numel() * y_host.element_size(), "steps": e2e_steps,
            "how": "B200*ResNet.forward(cpu_tensor) -> ievm_forward_*_host: pinned H2D + forward + D2H per step"}
 
+    # ---- the same call fed with decoded 8-bit images (ToTensor+Normalize+quantize fused) ----
+    e2e_u8 = None
+    if i8:
+        xu8 = torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8,
+                            generator=torch.Generator().manual_seed(11 + rank)).pin_memory()
+        for _ in range(2):
+            eng.forward_u8(xu8)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            yu8 = eng.forward_u8(xu8)
+        barrier()
+        u8_s = max_over_ranks(time.perf_counter() - t0, dev)
+        e2e_u8 = {"value": world * n * e2e_steps / u8_s, "unit": "images/s",
+                  "h2d_bytes_per_step": xu8.numel(), "d2h_bytes_per_step": yu8.numel() * yu8.element_size(),
+                  "steps": e2e_steps,
+                  "how": "forward_u8(cpu uint8 NHWC images) -> ievm_forward_u8_host: the reference's ToTensor + Normalize "
+                         "(dataset.py:16-18) + quantize_per_tensor fused into the front-end kernel via a 3x256 LUT"}
+
     # ---- bs-1 latency (BASELINE.json: "p50 bs1 latency ms"; protocol of engines.py:26-34, synchronised) ----
     latency = None
     if rank == 0 and not args.no_latency:
@@ -398,7 +417,7 @@ def run_b200(args, rank, world, local_rank):
                        "l2_policy": "inputs larger than L2 (154 MB f32 batch vs 126 MB L2)" if i8 else
                                     "input batch 77 MB f16; activations stream through L2",
                        "cuda_graph": bool(args.graph)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": eng.launches_per_forward * args.steps,
+            "clocks": clocks, "e2e": e2e, "e2e_u8_pipeline": e2e_u8, "gpu_launches": eng.launches_per_forward * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "latency_bs1": latency,
             "logits_checksum": float(gathered.double().sum().item()),
         }

@@ -101,6 +101,16 @@ int ievm_forward_f16(ievm_handle* h, const void* x_nchw, int n, void* logits, vo
 int ievm_forward_i8_host(ievm_handle* h, const float* x_nchw_host, int n, float* logits_host);
 int ievm_forward_f16_host(ievm_handle* h, const void* x_nchw_host, int n, void* logits_host);
 
+/* SURVEY 8(f)-1, the input pipeline in front of the hot path.  INT8 engines accept decoded 8-bit images,
+ * x_nhwc = [n][224][224][3] u8 (RGB interleaved, what PIL / T.Resize hand to T.ToTensor in the reference's
+ * quantization/dataset.py:14-19), and fuse ToTensor + Normalize + quantize_per_tensor into the front-end kernel
+ * through a lookup table lut768 = [3][256] u8: lut[c][v] = quantised value of level v in channel c, which the host
+ * computes once with the reference's own float ops (ievm_b200.input_lut), so logits are bit-identical to feeding
+ * the f32 tensor.  Four times fewer input bytes over PCIe and HBM. */
+int ievm_set_input_lut(ievm_handle* h, const uint8_t* lut768);
+int ievm_forward_u8(ievm_handle* h, const uint8_t* x_nhwc, int n, float* logits, void* stream);
+int ievm_forward_u8_host(ievm_handle* h, const uint8_t* x_nhwc_host, int n, float* logits_host);
+
 /* Engine options: "conv_impl" 0 = tcgen05 tensor-core kernels (default), 1 = direct CUDA-core
  * cross-check kernels (tests only); "use_graph" 1 = replay forward() from a CUDA graph cached per
  * (n, x, logits) triple; "keep_tensors" 1 = one buffer per tensor (parity hooks); "profile" 1 =
@@ -149,6 +159,12 @@ int ievm_probe_im2col(const void* in_dev, int n, int h, int w, int c_pitch, int 
  * halo-patch convolution mode relies on. */
 int ievm_probe_patch(const void* in_dev, int n, int h, int w, int c_pitch, int rb, int img, int w0, int h0, int box_w,
                      int box_h, void* out_dev);
+
+/* the accumulation step of evaluate_accuracy (quantization/engines.py:59-63) on the device.
+ * logits: [n][classes] f32 (dtype IEVM_DTYPE_I8 engines) or f16 (IEVM_DTYPE_F16); labels int64 [n];
+ * counters2 (device, u64[2]) += {number of rows whose arg-max (lowest index on ties) equals the label, n}. */
+int ievm_count_correct(const void* logits, int dtype, const int64_t* labels, int n, int classes, uint64_t* counters2,
+                       void* stream);
 
 /* Soft-target KD evaluation loss over device logits (f32 [n][classes]) and labels (int64 [n]).
  * out3 (device, f32[3]) receives {mean CE, mean T^2*KL (batchmean), number correct};

@@ -25,7 +25,8 @@ EXPORTS = [
     "ievm_forward_f16_host", "ievm_set_option", "ievm_num_tensors", "ievm_tensor_shape",
     "ievm_launches_per_forward", "ievm_debug_read_tensor", "ievm_debug_conv_acc", "ievm_kd_loss",
     "ievm_last_error", "ievm_build_info", "ievm_probe_im2col", "ievm_profile_read", "ievm_probe_patch",
-    "ievm_debug_frontend",
+    "ievm_debug_frontend", "ievm_set_input_lut", "ievm_forward_u8", "ievm_forward_u8_host",
+    "ievm_count_correct",
 ]
 
 
@@ -113,6 +114,14 @@ def load():
     lib.ievm_probe_im2col.restype = C.c_int
     lib.ievm_probe_patch.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_void_p]
     lib.ievm_probe_patch.restype = C.c_int
+    lib.ievm_set_input_lut.argtypes = [H, C.c_void_p]
+    lib.ievm_set_input_lut.restype = C.c_int
+    lib.ievm_forward_u8.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ievm_forward_u8.restype = C.c_int
+    lib.ievm_forward_u8_host.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p]
+    lib.ievm_forward_u8_host.restype = C.c_int
+    lib.ievm_count_correct.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ievm_count_correct.restype = C.c_int
     lib.ievm_debug_frontend.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.ievm_debug_frontend.restype = C.c_int
     lib.ievm_profile_read.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]

@@ -61,7 +61,10 @@ constexpr int kF2Threads = 32 * (kF2EpiWarps + 2 + kF2QuantWarps);
 constexpr int kF2LowerPx = 16;                   // of a warpgroup's 28 pooled columns, the lane-c thread finishes 16
 constexpr int kF2XRows = 7;                      // uint4 rows of one exchange buffer (4 upper->lower, 3 lower->upper)
 
-template <int kDtype>
+// kIn: 0 = the path's native input (f32 NCHW for INT8, f16 NCHW for FP16); 1 = decoded 8-bit images, u8 NHWC (RGB
+// interleaved) mapped through a 3 x 256 lookup table that composes ToTensor, Normalize and quantize_per_tensor
+// (INT8 only; SURVEY 8(f)-1: the input pipeline in front of the hot path, 4x fewer input bytes).
+template <int kDtype, int kIn = 0>
 struct F2Cfg {
   static constexpr int kLpc = kDtype == kDtypeI8 ? 2 : 4;             // lines per chunk (a chunk = 4 input rows)
   static constexpr int kSegs = 2 * kLpc + 1;                          // lines one tile reads
@@ -72,13 +75,16 @@ struct F2Cfg {
   // (TMA faults on an 8-byte-aligned box start); they cover the 232 columns -4 .. 227 the records need
   static constexpr int kBoxX0 = kDtype == kDtypeI8 ? 4 : 8;
   static constexpr int kBoxW = 2 * kF2Rec + (kBoxX0 - 4) + (kDtype == kDtypeI8 ? 0 : 4);   // 232 / 240
-  static constexpr int kRawTx = 3 * 4 * kBoxW * kInElem;              // bytes one chunk's TMA delivers
+  // u8 NHWC rows are described to TMA as 32-bit words (box <= 256 elements): 176 words = 16 bytes before the
+  // image + 228 pixels x 3 bytes, rounded up to 16 bytes
+  static constexpr int kU8RowBytes = 704;
+  static constexpr int kRawTx = kIn == 1 ? 4 * kU8RowBytes : 3 * 4 * kBoxW * kInElem;   // bytes one chunk's TMA delivers
   static constexpr int kRawStride = (kRawTx + 127) / 128 * 128;
   static constexpr int kLines = kF2ChunkSlots * kLpc;                 // power of two
   static constexpr int kRecsPerChunk = kLpc * kF2Rec;
   static constexpr size_t kSmemBytes = 1024 + kABytes + static_cast<size_t>(kLines) * kF2LinePitch +
                                        static_cast<size_t>(kF2RawSlots) * kRawStride +
-                                       2 * 2 * kF2XRows * 64 * 16 + 64 * 8 + 16;
+                                       2 * 2 * kF2XRows * 64 * 16 + 64 * 8 + 32 + (kIn == 1 ? 768 : 0);
 };
 
 struct Frontend2Params {
@@ -93,6 +99,7 @@ struct Frontend2Params {
   const float* bdiv;         // i8: bias / (x_s * w_s[c]);  f16: folded bias
   const float* mult;         // i8: (x_s * w_s[c]) / out_s
   const int* zwsum;          // i8: in_zp * sum(w[c])
+  const uint8_t* lut;        // u8 input mode: [3][256] quantised value of every 8-bit level per channel
   int out_zp, out_lo;
   int32_t* dump_acc;         // debug: corrected stem accumulators [n][ho][112][64] (f16: float bit patterns)
   unsigned int* stuck_flag;
@@ -267,10 +274,10 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
   }
 }
 
-template <int kDtype>
+template <int kDtype, int kIn>
 __global__ void __launch_bounds__(kF2Threads, 1)
 frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Params p) {
-  using Cfg = F2Cfg<kDtype>;
+  using Cfg = F2Cfg<kDtype, kIn>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -285,6 +292,7 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
   uint64_t* tmem_full = line_empty + kF2ChunkSlots;
   uint64_t* tmem_empty = tmem_full + kF2TmemSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kF2TmemSlots);
+  uint8_t* sLut = reinterpret_cast<uint8_t*>(tmem_slot + 4);      // u8 input mode: [3][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -295,6 +303,9 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
     uint4* dst = reinterpret_cast<uint4*>(sW);
     for (int i = threadIdx.x; i < Cfg::kABytes / 16; i += kF2Threads) dst[i] = __ldg(src + i);
     fence_proxy_async_smem();
+    if (kIn == 1)
+      for (int i = threadIdx.x; i < 768 / 4; i += kF2Threads)
+        reinterpret_cast<uint32_t*>(sLut)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.lut) + i);
   }
   if (warp == kF2TmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -376,8 +387,12 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
         wait_or_die(&raw_empty[slot], ((q / kF2RawSlots) & 1u) ^ 1u, 0x800u | slot, p.stuck_flag);
         if (elect_one()) {
           mbar_expect_tx(&raw_full[slot], static_cast<uint32_t>(Cfg::kRawTx));
-          tma_load_3d(sRaw + slot * Cfg::kRawStride, &tmap_x, &raw_full[slot], -Cfg::kBoxX0, 4 * (un.t0 - 1 + j) - Cfg::kRowOff,
-                      3 * un.img);
+          if (kIn == 1)     // (32-bit words of a row, row, image): 4 words = 16 bytes before the first pixel
+            tma_load_3d(sRaw + slot * Cfg::kRawStride, &tmap_x, &raw_full[slot], -4, 4 * (un.t0 - 1 + j) - Cfg::kRowOff,
+                        un.img);
+          else
+            tma_load_3d(sRaw + slot * Cfg::kRawStride, &tmap_x, &raw_full[slot], -Cfg::kBoxX0, 4 * (un.t0 - 1 + j) - Cfg::kRowOff,
+                        3 * un.img);
         }
         __syncwarp();
       }
@@ -394,7 +409,42 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
         wait_or_die(&line_empty[cs], ((q / kF2ChunkSlots) & 1u) ^ 1u, 0x818u | cs, p.stuck_flag);
         const uint8_t* raw = sRaw + slot * Cfg::kRawStride;
         uint8_t* lines = sLines + cs * Cfg::kLpc * kF2LinePitch;
-        if (kDtype == kDtypeI8) {
+        if (kIn == 1) {
+          // u8 NHWC rows: pixel column x, channel c at byte 16 + 3x + c of the raw row.  Record (l, ri) covers columns
+          // 2p, 2p+1 (p = ri - 2): six consecutive bytes per row, already in record order (cp*3 + c); each goes
+          // through the lookup table.  Out-of-image records hold the zero point.
+          const int row0 = 4 * (un.t0 - 1 + j) - Cfg::kRowOff;
+          const uint32_t zp4 = static_cast<uint32_t>(p.in_zp) * 0x01010101u;
+#pragma unroll
+          for (int it = 0; it < (Cfg::kRecsPerChunk + kF2QuantThreads - 1) / kF2QuantThreads; ++it) {
+            const int idx = qt + it * kF2QuantThreads;
+            if (idx < Cfg::kRecsPerChunk) {
+              const int l = idx >= kF2Rec ? 1 : 0;
+              const int ri = idx - l * kF2Rec;
+              const int pcol = ri - 2;
+              const int row = row0 + 2 * l;
+              uint4 o = make_uint4(zp4, zp4, zp4, 0u);
+              if (pcol >= 0 && pcol < kF2W / 2 && row >= 0 && row < p.h) {
+                uint32_t b[12];
+#pragma unroll
+                for (int rp = 0; rp < 2; ++rp) {
+                  const uint16_t* src = reinterpret_cast<const uint16_t*>(raw + (2 * l + rp) * Cfg::kU8RowBytes + 16 + 6 * pcol);
+                  const uint32_t h0 = src[0], h1 = src[1], h2 = src[2];      // bytes (c0 c1) (c2 c0') (c1' c2')
+                  b[rp * 6 + 0] = sLut[h0 & 0xffu];
+                  b[rp * 6 + 1] = sLut[256 + (h0 >> 8)];
+                  b[rp * 6 + 2] = sLut[512 + (h1 & 0xffu)];
+                  b[rp * 6 + 3] = sLut[h1 >> 8];
+                  b[rp * 6 + 4] = sLut[256 + (h2 & 0xffu)];
+                  b[rp * 6 + 5] = sLut[512 + (h2 >> 8)];
+                }
+                o.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+                o.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+                o.z = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+              }
+              *reinterpret_cast<uint4*>(lines + l * kF2LinePitch + ri * 16) = o;
+            }
+          }
+        } else if (kDtype == kDtypeI8) {
           // record (l, ri): rows 2l, 2l+1 of the chunk, raw columns 2ri, 2ri+1; byte = rp*6 + cp*3 + c
           const float* rf = reinterpret_cast<const float*>(raw);
 #pragma unroll

@@ -166,6 +166,7 @@ struct ievm_handle {
   int opt_front_v2 = 1;    // IEVM_FRONT_V2=0: first-generation fused front end (INT8) / separate kernels (FP16)
   int front2_ok = 0;       // the network's front end fits frontend_v2.cuh (224-wide input, <= 64 stem channels)
   int front_tpu = 0;       // IEVM_FRONT_TPU: pooled rows per work unit (0 = heuristic)
+  uint8_t* lut_dev = nullptr;   // u8 input mode: [3][256] level -> quantised value (ievm_set_input_lut)
   size_t fe_smem = 0;
   int opt_cluster = 1;     // IEVM_CLUSTER=0: no 2-CTA clusters / weight multicast
   int opt_pdl = 1;         // IEVM_PDL=0: no programmatic dependent launch
@@ -925,13 +926,24 @@ int front2_tiles_per_unit(const ievm_handle* h, int n, int ph) {
   return best;
 }
 
-int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32_t* dump_acc) {
+int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32_t* dump_acc, bool u8_input = false) {
   const LayerPlan& Ls = h->layers[0];
   const LayerPlan& Lp = h->layers[1];
   const bool i8 = h->dtype == IEVM_DTYPE_I8;
-  // the input batch as (W, H, 3 * n) planes; boxes start 4 columns left of the image and are zero-filled outside
   CUtensorMap tmap;
-  {
+  if (u8_input) {
+    // decoded images [n][H][W][3] u8 as (32-bit words of a row, H, n); a box = 4 rows x 176 words starting 16 bytes
+    // before the row (TMA wants the box start on a 16-byte boundary)
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(h->in_w) * 3 / 4, static_cast<cuuint64_t>(h->in_h), static_cast<cuuint64_t>(n)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(h->in_w) * 3, static_cast<cuuint64_t>(h->in_w) * 3 * h->in_h};
+    cuuint32_t box[3] = {F2Cfg<kDtypeI8, 1>::kU8RowBytes / 4, 4, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = g_encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(x), dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled (u8 input) failed: CUresult %d", (int)r);
+  } else {
+    // the input batch as (W, H, 3 * n) planes; boxes start 4 columns left of the image and are zero-filled outside
     const size_t es = i8 ? 4 : 2;
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(h->in_w), static_cast<cuuint64_t>(h->in_h), static_cast<cuuint64_t>(3) * n};
     cuuint64_t strides[2] = {h->in_w * es, static_cast<cuuint64_t>(h->in_w) * h->in_h * es};
@@ -959,13 +971,15 @@ int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32
   fp.bdiv = Ls.ep0;
   fp.mult = Ls.ep1;
   fp.zwsum = Ls.zwsum;
+  fp.lut = h->lut_dev;
   fp.out_zp = Ls.d.out_zp;
   fp.out_lo = Ls.d.relu ? Ls.d.out_zp : 0;
   fp.dump_acc = dump_acc;
   fp.stuck_flag = h->stuck_dev;
   const int grid = std::min(n * fp.upi, h->num_sms);
-  if (i8) frontend2_kernel<kDtypeI8><<<grid, kF2Threads, F2Cfg<kDtypeI8>::kSmemBytes, s>>>(tmap, fp);
-  else frontend2_kernel<kDtypeF16><<<grid, kF2Threads, F2Cfg<kDtypeF16>::kSmemBytes, s>>>(tmap, fp);
+  if (u8_input) frontend2_kernel<kDtypeI8, 1><<<grid, kF2Threads, F2Cfg<kDtypeI8, 1>::kSmemBytes, s>>>(tmap, fp);
+  else if (i8) frontend2_kernel<kDtypeI8, 0><<<grid, kF2Threads, F2Cfg<kDtypeI8>::kSmemBytes, s>>>(tmap, fp);
+  else frontend2_kernel<kDtypeF16, 0><<<grid, kF2Threads, F2Cfg<kDtypeF16>::kSmemBytes, s>>>(tmap, fp);
   CUDA_TRY(cudaGetLastError());
   return IEVM_OK;
 }
@@ -1008,7 +1022,7 @@ bool front_end_is_chunked(const ievm_handle* h) {
          h->layers[1].d.in_tensor == h->layers[0].d.out_tensor && h->tensors[h->layers[0].d.out_tensor].last_use == 1;
 }
 
-int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStream_t s) {
+int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStream_t s, bool u8_input = false) {
   const bool i8 = h->dtype == IEVM_DTYPE_I8;
   const bool prof = h->profile != 0;
   if (prof) {
@@ -1022,10 +1036,14 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     CUDA_TRY(cudaEventRecord(h->prof_events[0], s));
   }
   size_t first_layer = 0;
+  if (u8_input && !front_end_is_v2(h))
+    return fail(IEVM_ERR_UNSUPPORTED, "8-bit image input needs the fused front end (224-wide input, <= 64 stem channels, "
+                                      "keep_tensors = 0, conv_impl = 0)");
+  if (u8_input && h->lut_dev == nullptr) return fail(IEVM_ERR_BAD_ARG, "call ievm_set_input_lut before ievm_forward_u8");
   if (front_end_is_v2(h)) {
     // profile slots: the fused kernel is attributed to the stem's slot (quantize and maxpool read 0)
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
-    if (int rc = launch_frontend2(h, x, n, s, nullptr)) return rc;
+    if (int rc = launch_frontend2(h, x, n, s, nullptr, u8_input)) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[2], s));
     first_layer = 2;
   } else if (front_end_is_fused(h)) {
@@ -1100,21 +1118,21 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
   return IEVM_OK;
 }
 
-int forward_common(ievm_handle* h, int want_dtype, const void* x, int n, void* logits, void* stream) {
+int forward_common(ievm_handle* h, int want_dtype, const void* x, int n, void* logits, void* stream, bool u8_input = false) {
   if (!h || !x || !logits) return fail(IEVM_ERR_BAD_ARG, "null argument");
   if (h->dtype != want_dtype) return fail(IEVM_ERR_BAD_ARG, "engine dtype does not match this entry point");
   if (n < 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "batch %d outside [0, %d]", n, h->max_batch);
   if (n == 0) return IEVM_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!h->use_graph || h->profile) return enqueue_forward(h, x, n, logits, s);
-  const auto key = std::make_tuple(n, x, logits);
+  if (!h->use_graph || h->profile) return enqueue_forward(h, x, n, logits, s, u8_input);
+  const auto key = std::make_tuple(u8_input ? -n : n, x, logits);
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
     cudaStream_t cs = h->own_stream;
     cudaGraph_t graph = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_forward(h, x, n, logits, cs);
+    const int rc = enqueue_forward(h, x, n, logits, cs, u8_input);
     const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(IEVM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -1298,9 +1316,13 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   }
   if (rc == IEVM_OK && h->front2_ok) {
     const cudaError_t e = h->dtype == IEVM_DTYPE_I8
-        ? cudaFuncSetAttribute(frontend2_kernel<kDtypeI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2Cfg<kDtypeI8>::kSmemBytes)
-        : cudaFuncSetAttribute(frontend2_kernel<kDtypeF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2Cfg<kDtypeF16>::kSmemBytes);
+        ? cudaFuncSetAttribute(frontend2_kernel<kDtypeI8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2Cfg<kDtypeI8>::kSmemBytes)
+        : cudaFuncSetAttribute(frontend2_kernel<kDtypeF16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2Cfg<kDtypeF16>::kSmemBytes);
     if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend2_kernel): %s", cudaGetErrorString(e));
+    if (rc == IEVM_OK && h->dtype == IEVM_DTYPE_I8 &&
+        cudaFuncSetAttribute(frontend2_kernel<kDtypeI8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)F2Cfg<kDtypeI8, 1>::kSmemBytes) != cudaSuccess)
+      rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend2_kernel, u8 input) failed");
   }
   if (rc == IEVM_OK) {
     for (const LayerPlan& L : h->layers)
@@ -1356,15 +1378,16 @@ int ievm_forward_f16(ievm_handle* h, const void* x, int n, void* logits, void* s
   return forward_common(h, IEVM_DTYPE_F16, x, n, logits, stream);
 }
 
-static int forward_host_common(ievm_handle* h, int dtype, const void* x_host, int n, void* logits_host) {
+static int forward_host_common(ievm_handle* h, int dtype, const void* x_host, int n, void* logits_host, bool u8_input = false) {
   if (!h || !x_host || !logits_host) return fail(IEVM_ERR_BAD_ARG, "null argument");
   if (n <= 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "batch %d outside [1, %d]", n, h->max_batch);
   CUDA_TRY(cudaSetDevice(h->device));
-  const size_t in_elem = dtype == IEVM_DTYPE_I8 ? 4 : 2;
+  const size_t in_elem = u8_input ? 1 : (dtype == IEVM_DTYPE_I8 ? 4 : 2);
   const size_t out_elem = dtype == IEVM_DTYPE_I8 ? 4 : 2;
   const size_t per_img = static_cast<size_t>(h->in_c) * h->in_h * h->in_w * in_elem;
   if (!h->stage_in) {
-    CUDA_TRY(cudaMalloc(&h->stage_in, per_img * h->max_batch));
+    const size_t native = static_cast<size_t>(h->in_c) * h->in_h * h->in_w * (dtype == IEVM_DTYPE_I8 ? 4 : 2);
+    CUDA_TRY(cudaMalloc(&h->stage_in, native * h->max_batch));
     CUDA_TRY(cudaMalloc(&h->stage_out, out_elem * h->classes * h->max_batch));
   }
   // Chunked pipeline: the H2D copy of chunk i+1 (copy stream) overlaps the forward of chunk i (compute
@@ -1388,7 +1411,7 @@ static int forward_host_common(ievm_handle* h, int dtype, const void* x_host, in
       CUDA_TRY(cudaStreamWaitEvent(s, h->copy_events[c], 0));
     }
     if (int rc = forward_common(h, dtype, static_cast<uint8_t*>(h->stage_in) + c0 * per_img, nc,
-                                static_cast<uint8_t*>(h->stage_out) + c0 * out_elem * h->classes, s)) return rc;
+                                static_cast<uint8_t*>(h->stage_out) + c0 * out_elem * h->classes, s, u8_input)) return rc;
   }
   CUDA_TRY(cudaMemcpyAsync(logits_host, h->stage_out, out_elem * h->classes * n, cudaMemcpyDeviceToHost, s));
   return check_stuck(h, cudaStreamSynchronize(s), "forward (host buffers)");
@@ -1399,6 +1422,28 @@ int ievm_forward_i8_host(ievm_handle* h, const float* x_host, int n, float* logi
 }
 int ievm_forward_f16_host(ievm_handle* h, const void* x_host, int n, void* logits_host) {
   return forward_host_common(h, IEVM_DTYPE_F16, x_host, n, logits_host);
+}
+
+int ievm_set_input_lut(ievm_handle* h, const uint8_t* lut768) {
+  if (!h || !lut768) return fail(IEVM_ERR_BAD_ARG, "null argument");
+  if (h->dtype != IEVM_DTYPE_I8) return fail(IEVM_ERR_BAD_ARG, "the 8-bit image input path belongs to the INT8 engine");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->lut_dev) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, 768));
+    h->owned.push_back(p);
+    h->lut_dev = static_cast<uint8_t*>(p);
+  }
+  CUDA_TRY(cudaMemcpy(h->lut_dev, lut768, 768, cudaMemcpyHostToDevice));
+  return IEVM_OK;
+}
+
+int ievm_forward_u8(ievm_handle* h, const uint8_t* x_nhwc, int n, float* logits, void* stream) {
+  return forward_common(h, IEVM_DTYPE_I8, x_nhwc, n, logits, stream, true);
+}
+
+int ievm_forward_u8_host(ievm_handle* h, const uint8_t* x_nhwc_host, int n, float* logits_host) {
+  return forward_host_common(h, IEVM_DTYPE_I8, x_nhwc_host, n, logits_host, true);
 }
 
 int ievm_set_option(ievm_handle* h, const char* name, int value) {
@@ -1584,6 +1629,21 @@ int ievm_probe_patch(const void* in_dev, int n, int h, int w, int c_pitch, int r
   const unsigned code = *stuck_host;
   cudaFreeHost(stuck_host);
   if (e != cudaSuccess) return fail(IEVM_ERR_CUDA, "probe_patch: %s (stuck code 0x%x)", cudaGetErrorString(e), code);
+  return IEVM_OK;
+}
+
+int ievm_count_correct(const void* logits, int dtype, const int64_t* labels, int n, int classes, uint64_t* counters2,
+                       void* stream) {
+  if (!logits || !labels || !counters2 || n <= 0 || classes <= 0) return fail(IEVM_ERR_BAD_ARG, "ievm_count_correct: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
+  if (dtype == IEVM_DTYPE_F16)
+    count_correct_kernel<__half><<<blocks, 128, 0, st>>>(static_cast<const __half*>(logits), reinterpret_cast<const long long*>(labels),
+                                                         n, classes, reinterpret_cast<unsigned long long*>(counters2));
+  else
+    count_correct_kernel<float><<<blocks, 128, 0, st>>>(static_cast<const float*>(logits), reinterpret_cast<const long long*>(labels),
+                                                        n, classes, reinterpret_cast<unsigned long long*>(counters2));
+  CUDA_TRY(cudaGetLastError());
   return IEVM_OK;
 }
 

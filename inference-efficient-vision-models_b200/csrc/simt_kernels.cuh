@@ -508,4 +508,31 @@ __global__ void kd_finalize_kernel(float* out3, float inv_n) {
   if (threadIdx.x < 2) out3[threadIdx.x] *= inv_n;     // CE and KL are batch means; [2] stays a count
 }
 
+// --------------------------------------------------------------------------------------------
+// evaluate_accuracy (quantization/engines.py:59-63) without a host round trip per batch:
+// counters[0] += #(argmax(logits) == label), counters[1] += n.  torch.max returns the lowest index on ties.
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void count_correct_kernel(const T* __restrict__ logits, const long long* __restrict__ labels, int n, int classes,
+                                     unsigned long long* counters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int hit = 0;
+  if (i < n) {
+    const T* r = logits + static_cast<long long>(i) * classes;
+    float best = static_cast<float>(r[0]);
+    int arg = 0;
+    for (int c = 1; c < classes; ++c) {
+      const float v = static_cast<float>(r[c]);
+      if (v > best) {
+        best = v;
+        arg = c;
+      }
+    }
+    hit = arg == static_cast<int>(labels[i]) ? 1u : 0u;
+  }
+  const unsigned int warp_hits = __popc(__ballot_sync(0xffffffffu, hit != 0));
+  if ((threadIdx.x & 31) == 0 && warp_hits) atomicAdd(counters, static_cast<unsigned long long>(warp_hits));
+  if (i == 0) atomicAdd(counters + 1, static_cast<unsigned long long>(n));
+}
+
 }  // namespace ievm

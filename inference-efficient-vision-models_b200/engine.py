@@ -51,6 +51,22 @@ def _marshal(net: NetSpec):
     return nd, keep
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # quantization/dataset.py:17-18
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def input_lut(in_scale: float, in_zp: int, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> np.ndarray:
+    """[3, 256] uint8: lut[c, v] = quantize_per_tensor(Normalize(ToTensor(v)))[c], computed with the very torch /
+    torchvision ops the reference's transform and converted graph run, one 8-bit level at a time -- the fused
+    kernel is therefore bit-identical to the unfused f32 pipeline by construction."""
+    from torchvision.transforms import functional as TF
+    levels = torch.arange(256, dtype=torch.uint8).view(1, 256, 1).expand(1, 256, 3).contiguous()   # H=1, W=256, C=3
+    x = TF.to_tensor(levels.numpy())                         # [3, 1, 256] float32 in [0, 1]: v / 255
+    x = TF.normalize(x, list(mean), list(std))
+    q = torch.quantize_per_tensor(x, float(in_scale), int(in_zp), torch.quint8).int_repr()
+    return np.ascontiguousarray(q.view(3, 256).numpy())
+
+
 class _B200Engine(nn.Module):
     _torch_dtype = torch.float32
 
@@ -211,6 +227,35 @@ class B200QuantizedResNet(_B200Engine):
     @classmethod
     def from_converted(cls, gm, **kw) -> "B200QuantizedResNet":
         return cls(from_converted(gm), source=gm, **kw)
+
+    # ---- the input pipeline in front of the hot path -------------------------
+    def set_input_transform(self, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> np.ndarray:
+        """Fuse ``T.ToTensor() -> T.Normalize(mean, std)`` (quantization/dataset.py:16-18) and the graph's
+        ``quantize_per_tensor`` into the front-end kernel.  Returns the [3, 256] lookup table it uploaded."""
+        lut = input_lut(self.net.in_scale, self.net.in_zp, mean, std)
+        _lib.check(self._lib.ievm_set_input_lut(self._handle, lut.ctypes.data), "ievm_set_input_lut")
+        self._lut = lut
+        return lut
+
+    def forward_u8(self, images: torch.Tensor) -> torch.Tensor:
+        """Decoded 8-bit images ``[N, 224, 224, 3]`` (HWC, RGB, uint8; CPU or CUDA) -> f32 logits, bit-identical to
+        ``forward(Normalize(ToTensor(images)))``.  A quarter of the input bytes over PCIe and HBM."""
+        if getattr(self, "_lut", None) is None:
+            self.set_input_transform()
+        if images.dtype != torch.uint8 or images.dim() != 4 or tuple(images.shape[1:]) != (self.net.in_h, self.net.in_w, 3):
+            raise ValueError(f"expected uint8 [N,{self.net.in_h},{self.net.in_w},3], got {images.dtype} {tuple(images.shape)}")
+        n = images.shape[0]
+        if n > self.max_batch:
+            return torch.cat([self.forward_u8(images[i:i + self.max_batch]) for i in range(0, n, self.max_batch)])
+        x = images.contiguous()
+        if not x.is_cuda:
+            out = torch.empty((n, self.net.num_classes), dtype=torch.float32)
+            _lib.check(self._lib.ievm_forward_u8_host(self._handle, x.data_ptr(), n, out.data_ptr()), "ievm_forward_u8_host")
+            return out
+        out = torch.empty((n, self.net.num_classes), dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self._lib.ievm_forward_u8(self._handle, x.data_ptr(), n, out.data_ptr(), stream), "ievm_forward_u8")
+        return out
 
     @classmethod
     def from_quantized_state_dict(cls, sd, **kw) -> "B200QuantizedResNet":

@@ -159,6 +159,65 @@ def test_int8_fused_front_end_accumulators_and_pooled_tensor(n, tpu, monkeypatch
     eng.close()
 
 
+@pytest.mark.parametrize("n", [1, 6])
+def test_int8_u8_image_input_is_bit_identical_to_the_f32_pipeline(n):
+    """decoded u8 HWC images through the fused ToTensor+Normalize+quantize front end == the
+    reference's transform (quantization/dataset.py:14-19) followed by the converted module on the CPU."""
+    from PIL import Image
+    from torchvision import transforms as T
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    torch.backends.quantized.engine = "fbgemm"
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=8)
+    rng = np.random.default_rng(50 + n)
+    imgs = rng.integers(0, 256, (n, 224, 224, 3), dtype=np.uint8)
+    imgs[0, :3] = 255
+    imgs[-1, -2:, -5:] = 0
+    tf = T.Compose([T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    x = torch.stack([tf(Image.fromarray(im)) for im in imgs])
+    with torch.no_grad():
+        ref = gm(x)
+    u8 = torch.from_numpy(imgs)
+    assert torch.equal(eng.forward_u8(u8.cuda()).cpu(), ref)          # device buffers
+    assert torch.equal(eng.forward_u8(u8), ref)                       # host buffers (H2D of a quarter of the bytes)
+    assert torch.equal(eng(x.cuda()).cpu(), ref)
+    eng.close()
+
+
+def test_engines_from_on_disk_artifacts_and_eval_drop_ins(tmp_path):
+    """engines built from the files the reference writes; evaluate_accuracy / measure_latency
+    drop-ins agree with the reference's own helpers run on the CPU module."""
+    import ievm_b200
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    torch.save(gm.state_dict(), tmp_path / "model_static_int8.pth")                   # quantization/main.py:306-308
+    student = mf.make_student(mf.PRUNED_WIDTHS)
+    torch.save(student, tmp_path / "pruned_model.pth")                                # pruning/main.py:164-165
+    torch.save(mf.cast_fp16(student).state_dict(), tmp_path / "model_fp16.pth")
+    e8 = ievm_b200.load_engine(str(tmp_path / "model_static_int8.pth"), max_batch=16)
+    e16a = ievm_b200.load_engine(str(tmp_path / "pruned_model.pth"), max_batch=16)
+    e16b = ievm_b200.load_engine(str(tmp_path / "model_fp16.pth"), max_batch=16)
+    assert isinstance(e8, ievm_b200.B200QuantizedResNet) and isinstance(e16a, ievm_b200.B200HalfResNet)
+    x = mf.synthetic_images(16, seed=3)
+    torch.backends.quantized.engine = "fbgemm"
+    with torch.no_grad():
+        ref = gm(x)
+    assert torch.equal(e8(x.cuda()).cpu(), ref)
+    assert torch.equal(e16a(x.half().cuda()), e16b(x.half().cuda()))
+    # evaluate_accuracy: same number as the reference's loop (engines.py:37-65) on the CPU module
+    labels = torch.randint(0, 6, (48,), generator=torch.Generator().manual_seed(4))
+    xs = mf.synthetic_images(48, seed=8)
+    loader = [(xs[i:i + 16], labels[i:i + 16]) for i in range(0, 48, 16)]
+    with torch.no_grad():
+        pred = torch.cat([torch.max(gm(b), 1)[1] for b, _ in loader])
+    ref_acc = 100 * int((pred == labels).sum()) / 48
+    assert ievm_b200.evaluate_accuracy(e8, loader) == pytest.approx(ref_acc)
+    acc16 = ievm_b200.evaluate_accuracy(e16a, loader)
+    assert 0.0 <= acc16 <= 100.0
+    ms = ievm_b200.measure_latency(e8, xs[:1], num_runs=20)
+    assert 0.0 < ms < 50.0
+    for e in (e8, e16a, e16b):
+        e.close()
+
+
 @pytest.mark.parametrize("n", [1, 2, 5, 13])
 def test_int8_ragged_batches(n):
     gm = cached_quantized(mf.PRUNED_WIDTHS)

@@ -81,6 +81,40 @@ def test_flatten_half_modules():
     assert torch.allclose(ref, got, atol=5e-3)
 
 
+def test_input_lut_equals_the_reference_transform_pipeline():
+    """lut[c][v] must equal quantize_per_tensor(Normalize(ToTensor(v))) from the reference's own
+    transform (quantization/dataset.py:14-19) for every level, so the fused u8 path is exact by construction."""
+    from PIL import Image
+    from torchvision import transforms as T
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    scale, zp = float(gm.conv1_input_scale_0), int(gm.conv1_input_zero_point_0)
+    lut = ievm_b200.input_lut(scale, zp)
+    assert lut.shape == (3, 256) and lut.dtype == np.uint8
+    img = np.random.default_rng(0).integers(0, 256, (224, 224, 3), dtype=np.uint8)
+    img[0, :256 % 224] = 0
+    img[1, :, :] = np.arange(224, dtype=np.uint8)[:, None]
+    t = T.Compose([T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])(Image.fromarray(img))
+    q = torch.quantize_per_tensor(t, scale, zp, torch.quint8).int_repr().numpy()
+    assert np.array_equal(q, np.stack([lut[c][img[..., c]] for c in range(3)]))
+
+
+def test_on_disk_formats_are_recognised(tmp_path):
+    """widths and block kind recovered from tensor shapes; the rebuilt module reproduces the saved one."""
+    from ievm_b200 import pipeline
+    m = mf.make_student((24, 40, 56, 72))
+    sd = {k: v.half() if v.is_floating_point() else v for k, v in m.state_dict().items()}      # model_fp16.pth layout
+    assert pipeline._widths_from_float_state_dict(sd) == ("basic", [24, 40, 56, 72], 6)
+    rebuilt = pipeline._module_from_float_state_dict(sd)
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        assert torch.allclose(rebuilt(x), m.half().float()(x), atol=1e-5)
+    assert pipeline._widths_from_float_state_dict(mf.make_teacher().state_dict())[0] == "bottleneck"
+    with pytest.raises(ValueError):
+        pipeline.load_engine({"foo": torch.zeros(1)})
+    with pytest.raises(TypeError):
+        pipeline.load_engine(3.14)
+
+
 def test_unsupported_graphs_fail_loudly():
     net = ievm_b200.from_converted(cached_quantized(mf.PRUNED_WIDTHS))
     import copy
