@@ -49,8 +49,7 @@ constexpr int kF2Rec = 116;                      // records per line (column pai
 constexpr int kF2LinePitch = kF2Rec * 16;        // 1856 B
 constexpr int kF2RawSlots = 6;
 constexpr int kF2ChunkSlots = 8;                 // chunk slots in the line ring
-constexpr int kF2TmemSlots = 4;
-constexpr int kF2TmemSlotCols = 128;
+constexpr int kF2TmemSlotCols = 128;              // accumulator slots; the weight operand sits behind them in TMEM
 constexpr int kF2EpiWarps = 8;
 constexpr int kF2QuantWarps = 4;
 constexpr int kF2QuantThreads = 32 * kF2QuantWarps;
@@ -69,7 +68,11 @@ struct F2Cfg {
   static constexpr int kLpc = kDtype == kDtypeI8 ? 2 : 4;             // lines per chunk (a chunk = 4 input rows)
   static constexpr int kSegs = 2 * kLpc + 1;                          // lines one tile reads
   static constexpr int kRowOff = kDtype == kDtypeI8 ? 4 : 3;          // chunk ci = input rows 4ci - kRowOff ..
-  static constexpr int kABytes = kSegs * 64 * 128;                    // weight operand: 128 rows x kSegs x 64 B
+  static constexpr int kARowBytes = kSegs * 64;                       // weight operand: 128 rows x kSegs x 64 B, kept
+  static constexpr int kABytes = kARowBytes * 128;                    //   in TENSOR MEMORY (lane = row, 4 bytes per column)
+  static constexpr int kACols = kARowBytes / 4;                       // 80 / 144 columns
+  static constexpr int kSlots = (512 - kACols) / kF2TmemSlotCols;     // accumulator ring: 3 (INT8) / 2 (FP16) slots
+  static constexpr int kACol0 = kSlots * kF2TmemSlotCols;
   static constexpr int kInElem = kDtype == kDtypeI8 ? 4 : 2;          // f32 / f16 input
   // raw rows start kBoxX0 columns left of the image so that the box begins on a 16-byte boundary of the row
   // (TMA faults on an 8-byte-aligned box start); they cover the 232 columns -4 .. 227 the records need
@@ -82,7 +85,7 @@ struct F2Cfg {
   static constexpr int kRawStride = (kRawTx + 127) / 128 * 128;
   static constexpr int kLines = kF2ChunkSlots * kLpc;                 // power of two
   static constexpr int kRecsPerChunk = kLpc * kF2Rec;
-  static constexpr size_t kSmemBytes = 1024 + kABytes + static_cast<size_t>(kLines) * kF2LinePitch +
+  static constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(kLines) * kF2LinePitch +
                                        static_cast<size_t>(kF2RawSlots) * kRawStride +
                                        2 * 2 * kF2XRows * 64 * 16 + 64 * 8 + 32 + (kIn == 1 ? 768 : 0);
 };
@@ -94,7 +97,7 @@ struct Frontend2Params {
   int in_zp;
   float inv_scale;
   uint32_t idesc;
-  const uint8_t* wpack;      // weight operand image (F2Cfg::kABytes), see pack_front2_weights
+  const uint8_t* wpack;      // weight operand, row-major [128][kARowBytes] (upload_front2_weights)
   void* out;                 // [n][ph][56][64] u8 / f16
   const float* bdiv;         // i8: bias / (x_s * w_s[c]);  f16: folded bias
   const float* mult;         // i8: (x_s * w_s[c]) / out_s
@@ -136,6 +139,48 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "memory");
 }
 
+// 32 lanes x 16 consecutive 32-bit columns, registers -> TMEM: thread t of the warp writes lane (lane_base + t).
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]: the M-side operand is read from tensor memory (lane = row, K packed four bytes
+// per column), so only B crosses the shared-memory read port.  Measured on B200: tcgen05.mma fetches shared-memory
+// operands at ~64 B/clk/SM, which -- not the tensor pipe -- bounds M128 x N<=128 shapes in the SS form.
+template <int kDtype>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if (kDtype == kDtypeI8) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
 // Accumulator words are int32 (INT8) or float bit patterns (FP16); "lowest" is the pool's padding value.
 template <int kDtype>
 __device__ __forceinline__ uint32_t f2_lowest() {
@@ -154,7 +199,7 @@ __device__ __forceinline__ uint32_t f2_max3(uint32_t a, uint32_t b, uint32_t c) 
 }
 
 // Epilogue of one warpgroup (kWg = 0: pooled columns 0..27, kWg = 1: 28..55).
-template <int kDtype, int kWg>
+template <int kDtype, int kWg, int kSlots>
 __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t tmem_base, uint64_t* tmem_full,
                                             uint64_t* tmem_empty, uint4* s_x, int units) {
   constexpr int kOff = kWg == 0 ? -1 : 7;        // register index of a pooled column's first stem column: 2k + kOff
@@ -174,13 +219,19 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
   uint32_t prev[kF2PxPerWg];                     // upper threads: horizontal maxima of the previous tile's row
 #pragma unroll
   for (int k = 0; k < kF2PxPerWg; ++k) prev[k] = kLow;
-  int t = 0;
+  int t = 0, ts_next = 0;
+  uint32_t ph_next = 0;
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const F2Unit un = f2_unit(p, u);
     for (int i = 0; i <= un.nt; ++i, ++t) {
       const int T = un.t0 - 1 + i;               // pooled row of this tile (the warm-up tile i == 0 only feeds `prev`)
-      const int ts = t & (kF2TmemSlots - 1);
-      wait_or_die(&tmem_full[ts], (t >> 2) & 1u, 0x840u | ts, p.stuck_flag);
+      const int ts = ts_next;
+      const uint32_t ph = ph_next;
+      if (++ts_next == kSlots) {
+        ts_next = 0;
+        ph_next ^= 1u;
+      }
+      wait_or_die(&tmem_full[ts], ph, 0x840u | ts, p.stuck_flag);
       tc_fence_after();
       const uint32_t taddr = lane_addr + static_cast<uint32_t>(ts * kF2TmemSlotCols);
       const bool real = i > 0;
@@ -281,8 +332,7 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sW = smem;
-  uint8_t* sLines = sW + Cfg::kABytes;
+  uint8_t* sLines = smem;
   uint8_t* sRaw = sLines + Cfg::kLines * kF2LinePitch;
   uint4* sX = reinterpret_cast<uint4*>(sRaw + kF2RawSlots * Cfg::kRawStride);
   uint64_t* raw_full = reinterpret_cast<uint64_t*>(sX + 2 * 2 * kF2XRows * 64);
@@ -290,23 +340,16 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
   uint64_t* line_full = raw_empty + kF2RawSlots;
   uint64_t* line_empty = line_full + kF2ChunkSlots;
   uint64_t* tmem_full = line_empty + kF2ChunkSlots;
-  uint64_t* tmem_empty = tmem_full + kF2TmemSlots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kF2TmemSlots);
+  uint64_t* tmem_empty = tmem_full + Cfg::kSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + Cfg::kSlots);
   uint8_t* sLut = reinterpret_cast<uint8_t*>(tmem_slot + 4);      // u8 input mode: [3][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // weight operand image: plain copy (it is already in the UMMA core-matrix order)
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.wpack);
-    uint4* dst = reinterpret_cast<uint4*>(sW);
-    for (int i = threadIdx.x; i < Cfg::kABytes / 16; i += kF2Threads) dst[i] = __ldg(src + i);
-    fence_proxy_async_smem();
-    if (kIn == 1)
-      for (int i = threadIdx.x; i < 768 / 4; i += kF2Threads)
-        reinterpret_cast<uint32_t*>(sLut)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.lut) + i);
-  }
+  if (kIn == 1)
+    for (int i = threadIdx.x; i < 768 / 4; i += kF2Threads)
+      reinterpret_cast<uint32_t*>(sLut)[i] = __ldg(reinterpret_cast<const uint32_t*>(p.lut) + i);
   if (warp == kF2TmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     for (int i = 0; i < kF2RawSlots; ++i) {
@@ -317,7 +360,7 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
       mbar_init(&line_full[i], kF2QuantThreads);
       mbar_init(&line_empty[i], 1);
     }
-    for (int i = 0; i < kF2TmemSlots; ++i) {
+    for (int i = 0; i < Cfg::kSlots; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2);              // one arrival per epilogue warpgroup
     }
@@ -333,24 +376,47 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   griddep_launch_dependents();
 
+  // weight operand -> tensor memory, once per CTA: thread (quadrant q, lane l) of warps 0..3 owns row 32 q + l
+  if (warp < 4) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wpack + static_cast<size_t>(warp * 32 + lane) * Cfg::kARowBytes);
+    const uint32_t a_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + Cfg::kACol0;
+#pragma unroll 1
+    for (int c = 0; c < Cfg::kACols / 16; ++c) {
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 q = __ldg(src + 4 * c + j);
+        w[4 * j] = q.x;
+        w[4 * j + 1] = q.y;
+        w[4 * j + 2] = q.z;
+        w[4 * j + 3] = q.w;
+      }
+      tmem_st_32x32b_x16(a_addr + static_cast<uint32_t>(16 * c), w);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
   const int units = p.n * p.upi;
 
   if (warp < kF2EpiWarps) {
-    if (warp < 4) f2_epilogue<kDtype, 0>(p, tmem_base, tmem_full, tmem_empty, sX, units);
-    else f2_epilogue<kDtype, 1>(p, tmem_base, tmem_full, tmem_empty, sX, units);
+    if (warp < 4) f2_epilogue<kDtype, 0, Cfg::kSlots>(p, tmem_base, tmem_full, tmem_empty, sX, units);
+    else f2_epilogue<kDtype, 1, Cfg::kSlots>(p, tmem_base, tmem_full, tmem_empty, sX, units);
   } else if (warp == kF2MmaWarp) {
     // ================================ MMA issuer ================================
     const uint32_t hi = (128u >> 4) | (1u << 14);                                  // SBO = 128 B, version 1, no swizzle
-    const uint32_t a_lo0 = ((smem_u32(sW) & 0x3FFFFu) >> 4) | ((2048u >> 4) << 16);     // LBO = 2048 B (next K chunk)
+    const uint32_t a_tmem0 = tmem_base + Cfg::kACol0;                                  // 8 columns (32 bytes of K) per k-step
     const uint32_t b_lo0 = ((smem_u32(sLines) & 0x3FFFFu) >> 4) | (1u << 16);          // LBO = 16 B (next record)
-    int q0 = 0, t = 0;
+    int q0 = 0, t = 0, ts = 0;
+    uint32_t ph = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const F2Unit un = f2_unit(p, u);
       for (int i = 0; i <= un.nt; ++i, ++t) {
         const int qn = q0 + i + 2;               // newest chunk this tile reads (chunks complete in order)
         wait_or_die(&line_full[qn % kF2ChunkSlots], (qn / kF2ChunkSlots) & 1u, 0x820u | (qn % kF2ChunkSlots), p.stuck_flag);
-        const int ts = t & (kF2TmemSlots - 1);
-        wait_or_die(&tmem_empty[ts], ((t >> 2) & 1u) ^ 1u, 0x830u | ts, p.stuck_flag);
+        wait_or_die(&tmem_empty[ts], ph ^ 1u, 0x830u | ts, p.stuck_flag);
         tc_fence_after();
         fence_proxy_async_smem();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * kF2TmemSlotCols);
@@ -360,11 +426,9 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
           for (int s = 0; s < Cfg::kSegs; ++s) {
             const uint32_t b_lo = b_lo0 + static_cast<uint32_t>((line0 + s) & (Cfg::kLines - 1)) * (kF2LinePitch >> 4);
 #pragma unroll
-            for (int jh = 0; jh < 2; ++jh) {
-              const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(2 * s + jh) * (4096u >> 4);
-              if (kDtype == kDtypeI8) umma_i8_lohi(d_tmem, a_lo, b_lo + 2u * jh, hi, p.idesc, (s | jh) != 0 ? 1u : 0u);
-              else umma_f16_lohi(d_tmem, a_lo, b_lo + 2u * jh, hi, p.idesc, (s | jh) != 0 ? 1u : 0u);
-            }
+            for (int jh = 0; jh < 2; ++jh)
+              umma_ts<kDtype>(d_tmem, a_tmem0 + static_cast<uint32_t>(2 * s + jh) * 8u, b_lo + 2u * jh, hi, p.idesc,
+                              (s | jh) != 0 ? 1u : 0u);
           }
           umma_commit(&tmem_full[ts]);
           umma_commit(&line_empty[(q0 + i) % kF2ChunkSlots]);      // tile i is the last reader of chunk i
@@ -374,6 +438,10 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
           }
         }
         __syncwarp();
+        if (++ts == Cfg::kSlots) {
+          ts = 0;
+          ph ^= 1u;
+        }
       }
       q0 += un.nt + 3;
     }

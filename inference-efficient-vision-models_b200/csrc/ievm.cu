@@ -511,8 +511,8 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
 }
 
 // Weight operand of frontend_v2.cuh: A[m][k], m = 64 * r + cout (r = which of the tile's two stem rows),
-// K bytes = line s (0 .. kSegs-1) x 64: record j (0..3) x 16 bytes.  Stored as UMMA no-swizzle K-major core
-// matrices: byte (m, kb) at ((kb / 16) * 16 + m / 8) * 128 + (m % 8) * 16 + kb % 16  (SBO = 128, LBO = 2048).
+// K bytes = line s (0 .. kSegs-1) x 64: record j (0..3) x 16 bytes; stored row-major [128][kSegs * 64] (the kernel
+// copies it into tensor memory, one row per lane).
 //   INT8: record byte = rp * 6 + cp * 3 + c, line s = input row pair: ky = 2 * (s - r) + rp - 1, kx = 2 * j + cp - 1
 //   FP16: record half = cp * 3 + c,          line s = input row:      ky = s - 2 * r,             kx = 2 * j + cp - 1
 int upload_front2_weights(ievm_handle* h, LayerPlan& L) {
@@ -521,7 +521,8 @@ int upload_front2_weights(ievm_handle* h, LayerPlan& L) {
   const int segs = i8 ? F2Cfg<kDtypeI8>::kSegs : F2Cfg<kDtypeF16>::kSegs;
   const int abytes = i8 ? F2Cfg<kDtypeI8>::kABytes : F2Cfg<kDtypeF16>::kABytes;
   std::vector<uint8_t> img(abytes, 0);
-  auto at = [&](int m, int kb) -> uint8_t* { return &img[(static_cast<size_t>(kb / 16) * 16 + m / 8) * 128 + (m % 8) * 16 + kb % 16]; };
+  const int row_bytes = abytes / 128;
+  auto at = [&](int m, int kb) -> uint8_t* { return &img[static_cast<size_t>(m) * row_bytes + kb]; };
   for (int r = 0; r < 2; ++r)
     for (int co = 0; co < d.cout; ++co)
       for (int s = 0; s < segs; ++s)
