@@ -23,6 +23,7 @@
 #include "stem_tc.cuh"
 #include "frontend_fused.cuh"
 #include "frontend_v2.cuh"
+#include "conv_wt.cuh"
 
 namespace {
 
@@ -134,6 +135,10 @@ struct LayerPlan {
   int stages = 0, tmem_cols = 0, resident_b = 0;
   int mode = 0;                 // kModeIm2col | kModeHalo
   int fast_round = 0;           // see ConvTcParams::fast_round
+  // weights-stationary kernel (conv_wt.cuh) for narrow 3x3 stride-1 INT8 layers
+  int wt = 0, wt_stages = 0, wt_stage_bytes = 0, wt_tx_bytes = 0;
+  void* w_wt = nullptr;         // [128][768] weight operand (two output rows stacked in M)
+  CUtensorMap tmap_wt;
   int cluster = 1;              // CTAs per cluster sharing the weight tile by TMA multicast
   int max_clusters = 0;         // co-resident clusters the device can hold (cluster > 1)
   int wp = 0, patch_rows = 0, tiles_per_img = 0, a_stage_bytes = 0, a_tx_bytes = 0;
@@ -163,6 +168,8 @@ struct ievm_handle {
   int opt_halo = 1;        // IEVM_HALO=0 disables the halo-patch mode (all convs use per-tap im2col TMA)
   int opt_halo_rb128 = 0;
   int opt_fused_front = 1; // IEVM_FUSED_FRONT=0: separate quantize / stem / maxpool kernels
+  int opt_wt = 0;          // IEVM_WT=1: narrow 3x3 layers use the weights-stationary kernel of conv_wt.cuh (experiment:
+                           // correct, but slower than conv_tc.cuh -- see the header of conv_wt.cuh)
   int opt_front_v2 = 1;    // IEVM_FRONT_V2=0: first-generation fused front end (INT8) / separate kernels (FP16)
   int front2_ok = 0;       // the network's front end fits frontend_v2.cuh (224-wide input, <= 64 stem channels)
   int front_tpu = 0;       // IEVM_FRONT_TPU: pooled rows per work unit (0 = heuristic)
@@ -299,6 +306,15 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
       const TensorInfo& tr = h->tensors[d.res_tensor];
       if (tr.h != L.ho || tr.w != L.wo || tr.c != d.cout || tr.pitch != L.cout_pad)
         return fail(IEVM_ERR_BAD_ARG, "layer %d: residual shape mismatch", i);
+    }
+    if (h->opt_wt && h->dtype == IEVM_DTYPE_I8 && d.ksize == 3 && d.stride == 1 && d.pad == 1 && L.cin_pitch == 64 &&
+        L.cout_pad == 64 && L.h % 2 == 0 && L.w + 2 <= 64 && L.w >= 4) {
+      const int wp = L.w + 2;
+      L.wt = 1;
+      L.wt_tx_bytes = 4 * wp * 64;
+      L.wt_stage_bytes = round_up((3 * wp + 2 + 64) * 64, 1024);     // the last taps' views run past the patch (junk columns)
+      L.wt_stages = std::min(kWtMaxStages, (h->smem_optin - 2048) / L.wt_stage_bytes);
+      if (L.wt_stages < 2) L.wt = 0;
     }
     const int row_bytes = L.cin_pitch * h->elem;
     constexpr int kMaxStages = 16;
@@ -495,6 +511,20 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
     int8_t* dw = nullptr;
     if (int rc = dev_upload(h, wp, &dw)) return rc;
     L.w_packed = dw;
+    if (L.wt) {
+      // lane m = 64 * r + co (r = parity of the output row), K = (dy * 3 + kx) * 64 + ci, filter row ky = dy - r
+      std::vector<int8_t> wt(static_cast<size_t>(128) * kWtKSteps * 32, 0);
+      for (int r = 0; r < 2; ++r)
+        for (int co = 0; co < d.cout; ++co)
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
+              for (int ci = 0; ci < d.cin; ++ci)
+                wt[static_cast<size_t>(64 * r + co) * (kWtKSteps * 32) + ((ky + r) * 3 + kx) * 64 + ci] =
+                    w[(static_cast<size_t>(co) * d.cin + ci) * 9 + ky * 3 + kx];
+      int8_t* dwt = nullptr;
+      if (int rc = dev_upload(h, wt, &dwt)) return rc;
+      L.w_wt = dwt;
+    }
   } else {
     const uint16_t* w = static_cast<const uint16_t*>(d.weight);
     std::vector<uint16_t> wp(static_cast<size_t>(L.cout_pad) * k_total, 0);
@@ -670,6 +700,16 @@ int encode_maps(ievm_handle* h) {
     if (L.d.op != IEVM_OP_CONV || L.is_stem) continue;
     const CUtensorMapSwizzle sw = L.kc_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const size_t e = h->elem;
+    if (L.wt) {      // conv_wt.cuh: the 4 x (W+2) x 64 B input patch of a row pair
+      cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(L.w), static_cast<cuuint64_t>(L.h), static_cast<cuuint64_t>(h->max_batch)};
+      cuuint64_t strides[3] = {64, static_cast<cuuint64_t>(L.w) * 64, static_cast<cuuint64_t>(L.h) * L.w * 64};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(L.w + 2), 4, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      const CUresult r = g_encode_tiled(&L.tmap_wt, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, tensor_ptr(h, L.d.in_tensor), dims, strides,
+                                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled (row-pair patch) failed for layer %zu: CUresult %d", i, (int)r);
+    }
     if (L.mode == kModeHalo) {
       cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cin_pitch), static_cast<cuuint64_t>(L.w),
                             static_cast<cuuint64_t>(L.h), static_cast<cuuint64_t>(h->max_batch)};
@@ -799,6 +839,33 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
     return IEVM_OK;
   }
   const bool has_res = p.res != nullptr;
+  if (L.wt && dump_acc == nullptr) {
+    ConvWtParams q;
+    memset(&q, 0, sizeof(q));
+    q.n = n; q.h = L.h; q.w = L.w; q.wp = L.w + 2;
+    q.tiles_per_img = L.h / 2;
+    q.tiles = n * q.tiles_per_img;
+    q.tpi_magic = (q.tiles_per_img > 1 && static_cast<long long>(q.tiles) * q.tiles_per_img < 0x100000000ll)
+                      ? static_cast<uint32_t>((0x100000000ull + q.tiles_per_img - 1) / q.tiles_per_img) : 0u;
+    q.stages = L.wt_stages; q.stage_bytes = L.wt_stage_bytes; q.tx_bytes = L.wt_tx_bytes;
+    q.cols_per_warp = (L.w + 3) / 4;
+    q.idesc = make_idesc_i8_s8u8(64, 128);
+    q.wpack = static_cast<const uint8_t*>(L.w_wt);
+    q.out = static_cast<uint8_t*>(p.out);
+    q.res = static_cast<const uint8_t*>(p.res);
+    q.ep0 = L.ep0; q.ep1 = L.ep1;
+    q.out_zp = p.out_zp; q.out_lo = p.out_lo;
+    q.a_scale = p.a_scale; q.res_scale = p.res_scale; q.inv_add_scale = p.inv_add_scale;
+    q.res_zp = p.res_zp; q.add_zp = p.add_zp;
+    q.fast_round = L.fast_round;
+    q.stuck_flag = h->stuck_dev;
+    const unsigned wgrid = static_cast<unsigned>(std::min(q.tiles, h->num_sms));
+    const size_t wsmem = 1024 + static_cast<size_t>(q.stages) * q.stage_bytes + (2 * kWtMaxStages + 2 * kWtAcc) * 8 + 16;
+    if (has_res) CUDA_TRY(launch_kernel(conv_wt_kernel<true>, wgrid, kWtThreads, wsmem, s, h->opt_pdl != 0, L.tmap_wt, q));
+    else CUDA_TRY(launch_kernel(conv_wt_kernel<false>, wgrid, kWtThreads, wsmem, s, h->opt_pdl != 0, L.tmap_wt, q));
+    CUDA_TRY(cudaGetLastError());
+    return IEVM_OK;
+  }
   const unsigned cl = static_cast<unsigned>(L.cluster);
   int grid = std::min(p.m_tiles * p.n_tiles, h->num_sms);
   if (cl > 1) {
@@ -1244,6 +1311,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
   if (const char* e = getenv("IEVM_FRONT_CHUNK")) h->front_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FRONT_V2")) h->opt_front_v2 = atoi(e);
+  if (const char* e = getenv("IEVM_WT")) h->opt_wt = atoi(e);
   if (const char* e = getenv("IEVM_FRONT_TPU")) h->front_tpu = atoi(e);
   int rc = plan_shapes(h, nd);
   for (size_t i = 0; rc == IEVM_OK && i < h->layers.size(); ++i) {
@@ -1257,9 +1325,9 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
     for (size_t i = 0; i < h->layers.size(); ++i) {
       const LayerPlan& L = h->layers[i];
       if (L.d.op != IEVM_OP_CONV || L.is_stem) continue;
-      fprintf(stderr, "[ievm] layer %2zu %dx%d s%d %4d->%4d @%dx%d mode=%s kc=%d kchunks=%d bn=%d n_tiles=%d cluster=%d stages=%d residentB=%d fast_round=%d smem=%zu\n",
+      fprintf(stderr, "[ievm] layer %2zu %dx%d s%d %4d->%4d @%dx%d mode=%s kc=%d kchunks=%d bn=%d n_tiles=%d cluster=%d stages=%d residentB=%d fast_round=%d wt=%d smem=%zu\n",
               i, L.d.ksize, L.d.ksize, L.d.stride, L.d.cin, L.d.cout, L.ho, L.wo, L.mode == kModeHalo ? "halo" : "im2col",
-              L.kc_bytes, L.kchunks, L.bn, L.n_tiles, L.cluster, L.stages, L.resident_b, L.fast_round, L.smem_bytes);
+              L.kc_bytes, L.kchunks, L.bn, L.n_tiles, L.cluster, L.stages, L.resident_b, L.fast_round, L.wt, L.smem_bytes);
     }
   }
   if (rc == IEVM_OK) rc = assign_buffers(h);
@@ -1282,6 +1350,8 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
       IEVM_ATTR(kDtypeF16, false, kModeIm2col, 2); IEVM_ATTR(kDtypeF16, true, kModeIm2col, 2);
       IEVM_ATTR(kDtypeF16, false, kModeHalo, 1);   IEVM_ATTR(kDtypeF16, true, kModeHalo, 1);
 #undef IEVM_ATTR
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
       if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       // how many 2-CTA clusters of the heaviest configuration can be co-resident (GPC packing may strand SMs)
       for (LayerPlan& L : h->layers) {
