@@ -264,6 +264,7 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
     if (d.op == IEVM_OP_HEAD) {
       if (d.cin != tin.c) return fail(IEVM_ERR_BAD_ARG, "head: cin %d != producer channels %d", d.cin, tin.c);
       if (d.cout > kMaxClasses) return fail(IEVM_ERR_UNSUPPORTED, "head: more than %d classes", kMaxClasses);
+      if (tin.pitch > kHeadSumWords) return fail(IEVM_ERR_UNSUPPORTED, "head: more than %d input channels", kHeadSumWords);
       continue;
     }
     if (d.out_tensor <= 0 || d.out_tensor > max_id || h->tensors[d.out_tensor].h != 0)

@@ -219,37 +219,63 @@ struct HeadParams {
 constexpr int kHeadThreads = 128;
 constexpr int kMaxClasses = 16;
 
+constexpr int kHeadSumWords = 4096;          // shared partial channel sums: pixel phases x channel pitch
+
+// Phase 1 (both heads): per-channel sums over the image's pixels with 16-byte loads.  Thread (ph, g) walks pixels
+// ph, ph + PH, ... of 16-byte channel group g; the PH partial sums per channel are combined in a fixed order in
+// phase 2, so the result does not depend on scheduling (and the integer sums are exact anyway).
+__device__ __forceinline__ void head_phases(int groups, int& g_stride, int& ph_count) {
+  ph_count = groups >= kHeadThreads ? 1 : kHeadThreads / groups;
+  g_stride = groups >= kHeadThreads ? kHeadThreads : groups;
+}
+
 __global__ void __launch_bounds__(kHeadThreads)
 head_i8_kernel(const uint8_t* __restrict__ in, float* __restrict__ logits, uint8_t* __restrict__ pooled_dbg,
                const HeadParams p) {
+  __shared__ int s_sum[kHeadSumWords];
   __shared__ int s_part[kHeadThreads / 32][kMaxClasses];
   griddep_launch_dependents();
   griddep_wait();
   const int img = blockIdx.x;
   const uint8_t* base = in + static_cast<long long>(img) * p.hw * p.cpad;
+  const int groups = p.cpad >> 4;
+  int g_stride, ph_count;
+  head_phases(groups, g_stride, ph_count);
+  if (ph_count * p.cpad > kHeadSumWords) ph_count = kHeadSumWords / p.cpad;      // very wide heads: fewer phases
+  const int ph = threadIdx.x / g_stride, g0 = threadIdx.x - ph * g_stride;
+  if (ph < ph_count) {
+    for (int g = g0; g < groups; g += g_stride) {
+      int sum[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sum[j] = 0;
+      for (int px = ph; px < p.hw; px += ph_count) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + px * p.cpad + g * 16));
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          sum[4 * k] += wv[k] & 0xff;
+          sum[4 * k + 1] += (wv[k] >> 8) & 0xff;
+          sum[4 * k + 2] += (wv[k] >> 16) & 0xff;
+          sum[4 * k + 3] += wv[k] >> 24;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s_sum[ph * p.cpad + g * 16 + j] = sum[j];
+    }
+  }
+  __syncthreads();
   int acc[kMaxClasses];
 #pragma unroll
   for (int o = 0; o < kMaxClasses; ++o) acc[o] = 0;
   const float cnt = static_cast<float>(p.hw);
-  for (int c4 = threadIdx.x * 4; c4 < p.cpad; c4 += kHeadThreads * 4) {
-    int s[4] = {0, 0, 0, 0};
-    for (int px = 0; px < p.hw; ++px) {
-      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + px * p.cpad + c4));
-      s[0] += v & 0xff;
-      s[1] += (v >> 8) & 0xff;
-      s[2] += (v >> 16) & 0xff;
-      s[3] += v >> 24;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c4 + j;
-      if (c >= p.c) continue;
-      int q = __float2int_rn(__fdiv_rn(__int2float_rn(s[j]), cnt));
-      q = min(max(q, 0), 255);
-      if (pooled_dbg) pooled_dbg[static_cast<long long>(img) * p.c + c] = static_cast<uint8_t>(q);
-      const int xv = q - p.in_zp;
-      for (int o = 0; o < p.classes; ++o) acc[o] += xv * static_cast<int>(p.w[o * p.cpad + c]);
-    }
+  for (int c = threadIdx.x; c < p.c; c += kHeadThreads) {
+    int sc = 0;
+    for (int k = 0; k < ph_count; ++k) sc += s_sum[k * p.cpad + c];
+    int q = __float2int_rn(__fdiv_rn(__int2float_rn(sc), cnt));
+    q = min(max(q, 0), 255);
+    if (pooled_dbg) pooled_dbg[static_cast<long long>(img) * p.c + c] = static_cast<uint8_t>(q);
+    const int xv = q - p.in_zp;
+    for (int o = 0; o < p.classes; ++o) acc[o] += xv * static_cast<int>(p.w[o * p.cpad + c]);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int o = 0; o < p.classes; ++o) {
@@ -277,28 +303,46 @@ struct HeadF16Params {
 
 __global__ void __launch_bounds__(kHeadThreads)
 head_f16_kernel(const __half* __restrict__ in, __half* __restrict__ logits, const HeadF16Params p) {
+  __shared__ float s_sum[kHeadSumWords];
   __shared__ float s_part[kHeadThreads / 32][kMaxClasses];
   griddep_launch_dependents();
   griddep_wait();
   const int img = blockIdx.x;
   const __half* base = in + static_cast<long long>(img) * p.hw * p.cpad;
+  const int groups = p.cpad >> 3;                  // 8 halves = 16 bytes
+  int g_stride, ph_count;
+  head_phases(groups, g_stride, ph_count);
+  if (ph_count * p.cpad > kHeadSumWords) ph_count = kHeadSumWords / p.cpad;
+  const int ph = threadIdx.x / g_stride, g0 = threadIdx.x - ph * g_stride;
+  if (ph < ph_count) {
+    for (int g = g0; g < groups; g += g_stride) {
+      float sum[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum[j] = 0.f;
+      for (int px = ph; px < p.hw; px += ph_count) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + px * p.cpad + g * 8));
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wv[k]));
+          sum[2 * k] += f.x;
+          sum[2 * k + 1] += f.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_sum[ph * p.cpad + g * 8 + j] = sum[j];
+    }
+  }
+  __syncthreads();
   float acc[kMaxClasses];
 #pragma unroll
   for (int o = 0; o < kMaxClasses; ++o) acc[o] = 0.f;
   const float inv = 1.0f / static_cast<float>(p.hw);
-  for (int c2 = threadIdx.x * 2; c2 < p.cpad; c2 += kHeadThreads * 2) {
-    float s0 = 0.f, s1 = 0.f;
-    for (int px = 0; px < p.hw; ++px) {
-      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(base + px * p.cpad + c2));
-      s0 += v.x;
-      s1 += v.y;
-    }
-    const float m0 = __half2float(__float2half_rn(s0 * inv));
-    const float m1 = __half2float(__float2half_rn(s1 * inv));
-    for (int o = 0; o < p.classes; ++o) {
-      if (c2 < p.c) acc[o] += m0 * __half2float(p.w[o * p.cpad + c2]);
-      if (c2 + 1 < p.c) acc[o] += m1 * __half2float(p.w[o * p.cpad + c2 + 1]);
-    }
+  for (int c = threadIdx.x; c < p.c; c += kHeadThreads) {
+    float sc = 0.f;
+    for (int k = 0; k < ph_count; ++k) sc += s_sum[k * p.cpad + c];
+    const float m = __half2float(__float2half_rn(sc * inv));
+    for (int o = 0; o < p.classes; ++o) acc[o] += m * __half2float(p.w[o * p.cpad + c]);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int o = 0; o < p.classes; ++o) {
