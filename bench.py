@@ -265,8 +265,8 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
+    # stdout carries exactly one JSON line: whatever NCCL has to say (its version banner included) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
