@@ -16,6 +16,10 @@
  *                         hand them over (engines.py:52-60): H2D + forward + D2H in one call
  *   ievm_kd_loss       <- CE + T^2 * KLDiv(batchmean) soft-target loss
  *                         (knowledge_distillation/train.py:47-57; main.py:128-129)
+ *   ievm_set_input_lut,
+ *   ievm_forward_u8*   <- the dataset transform in front of the call, T.ToTensor() + T.Normalize(mean, std)
+ *                         (quantization/dataset.py:14-19), fused with the graph's quantize_per_tensor node
+ *   ievm_count_correct <- the accumulation of evaluate_accuracy (quantization/engines.py:59-63; main.py:288-290)
  *   ievm_debug_*       <- no reference counterpart: parity hooks (per-tensor activations and the
  *                         int32 accumulators torch never exposes)
  *

@@ -21,7 +21,9 @@
 // 3. M = 128 holds TWO stem rows: rows 0..63 of the weight operand compute stem row 2T, rows 64..127 hold the
 //    same filters shifted down by one row pair (two input rows) and compute stem row 2T+1 from the same
 //    B operand.  A tile = pooled row T = 5 (INT8) / 9 (FP16) lines x 2 k-steps = 10 / 18 MMAs of
-//    M128 x N112.  Pooled row T needs stem rows 2T-1, 2T, 2T+1: thread (lane 64+c) keeps the horizontal maxima of
+//    M128 x N112.  The weight operand is copied once per CTA into TENSOR MEMORY (TS-form MMA): tcgen05.mma fetches
+//    shared-memory operands at ~64 B/clk/SM, so keeping the 128-row operand out of shared memory is worth 12 %.
+//    Pooled row T needs stem rows 2T-1, 2T, 2T+1: thread (lane 64+c) keeps the horizontal maxima of
 //    row 2T-1 in registers from the previous tile, thread (lane c) has row 2T; the two exchange half of
 //    their maxima through shared memory and each finishes half of the pooled columns.
 //

@@ -153,3 +153,21 @@ def test_sharding_helpers_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_bench_work_model_matches_the_survey():
+    """bench.py's per-launch work table (the roofline's numerator) reproduces SURVEY 8(d): 1.4668 GMAC per image for
+    the pruned INT8 net, and the network roofline is the sum of per-launch max(compute, HBM) times."""
+    import bench
+    net = ievm_b200.from_converted(cached_quantized(mf.PRUNED_WIDTHS))
+    rows = bench.layer_table(net, 1)
+    names = [r[0] for r in rows]
+    assert names[0] == "quantize_input" and names[1] == "conv1" and names[-1] == "fc" and len(rows) == 23
+    assert sum(m for _, m, _ in rows) == 1466823640 + 2760          # 20 convs + the 460 x 6 fc
+    table = {n: (m, b) for n, m, b in rows}
+    pk = {"hbm_gbs": 6545.3, "bf16_tflops": 1677.3, "bf16_tflops_sustained": 1386.9, "source": "test"}
+    ms = bench.network_roofline_ms(table, pk, True)
+    expect = 1e3 * sum(max(2 * m / (2 * 1386.9e12), b / 6545.3e9) for m, b in table.values())
+    assert ms == pytest.approx(expect) and 0 < ms < 0.01          # a single image: microseconds
+    lo, hi = bench.shard_bounds(1024, 3, 8)
+    assert (lo, hi) == (384, 512)
