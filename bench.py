@@ -265,8 +265,12 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
-    # stdout carries exactly one JSON line: whatever NCCL has to say (its version banner included) goes to stderr
+    # stdout carries exactly one JSON line: whatever libraries print on file descriptor 1 (NCCL's version banner
+    # among them) is sent to stderr for the duration of the run; the line itself goes to the saved descriptor
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -425,6 +429,9 @@ def run_b200(args, rank, world, local_rank):
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     if line is not None:
         print(json.dumps(line), flush=True)
 
