@@ -115,6 +115,19 @@ int ievm_set_input_lut(ievm_handle* h, const uint8_t* lut768);
 int ievm_forward_u8(ievm_handle* h, const uint8_t* x_nhwc, int n, float* logits, void* stream);
 int ievm_forward_u8_host(ievm_handle* h, const uint8_t* x_nhwc_host, int n, float* logits_host);
 
+/* The remaining step of that transform, T.Resize((H, W)) on the decoded image (quantization/dataset.py:15), is
+ * Pillow's 8-bit bilinear ImagingResample; ievm_set_resize installs its per-output-pixel tables for source images of
+ * src_h x src_w -- bounds_*[o] = {first source index, taps}, kk_*[o][ksize_*] = 22-bit fixed-point coefficients,
+ * computed on the host exactly as Resample.c:precompute_coeffs does (ievm_b200.pipeline.pil_bilinear_coeffs) -- and
+ * ievm_forward_u8_resize runs resize (horizontal, then vertical, 8-bit intermediate: bit-identical to PIL) +
+ * ToTensor + Normalize + the quantized network on x_nhwc = [n][src_h][src_w][3] u8. */
+int ievm_set_resize(ievm_handle* h, int src_h, int src_w, const int32_t* bounds_w, const int32_t* kk_w, int ksize_w,
+                    const int32_t* bounds_h, const int32_t* kk_h, int ksize_h);
+int ievm_forward_u8_resize(ievm_handle* h, const uint8_t* x_nhwc, int n, float* logits, void* stream);
+int ievm_forward_u8_resize_host(ievm_handle* h, const uint8_t* x_nhwc_host, int n, float* logits_host);
+/* Parity hook: only the resize, result [n][H][W][3] u8 copied to the host. */
+int ievm_debug_resize(ievm_handle* h, const uint8_t* x_dev, int n, uint8_t* out_host, uint64_t out_bytes);
+
 /* Engine options: "conv_impl" 0 = tcgen05 tensor-core kernels (default), 1 = direct CUDA-core
  * cross-check kernels (tests only); "use_graph" 1 = replay forward() from a CUDA graph cached per
  * (n, x, logits) triple; "keep_tensors" 1 = one buffer per tensor (parity hooks); "profile" 1 =

@@ -26,7 +26,7 @@ EXPORTS = [
     "ievm_launches_per_forward", "ievm_debug_read_tensor", "ievm_debug_conv_acc", "ievm_kd_loss",
     "ievm_last_error", "ievm_build_info", "ievm_probe_im2col", "ievm_profile_read", "ievm_probe_patch",
     "ievm_debug_frontend", "ievm_set_input_lut", "ievm_forward_u8", "ievm_forward_u8_host",
-    "ievm_count_correct",
+    "ievm_count_correct", "ievm_set_resize", "ievm_forward_u8_resize", "ievm_forward_u8_resize_host", "ievm_debug_resize",
 ]
 
 
@@ -120,6 +120,14 @@ def load():
     lib.ievm_forward_u8.restype = C.c_int
     lib.ievm_forward_u8_host.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p]
     lib.ievm_forward_u8_host.restype = C.c_int
+    lib.ievm_set_resize.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.ievm_set_resize.restype = C.c_int
+    lib.ievm_forward_u8_resize.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ievm_forward_u8_resize.restype = C.c_int
+    lib.ievm_forward_u8_resize_host.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p]
+    lib.ievm_forward_u8_resize_host.restype = C.c_int
+    lib.ievm_debug_resize.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+    lib.ievm_debug_resize.restype = C.c_int
     lib.ievm_count_correct.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.ievm_count_correct.restype = C.c_int
     lib.ievm_debug_frontend.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]

@@ -29,7 +29,10 @@
 namespace ievm {
 
 constexpr int kTileM = 128;
-constexpr int kEpiWarps = 16;
+#ifndef IEVM_EPI_WARPS
+#define IEVM_EPI_WARPS 16      // multiple of 4 whose quarter is a power of two: 8 or 16 (A/B builds)
+#endif
+constexpr int kEpiWarps = IEVM_EPI_WARPS;
 constexpr int kEpiSub = kEpiWarps / 4;     // epilogue warps per TMEM lane quadrant (stem_tc.cuh: they interleave chunks)
 constexpr int kEpiGroups = kEpiWarps / 4;  // conv_tc_kernel: groups of four warps, each owning every 4th tile
 constexpr int kMaxAcc = 8;                 // accumulator buffers in TMEM (512 columns / 64)

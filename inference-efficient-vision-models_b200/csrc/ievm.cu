@@ -174,6 +174,15 @@ struct ievm_handle {
   int front2_ok = 0;       // the network's front end fits frontend_v2.cuh (224-wide input, <= 64 stem channels)
   int front_tpu = 0;       // IEVM_FRONT_TPU: pooled rows per work unit (0 = heuristic)
   uint8_t* lut_dev = nullptr;   // u8 input mode: [3][256] level -> quantised value (ievm_set_input_lut)
+  // resize front stage (ievm_set_resize): Pillow bilinear tables and the two intermediate images
+  int rs_in_h = 0, rs_in_w = 0, rs_ksize_w = 0, rs_ksize_h = 0;
+  int2* rs_bounds_w = nullptr;
+  int2* rs_bounds_h = nullptr;
+  int* rs_kk_w = nullptr;
+  int* rs_kk_h = nullptr;
+  uint8_t* rs_tmp = nullptr;    // [max_batch][rs_in_h][in_w][3]
+  uint8_t* rs_out = nullptr;    // [max_batch][in_h][in_w][3]
+  size_t stage_in_bytes = 0;
   size_t fe_smem = 0;
   int opt_cluster = 1;     // IEVM_CLUSTER=0: no 2-CTA clusters / weight multicast
   int opt_pdl = 1;         // IEVM_PDL=0: no programmatic dependent launch
@@ -1091,7 +1100,38 @@ bool front_end_is_chunked(const ievm_handle* h) {
          h->layers[1].d.in_tensor == h->layers[0].d.out_tensor && h->tensors[h->layers[0].d.out_tensor].last_use == 1;
 }
 
-int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStream_t s, bool u8_input = false) {
+// Input modes of the forward entry points.
+enum : int { kInNative = 0, kInU8 = 1, kInU8Resize = 2 };
+
+int launch_resize(ievm_handle* h, const uint8_t* x, int n, cudaStream_t s) {
+  if (!h->rs_out) return fail(IEVM_ERR_BAD_ARG, "call ievm_set_resize before ievm_forward_u8_resize");
+  const uint8_t* src = x;
+  if (h->rs_in_w != h->in_w) {      // horizontal pass: [n * rs_in_h rows][rs_in_w] -> [..][in_w]
+    const long long rows = static_cast<long long>(n) * h->rs_in_h;
+    uint8_t* dst = h->rs_in_h != h->in_h ? h->rs_tmp : h->rs_out;
+    resize_rows_u8_kernel<<<static_cast<unsigned>((rows * h->in_w + 255) / 256), 256, 0, s>>>(
+        src, dst, rows, h->rs_in_w, h->in_w, h->rs_bounds_w, h->rs_kk_w, h->rs_ksize_w);
+    src = dst;
+  }
+  if (h->rs_in_h != h->in_h) {      // vertical pass
+    const long long total = static_cast<long long>(n) * h->in_h * h->in_w;
+    resize_cols_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(
+        src, h->rs_out, n, h->rs_in_h, h->in_h, h->in_w, h->rs_bounds_h, h->rs_kk_h, h->rs_ksize_h);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return IEVM_OK;
+}
+
+int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStream_t s, int in_mode = kInNative) {
+  if (in_mode == kInU8Resize) {
+    if (h->rs_in_h == h->in_h && h->rs_in_w == h->in_w) in_mode = kInU8;          // already the right size
+    else {
+      if (int rc = launch_resize(h, static_cast<const uint8_t*>(x), n, s)) return rc;
+      x = h->rs_out;
+      in_mode = kInU8;
+    }
+  }
+  const bool u8_input = in_mode == kInU8;
   const bool i8 = h->dtype == IEVM_DTYPE_I8;
   const bool prof = h->profile != 0;
   if (prof) {
@@ -1187,21 +1227,21 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
   return IEVM_OK;
 }
 
-int forward_common(ievm_handle* h, int want_dtype, const void* x, int n, void* logits, void* stream, bool u8_input = false) {
+int forward_common(ievm_handle* h, int want_dtype, const void* x, int n, void* logits, void* stream, int in_mode = kInNative) {
   if (!h || !x || !logits) return fail(IEVM_ERR_BAD_ARG, "null argument");
   if (h->dtype != want_dtype) return fail(IEVM_ERR_BAD_ARG, "engine dtype does not match this entry point");
   if (n < 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "batch %d outside [0, %d]", n, h->max_batch);
   if (n == 0) return IEVM_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!h->use_graph || h->profile) return enqueue_forward(h, x, n, logits, s, u8_input);
-  const auto key = std::make_tuple(u8_input ? -n : n, x, logits);
+  if (!h->use_graph || h->profile) return enqueue_forward(h, x, n, logits, s, in_mode);
+  const auto key = std::make_tuple(n * 4 + in_mode, x, logits);
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
     cudaStream_t cs = h->own_stream;
     cudaGraph_t graph = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_forward(h, x, n, logits, cs, u8_input);
+    const int rc = enqueue_forward(h, x, n, logits, cs, in_mode);
     const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(IEVM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -1431,6 +1471,9 @@ void ievm_destroy(ievm_handle* h) {
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   for (void* p : h->buffers) cudaFree(p);
   for (void* p : h->owned) cudaFree(p);
+  for (void* q : {static_cast<void*>(h->rs_bounds_w), static_cast<void*>(h->rs_bounds_h), static_cast<void*>(h->rs_kk_w),
+                  static_cast<void*>(h->rs_kk_h), static_cast<void*>(h->rs_tmp), static_cast<void*>(h->rs_out)})
+    if (q) cudaFree(q);
   if (h->stage_in) cudaFree(h->stage_in);
   if (h->stage_out) cudaFree(h->stage_out);
   if (h->pin_in) cudaFreeHost(h->pin_in);
@@ -1450,17 +1493,29 @@ int ievm_forward_f16(ievm_handle* h, const void* x, int n, void* logits, void* s
   return forward_common(h, IEVM_DTYPE_F16, x, n, logits, stream);
 }
 
-static int forward_host_common(ievm_handle* h, int dtype, const void* x_host, int n, void* logits_host, bool u8_input = false) {
+static int forward_host_common(ievm_handle* h, int dtype, const void* x_host, int n, void* logits_host, int in_mode = kInNative) {
   if (!h || !x_host || !logits_host) return fail(IEVM_ERR_BAD_ARG, "null argument");
   if (n <= 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "batch %d outside [1, %d]", n, h->max_batch);
   CUDA_TRY(cudaSetDevice(h->device));
-  const size_t in_elem = u8_input ? 1 : (dtype == IEVM_DTYPE_I8 ? 4 : 2);
+  const size_t in_elem = in_mode != kInNative ? 1 : (dtype == IEVM_DTYPE_I8 ? 4 : 2);
   const size_t out_elem = dtype == IEVM_DTYPE_I8 ? 4 : 2;
-  const size_t per_img = static_cast<size_t>(h->in_c) * h->in_h * h->in_w * in_elem;
-  if (!h->stage_in) {
+  const size_t per_img = in_mode == kInU8Resize ? static_cast<size_t>(3) * h->rs_in_h * h->rs_in_w
+                                                : static_cast<size_t>(h->in_c) * h->in_h * h->in_w * in_elem;
+  if (in_mode == kInU8Resize && !h->rs_out) return fail(IEVM_ERR_BAD_ARG, "call ievm_set_resize before ievm_forward_u8_resize_host");
+  {
     const size_t native = static_cast<size_t>(h->in_c) * h->in_h * h->in_w * (dtype == IEVM_DTYPE_I8 ? 4 : 2);
-    CUDA_TRY(cudaMalloc(&h->stage_in, native * h->max_batch));
-    CUDA_TRY(cudaMalloc(&h->stage_out, out_elem * h->classes * h->max_batch));
+    const size_t need = std::max(native, per_img) * h->max_batch;
+    if (h->stage_in_bytes < need) {
+      CUDA_TRY(cudaStreamSynchronize(h->own_stream));
+      if (h->stage_in) cudaFree(h->stage_in);
+      h->stage_in = nullptr;
+      h->stage_in_bytes = 0;
+      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);      // graphs captured on the old staging buffer
+      h->graphs.clear();
+      CUDA_TRY(cudaMalloc(&h->stage_in, need));
+      h->stage_in_bytes = need;
+    }
+    if (!h->stage_out) CUDA_TRY(cudaMalloc(&h->stage_out, out_elem * h->classes * h->max_batch));
   }
   // Chunked pipeline: the H2D copy of chunk i+1 (copy stream) overlaps the forward of chunk i (compute
   // stream); PCIe, not the GPU, bounds this entry point, so the chunk size only has to be large enough
@@ -1483,7 +1538,7 @@ static int forward_host_common(ievm_handle* h, int dtype, const void* x_host, in
       CUDA_TRY(cudaStreamWaitEvent(s, h->copy_events[c], 0));
     }
     if (int rc = forward_common(h, dtype, static_cast<uint8_t*>(h->stage_in) + c0 * per_img, nc,
-                                static_cast<uint8_t*>(h->stage_out) + c0 * out_elem * h->classes, s, u8_input)) return rc;
+                                static_cast<uint8_t*>(h->stage_out) + c0 * out_elem * h->classes, s, in_mode)) return rc;
   }
   CUDA_TRY(cudaMemcpyAsync(logits_host, h->stage_out, out_elem * h->classes * n, cudaMemcpyDeviceToHost, s));
   return check_stuck(h, cudaStreamSynchronize(s), "forward (host buffers)");
@@ -1511,11 +1566,60 @@ int ievm_set_input_lut(ievm_handle* h, const uint8_t* lut768) {
 }
 
 int ievm_forward_u8(ievm_handle* h, const uint8_t* x_nhwc, int n, float* logits, void* stream) {
-  return forward_common(h, IEVM_DTYPE_I8, x_nhwc, n, logits, stream, true);
+  return forward_common(h, IEVM_DTYPE_I8, x_nhwc, n, logits, stream, kInU8);
 }
 
 int ievm_forward_u8_host(ievm_handle* h, const uint8_t* x_nhwc_host, int n, float* logits_host) {
-  return forward_host_common(h, IEVM_DTYPE_I8, x_nhwc_host, n, logits_host, true);
+  return forward_host_common(h, IEVM_DTYPE_I8, x_nhwc_host, n, logits_host, kInU8);
+}
+
+int ievm_set_resize(ievm_handle* h, int src_h, int src_w, const int32_t* bounds_w, const int32_t* kk_w, int ksize_w,
+                    const int32_t* bounds_h, const int32_t* kk_h, int ksize_h) {
+  if (!h || src_h <= 0 || src_w <= 0 || !bounds_w || !kk_w || !bounds_h || !kk_h || ksize_w <= 0 || ksize_h <= 0)
+    return fail(IEVM_ERR_BAD_ARG, "ievm_set_resize: bad arguments");
+  if (h->dtype != IEVM_DTYPE_I8) return fail(IEVM_ERR_BAD_ARG, "the 8-bit image input path belongs to the INT8 engine");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (void* q : {static_cast<void*>(h->rs_bounds_w), static_cast<void*>(h->rs_bounds_h), static_cast<void*>(h->rs_kk_w),
+                  static_cast<void*>(h->rs_kk_h), static_cast<void*>(h->rs_tmp), static_cast<void*>(h->rs_out)})
+    if (q) cudaFree(q);
+  h->rs_bounds_w = h->rs_bounds_h = nullptr;
+  h->rs_kk_w = h->rs_kk_h = nullptr;
+  h->rs_tmp = h->rs_out = nullptr;
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  h->graphs.clear();
+  h->rs_in_h = src_h; h->rs_in_w = src_w; h->rs_ksize_w = ksize_w; h->rs_ksize_h = ksize_h;
+  auto up = [&](const int32_t* src, size_t count, void** dst) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, count * sizeof(int32_t));
+    return e != cudaSuccess ? e : cudaMemcpy(*dst, src, count * sizeof(int32_t), cudaMemcpyHostToDevice);
+  };
+  CUDA_TRY(up(bounds_w, static_cast<size_t>(h->in_w) * 2, reinterpret_cast<void**>(&h->rs_bounds_w)));
+  CUDA_TRY(up(kk_w, static_cast<size_t>(h->in_w) * ksize_w, reinterpret_cast<void**>(&h->rs_kk_w)));
+  CUDA_TRY(up(bounds_h, static_cast<size_t>(h->in_h) * 2, reinterpret_cast<void**>(&h->rs_bounds_h)));
+  CUDA_TRY(up(kk_h, static_cast<size_t>(h->in_h) * ksize_h, reinterpret_cast<void**>(&h->rs_kk_h)));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->rs_tmp), static_cast<size_t>(h->max_batch) * src_h * h->in_w * 3 + 16));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->rs_out), static_cast<size_t>(h->max_batch) * h->in_h * h->in_w * 3 + 16));
+  return IEVM_OK;
+}
+
+int ievm_forward_u8_resize(ievm_handle* h, const uint8_t* x_nhwc, int n, float* logits, void* stream) {
+  return forward_common(h, IEVM_DTYPE_I8, x_nhwc, n, logits, stream, kInU8Resize);
+}
+
+int ievm_forward_u8_resize_host(ievm_handle* h, const uint8_t* x_nhwc_host, int n, float* logits_host) {
+  return forward_host_common(h, IEVM_DTYPE_I8, x_nhwc_host, n, logits_host, kInU8Resize);
+}
+
+int ievm_debug_resize(ievm_handle* h, const uint8_t* x_dev, int n, uint8_t* out_host, uint64_t out_bytes) {
+  if (!h || !x_dev || !out_host || n <= 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "debug_resize: bad arguments");
+  const size_t bytes = static_cast<size_t>(n) * h->in_h * h->in_w * 3;
+  if (out_bytes < bytes) return fail(IEVM_ERR_BAD_ARG, "debug_resize: host buffer too small");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = launch_resize(h, x_dev, n, h->own_stream)) return rc;
+  CUDA_TRY(cudaStreamSynchronize(h->own_stream));
+  const uint8_t* src = (h->rs_in_h == h->in_h && h->rs_in_w == h->in_w) ? x_dev : h->rs_out;
+  CUDA_TRY(cudaMemcpy(out_host, src, bytes, cudaMemcpyDeviceToHost));
+  return IEVM_OK;
 }
 
 int ievm_set_option(ievm_handle* h, const char* name, int value) {

@@ -579,4 +579,64 @@ __global__ void count_correct_kernel(const T* __restrict__ logits, const long lo
   if (i == 0) atomicAdd(counters + 1, static_cast<unsigned long long>(n));
 }
 
+// --------------------------------------------------------------------------------------------
+// T.Resize((224, 224)) of the reference's dataset transform (quantization/dataset.py:15) on decoded 8-bit images:
+// Pillow's ImagingResample (bilinear), bit for bit -- a horizontal then a vertical pass, each a weighted sum with
+// 22-bit fixed-point coefficients (precomputed on the host exactly as Resample.c:precompute_coeffs does), a rounding
+// bias of half an LSB and a clip to [0, 255]; the intermediate image is rounded to 8 bits between the passes.
+// bounds[o] = (first input index, taps), kk[o][ksize] = coefficients.  One thread per output pixel (3 channels).
+// --------------------------------------------------------------------------------------------
+constexpr int kResizePrecisionBits = 32 - 8 - 2;
+
+__device__ __forceinline__ uint8_t resize_clip8(int acc) { return static_cast<uint8_t>(min(max(acc >> kResizePrecisionBits, 0), 255)); }
+
+// in [rows][in_w][3] -> out [rows][out_w][3]
+__global__ void __launch_bounds__(256)
+resize_rows_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long rows, int in_w, int out_w,
+                      const int2* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * out_w) return;
+  const long long r = i / out_w;
+  const int xx = static_cast<int>(i - r * out_w);
+  const int2 b = __ldg(bounds + xx);
+  const uint8_t* src = in + (r * in_w + b.x) * 3;
+  int a0 = 1 << (kResizePrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int x = 0; x < b.y; ++x) {
+    const int k = __ldg(kk + xx * ksize + x);
+    a0 += static_cast<int>(src[3 * x]) * k;
+    a1 += static_cast<int>(src[3 * x + 1]) * k;
+    a2 += static_cast<int>(src[3 * x + 2]) * k;
+  }
+  uint8_t* dst = out + i * 3;
+  dst[0] = resize_clip8(a0);
+  dst[1] = resize_clip8(a1);
+  dst[2] = resize_clip8(a2);
+}
+
+// in [n][in_h][w][3] -> out [n][out_h][w][3]
+__global__ void __launch_bounds__(256)
+resize_cols_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n, int in_h, int out_h, int w,
+                      const int2* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long per_img = static_cast<long long>(out_h) * w;
+  if (i >= per_img * n) return;
+  const long long img = i / per_img;
+  const int rem = static_cast<int>(i - img * per_img);
+  const int yy = rem / w, x = rem - yy * w;
+  const int2 b = __ldg(bounds + yy);
+  const uint8_t* src = in + ((img * in_h + b.x) * w + x) * 3;
+  const long long row_stride = static_cast<long long>(w) * 3;
+  int a0 = 1 << (kResizePrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int y = 0; y < b.y; ++y) {
+    const int k = __ldg(kk + yy * ksize + y);
+    a0 += static_cast<int>(src[y * row_stride]) * k;
+    a1 += static_cast<int>(src[y * row_stride + 1]) * k;
+    a2 += static_cast<int>(src[y * row_stride + 2]) * k;
+  }
+  uint8_t* dst = out + i * 3;
+  dst[0] = resize_clip8(a0);
+  dst[1] = resize_clip8(a1);
+  dst[2] = resize_clip8(a2);
+}
+
 }  // namespace ievm

@@ -55,6 +55,40 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)      # quantization/dataset.py:17-18
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
+def pil_bilinear_coeffs(in_size: int, out_size: int):
+    """Per-output-pixel tables of Pillow's 8-bit bilinear resample (``Resample.c``: ``precompute_coeffs`` followed by
+    ``normalize_coeffs_8bpc``) for resizing ``in_size`` to ``out_size`` along one axis: ``bounds[o] = (first source
+    index, taps)`` and ``kk[o, :taps]`` = 22-bit fixed-point weights.  Python floats are C doubles and ``int()``
+    truncates like the C casts, so the tables equal Pillow's own (tests/test_host.py)."""
+    import math
+    precision_bits = 32 - 8 - 2
+    scale = filterscale = in_size / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = filterscale                      # bilinear filter: support 1.0
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    inv = 1.0 / filterscale
+    for o in range(out_size):
+        center = (o + 0.5) * scale
+        lo = max(int(center - support + 0.5), 0)
+        hi = min(int(center + support + 0.5), in_size)
+        weights = []
+        for x in range(lo, hi):
+            d = abs((x - center + 0.5) * inv)
+            weights.append(1.0 - d if d < 1.0 else 0.0)
+        total = 0.0
+        for w in weights:
+            total += w
+        for t, w in enumerate(weights):
+            if total != 0.0:
+                w = w / total
+            kk[o, t] = int(w * (1 << precision_bits) - 0.5) if w < 0 else int(w * (1 << precision_bits) + 0.5)
+        bounds[o] = (lo, hi - lo)
+    return bounds, kk
+
+
 def input_lut(in_scale: float, in_zp: int, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> np.ndarray:
     """[3, 256] uint8: lut[c, v] = quantize_per_tensor(Normalize(ToTensor(v)))[c], computed with the very torch /
     torchvision ops the reference's transform and converted graph run, one 8-bit level at a time -- the fused
@@ -237,13 +271,34 @@ class B200QuantizedResNet(_B200Engine):
         self._lut = lut
         return lut
 
+    def set_resize(self, src_h: int, src_w: int) -> None:
+        """Install ``T.Resize((in_h, in_w))`` (quantization/dataset.py:15: Pillow's bilinear resample) for decoded
+        source images of ``src_h x src_w``."""
+        bw, kw = pil_bilinear_coeffs(int(src_w), self.net.in_w)
+        bh, kh = pil_bilinear_coeffs(int(src_h), self.net.in_h)
+        _lib.check(self._lib.ievm_set_resize(self._handle, int(src_h), int(src_w), bw.ctypes.data, kw.ctypes.data, kw.shape[1],
+                                             bh.ctypes.data, kh.ctypes.data, kh.shape[1]), "ievm_set_resize")
+        self._resize_src = (int(src_h), int(src_w))
+
+    def debug_resize(self, images: torch.Tensor) -> np.ndarray:
+        """Only the resize stage: uint8 CUDA ``[N, h, w, 3]`` -> uint8 ``[N, in_h, in_w, 3]`` (parity hook)."""
+        if getattr(self, "_resize_src", None) != tuple(images.shape[1:3]):
+            self.set_resize(images.shape[1], images.shape[2])
+        x = images.contiguous()
+        out = np.empty((x.shape[0], self.net.in_h, self.net.in_w, 3), np.uint8)
+        _lib.check(self._lib.ievm_debug_resize(self._handle, x.data_ptr(), x.shape[0], out.ctypes.data, out.nbytes), "debug_resize")
+        return out
+
     def forward_u8(self, images: torch.Tensor) -> torch.Tensor:
-        """Decoded 8-bit images ``[N, 224, 224, 3]`` (HWC, RGB, uint8; CPU or CUDA) -> f32 logits, bit-identical to
-        ``forward(Normalize(ToTensor(images)))``.  A quarter of the input bytes over PCIe and HBM."""
+        """Decoded 8-bit images ``[N, h, w, 3]`` (HWC, RGB, uint8; CPU or CUDA) -> f32 logits, bit-identical to the
+        reference's ``Resize -> ToTensor -> Normalize`` transform followed by the converted module.  Images that are
+        already ``in_h x in_w`` skip the resize.  A quarter (or less) of the input bytes over PCIe and HBM."""
         if getattr(self, "_lut", None) is None:
             self.set_input_transform()
-        if images.dtype != torch.uint8 or images.dim() != 4 or tuple(images.shape[1:]) != (self.net.in_h, self.net.in_w, 3):
-            raise ValueError(f"expected uint8 [N,{self.net.in_h},{self.net.in_w},3], got {images.dtype} {tuple(images.shape)}")
+        if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3:
+            raise ValueError(f"expected uint8 [N,h,w,3], got {images.dtype} {tuple(images.shape)}")
+        if tuple(images.shape[1:3]) != (self.net.in_h, self.net.in_w):
+            return self._forward_u8_resize(images)
         n = images.shape[0]
         if n > self.max_batch:
             return torch.cat([self.forward_u8(images[i:i + self.max_batch]) for i in range(0, n, self.max_batch)])
@@ -255,6 +310,23 @@ class B200QuantizedResNet(_B200Engine):
         out = torch.empty((n, self.net.num_classes), dtype=torch.float32, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _lib.check(self._lib.ievm_forward_u8(self._handle, x.data_ptr(), n, out.data_ptr(), stream), "ievm_forward_u8")
+        return out
+
+    def _forward_u8_resize(self, images: torch.Tensor) -> torch.Tensor:
+        if getattr(self, "_resize_src", None) != tuple(images.shape[1:3]):
+            self.set_resize(images.shape[1], images.shape[2])
+        n = images.shape[0]
+        if n > self.max_batch:
+            return torch.cat([self._forward_u8_resize(images[i:i + self.max_batch]) for i in range(0, n, self.max_batch)])
+        x = images.contiguous()
+        if not x.is_cuda:
+            out = torch.empty((n, self.net.num_classes), dtype=torch.float32)
+            _lib.check(self._lib.ievm_forward_u8_resize_host(self._handle, x.data_ptr(), n, out.data_ptr()),
+                       "ievm_forward_u8_resize_host")
+            return out
+        out = torch.empty((n, self.net.num_classes), dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self._lib.ievm_forward_u8_resize(self._handle, x.data_ptr(), n, out.data_ptr(), stream), "ievm_forward_u8_resize")
         return out
 
     @classmethod

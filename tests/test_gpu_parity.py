@@ -183,6 +183,32 @@ def test_int8_u8_image_input_is_bit_identical_to_the_f32_pipeline(n):
     eng.close()
 
 
+@pytest.mark.parametrize("hw", [(200, 200), (300, 260), (97, 131)])
+def test_int8_resize_stage_and_full_transform_are_bit_identical(hw):
+    """SURVEY 8(f)-1 complete: Resize (Pillow bilinear) + ToTensor + Normalize + quantize on the GPU == the reference's
+    transform (quantization/dataset.py:14-19) on PIL images followed by the converted module on the CPU."""
+    from PIL import Image
+    from torchvision import transforms as T
+    from oracle.pil_resize import resize_bilinear_u8
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    torch.backends.quantized.engine = "fbgemm"
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=8)
+    rng = np.random.default_rng(hw[0])
+    imgs = rng.integers(0, 256, (3,) + hw + (3,), dtype=np.uint8)
+    u8 = torch.from_numpy(imgs)
+    resized = eng.debug_resize(u8.cuda())
+    pil = np.stack([np.asarray(Image.fromarray(im).resize((224, 224), Image.BILINEAR)) for im in imgs])
+    assert np.array_equal(resized, pil), f"{(resized != pil).mean():.3%} bytes differ from PIL"
+    assert np.array_equal(resized, resize_bilinear_u8(imgs, 224, 224))
+    tf = T.Compose([T.Resize((224, 224)), T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    x = torch.stack([tf(Image.fromarray(im)) for im in imgs])
+    with torch.no_grad():
+        ref = gm(x)
+    assert torch.equal(eng.forward_u8(u8.cuda()).cpu(), ref)
+    assert torch.equal(eng.forward_u8(u8), ref)                       # host buffers
+    eng.close()
+
+
 def test_engines_from_on_disk_artifacts_and_eval_drop_ins(tmp_path):
     """engines built from the files the reference writes; evaluate_accuracy / measure_latency
     drop-ins agree with the reference's own helpers run on the CPU module."""

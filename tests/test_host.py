@@ -98,6 +98,15 @@ def test_input_lut_equals_the_reference_transform_pipeline():
     assert np.array_equal(q, np.stack([lut[c][img[..., c]] for c in range(3)]))
 
 
+def test_resize_tables_equal_the_oracle_restatement():
+    """The product's Pillow coefficient tables (host side of ievm_set_resize) against the oracle's restatement."""
+    from oracle.pil_resize import precompute_coeffs
+    for src in (200, 224, 300, 97, 31, 500):
+        b, k = ievm_b200.pil_bilinear_coeffs(src, 224)
+        bo, ko = precompute_coeffs(src, 224)
+        assert np.array_equal(b, bo) and np.array_equal(k, ko), src
+
+
 def test_on_disk_formats_are_recognised(tmp_path):
     """widths and block kind recovered from tensor shapes; the rebuilt module reproduces the saved one."""
     from ievm_b200 import pipeline

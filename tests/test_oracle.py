@@ -84,3 +84,18 @@ def test_fp16_golden_is_sane(golden_dir):
     g = np.load(os.path.join(golden_dir, "fp16_w57.npz"))
     rel = np.abs(g["logits_fp16"] - g["logits_fp32"]).max(axis=1) / np.maximum(np.abs(g["logits_fp32"]).max(axis=1), 1)
     assert rel.max() < 1e-2
+
+
+def test_pil_resize_restatement_matches_pillow():
+    """oracle/pil_resize.py against PIL.Image.resize and torchvision's T.Resize (the reference's transform,
+    quantization/dataset.py:15) on up- and down-scaling shapes: bit-identical."""
+    from PIL import Image
+    from torchvision import transforms as T
+    from oracle.pil_resize import resize_bilinear_u8
+    rng = np.random.default_rng(0)
+    for h, w in [(200, 200), (224, 224), (300, 260), (199, 257), (64, 500), (97, 31)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(img).resize((224, 224), Image.BILINEAR))
+        assert np.array_equal(resize_bilinear_u8(img, 224, 224), ref), (h, w)
+    img = rng.integers(0, 256, (200, 200, 3), dtype=np.uint8)          # NEU-DET images are 200 x 200
+    assert np.array_equal(resize_bilinear_u8(img, 224, 224), np.asarray(T.Resize((224, 224))(Image.fromarray(img))))
