@@ -347,6 +347,21 @@ def run_b200(args, rank, world, local_rank):
                   "how": "forward_u8(cpu uint8 NHWC images) -> ievm_forward_u8_host: the reference's ToTensor + Normalize "
                          "(dataset.py:16-18) + quantize_per_tensor fused into the front-end kernel via a 3x256 LUT"}
 
+        # ... and with the dataset's native 200 x 200 images: Resize (Pillow bilinear) runs on the GPU as well
+        x200 = torch.randint(0, 256, (n, 200, 200, 3), dtype=torch.uint8,
+                             generator=torch.Generator().manual_seed(13 + rank)).pin_memory()
+        for _ in range(2):
+            eng.forward_u8(x200)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            y200 = eng.forward_u8(x200)
+        barrier()
+        r_s = max_over_ranks(time.perf_counter() - t0, dev)
+        e2e_u8["with_resize_from_200x200"] = {"value": world * n * e2e_steps / r_s, "unit": "images/s",
+                                              "h2d_bytes_per_step": x200.numel(),
+                                              "d2h_bytes_per_step": y200.numel() * y200.element_size()}
+
     # ---- bs-1 latency (BASELINE.json: "p50 bs1 latency ms"; protocol of engines.py:26-34, synchronised) ----
     latency = None
     if rank == 0 and not args.no_latency:
