@@ -129,6 +129,8 @@ class _B200Engine(nn.Module):
         if images.dtype != self._torch_dtype:
             raise TypeError(f"expected {self._torch_dtype} input, got {images.dtype}")
         n = images.shape[0]
+        if n == 0:
+            return torch.empty((0, self.net.num_classes), dtype=self._torch_dtype, device=images.device)
         if n > self.max_batch:
             return torch.cat([self.forward(images[i:i + self.max_batch]) for i in range(0, n, self.max_batch)])
         if not images.is_cuda:
@@ -297,6 +299,8 @@ class B200QuantizedResNet(_B200Engine):
             self.set_input_transform()
         if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3:
             raise ValueError(f"expected uint8 [N,h,w,3], got {images.dtype} {tuple(images.shape)}")
+        if images.shape[0] == 0:
+            return torch.empty((0, self.net.num_classes), dtype=torch.float32, device=images.device)
         if tuple(images.shape[1:3]) != (self.net.in_h, self.net.in_w):
             return self._forward_u8_resize(images)
         n = images.shape[0]

@@ -254,6 +254,33 @@ def test_int8_ragged_batches(n):
     eng.close()
 
 
+def test_int8_edge_batches_and_argument_errors():
+    """Empty batch, a batch larger than max_batch (split by the wrapper), and the loud failures of the boundary:
+    wrong dtype / shape raise, the C entry points return an error status instead of touching memory."""
+    from ievm_b200 import _lib
+    gm = cached_quantized(mf.PRUNED_WIDTHS)
+    torch.backends.quantized.engine = "fbgemm"
+    eng = _engine(mf.PRUNED_WIDTHS, max_batch=4)
+    x = mf.synthetic_images(11, seed=60)
+    assert tuple(eng(x[:0].cuda()).shape) == (0, 6) and tuple(eng(x[:0]).shape) == (0, 6)
+    with torch.no_grad():
+        ref = gm(x)
+    assert torch.equal(eng(x.cuda()).cpu(), ref)                # 11 > max_batch = 4: 4 + 4 + 3
+    assert torch.equal(eng(x), ref)
+    with pytest.raises(TypeError):
+        eng(x.half().cuda())
+    with pytest.raises(ValueError):
+        eng(x[:, :, :200].cuda())
+    with pytest.raises(ValueError):
+        eng.forward_u8(torch.zeros(2, 3, 224, 224, dtype=torch.uint8))
+    lib = _lib.load()
+    out = torch.empty(5, 6, device="cuda")
+    assert lib.ievm_forward_i8(eng._handle, x.cuda().data_ptr(), 5, out.data_ptr(), None) < 0      # 5 > max_batch
+    assert b"outside" in lib.ievm_last_error()
+    assert lib.ievm_forward_f16(eng._handle, x.cuda().data_ptr(), 1, out.data_ptr(), None) < 0     # wrong entry point
+    eng.close()
+
+
 def test_int8_tensor_core_equals_direct_conv_at_batch_64():
     eng = _engine(mf.PRUNED_WIDTHS, max_batch=64)
     x = mf.synthetic_images(64, seed=5).cuda()
