@@ -19,6 +19,10 @@
  *   ievm_set_input_lut,
  *   ievm_forward_u8*   <- the dataset transform in front of the call, T.ToTensor() + T.Normalize(mean, std)
  *                         (quantization/dataset.py:14-19), fused with the graph's quantize_per_tensor node
+ *   ievm_observe,
+ *   ievm_observer_read <- the observer passes of PTQ calibration, `prepared_model(images)` over the calibration loader
+ *                         (quantization/engines.py:123-133 `_calibrate`; quantization/main.py:236-239): float forward on
+ *                         the FP16 engine, per-batch torch.aminmax of every observed tensor reduced on the device
  *   ievm_count_correct <- the accumulation of evaluate_accuracy (quantization/engines.py:59-63; main.py:288-290)
  *   ievm_debug_*       <- no reference counterpart: parity hooks (per-tensor activations and the
  *                         int32 accumulators torch never exposes)
@@ -54,7 +58,9 @@ typedef enum ievm_dtype { IEVM_DTYPE_I8 = 0, IEVM_DTYPE_F16 = 1 } ievm_dtype;
 typedef enum ievm_op {
   IEVM_OP_CONV = 0,    /* conv (+folded BN) [+ReLU] [+residual add (+ReLU)] */
   IEVM_OP_MAXPOOL = 1, /* MaxPool2d(3, 2, 1) */
-  IEVM_OP_HEAD = 2     /* AdaptiveAvgPool2d(1) + flatten + Linear (+ dequantize) -> logits */
+  IEVM_OP_HEAD = 2,    /* AdaptiveAvgPool2d(1) + flatten + Linear (+ dequantize) -> logits */
+  IEVM_OP_ADD_RELU = 3 /* F16 only: out = relu(in_tensor + res_tensor), the BasicBlock's residual add left un-fused so
+                          that calibration can observe the conv output in front of it (see ievm_observe) */
 } ievm_op;
 
 /* One node of the flattened graph.  Tensor id 0 is the network input (for INT8: the output of
@@ -128,10 +134,27 @@ int ievm_forward_u8_resize_host(ievm_handle* h, const uint8_t* x_nhwc_host, int 
 /* Parity hook: only the resize, result [n][H][W][3] u8 copied to the host. */
 int ievm_debug_resize(ievm_handle* h, const uint8_t* x_dev, int n, uint8_t* out_host, uint64_t out_bytes);
 
+/* calibration statistics on the device.  An FP16 engine built from the observer-instrumented float
+ * model (ievm_b200.netdesc.from_prepared: residual adds as IEVM_OP_ADD_RELU layers) with options keep_tensors = 1 and
+ * observe = 1 records, per ievm_observe call, what a min/max-family observer (MinMaxObserver,
+ * MovingAverageMinMaxObserver: quantization/main.py:196-207) keeps of a batch -- the pair torch.aminmax(x) -- for
+ * every observation point of the LAST forward, on the caller's stream, without synchronising:
+ *   point 0              the network input; x_f32 (device f32 [n][c][h][w], the un-rounded batch) when given, else the
+ *                        f16 buffer the forward read
+ *   point id, 1 <= id < T  tensor `id` over its real channels (T = ievm_num_tensors)
+ *   point T              the AdaptiveAvgPool2d output (rounded to f16)
+ *   point T + 1          the logits
+ * ievm_observer_read synchronises and copies the log as f32 [records][points][2] = {min, max} (NaN = nothing observed)
+ * and returns the number of records; ievm_set_option(h, "observe", 1) clears the log.  The host replays the pairs into
+ * the prepared module's observers (ievm_b200.calibration.calibrate), after which convert_fx runs unchanged. */
+int ievm_observer_points(const ievm_handle* h);
+int ievm_observe(ievm_handle* h, const float* x_f32, void* stream);
+int ievm_observer_read(ievm_handle* h, float* minmax_host, int max_records);
+
 /* Engine options: "conv_impl" 0 = tcgen05 tensor-core kernels (default), 1 = direct CUDA-core
  * cross-check kernels (tests only); "use_graph" 1 = replay forward() from a CUDA graph cached per
  * (n, x, logits) triple; "keep_tensors" 1 = one buffer per tensor (parity hooks); "profile" 1 =
- * per-launch event timing (see ievm_profile_read). */
+ * per-launch event timing (see ievm_profile_read); "observe" 1 = (re)start the calibration observer log (F16 engines). */
 int ievm_set_option(ievm_handle* h, const char* name, int value);
 
 /* Introspection used by the benchmark and tests. */

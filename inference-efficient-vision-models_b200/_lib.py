@@ -27,6 +27,7 @@ EXPORTS = [
     "ievm_last_error", "ievm_build_info", "ievm_probe_im2col", "ievm_profile_read", "ievm_probe_patch",
     "ievm_debug_frontend", "ievm_set_input_lut", "ievm_forward_u8", "ievm_forward_u8_host",
     "ievm_count_correct", "ievm_set_resize", "ievm_forward_u8_resize", "ievm_forward_u8_resize_host", "ievm_debug_resize",
+    "ievm_observer_points", "ievm_observe", "ievm_observer_read",
 ]
 
 
@@ -134,6 +135,12 @@ def load():
     lib.ievm_debug_frontend.restype = C.c_int
     lib.ievm_profile_read.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
     lib.ievm_profile_read.restype = C.c_int
+    lib.ievm_observer_points.argtypes = [H]
+    lib.ievm_observer_points.restype = C.c_int
+    lib.ievm_observe.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.ievm_observe.restype = C.c_int
+    lib.ievm_observer_read.argtypes = [H, C.c_void_p, C.c_int]
+    lib.ievm_observer_read.restype = C.c_int
     for name in ("ievm_forward_i8", "ievm_forward_f16", "ievm_forward_i8_host", "ievm_forward_f16_host",
                  "ievm_set_option", "ievm_num_tensors", "ievm_tensor_shape", "ievm_launches_per_forward",
                  "ievm_debug_read_tensor", "ievm_debug_conv_acc", "ievm_kd_loss"):

@@ -123,8 +123,11 @@ __device__ __forceinline__ int requant_i8(int acc, float bdiv, float mult, int z
 }
 __device__ __forceinline__ int add_relu_i8(int aq, int a_zp, float a_scale, int rq, int r_zp, float r_scale,
                                            float inv_scale, int zp) {
-  const float a = __fmul_rn(__int2float_rn(aq - a_zp), a_scale);
-  const float b = __fmul_rn(__int2float_rn(rq - r_zp), r_scale);
+  // ATen's vectorised qadd dequantises with ONE fused multiply-add against a pre-rounded product,
+  // fma(scale, float(q), fl(scale * -zp)) (Vectorized<quint8>::dequantize), not (q - zp) * scale: the two differ by an
+  // ulp often enough to move ~1e-5 of the outputs by one LSB when both zero points are large (oracle/int8_forward.py).
+  const float a = __fmaf_rn(a_scale, __int2float_rn(aq), __fmul_rn(a_scale, -__int2float_rn(a_zp)));
+  const float b = __fmaf_rn(r_scale, __int2float_rn(rq), __fmul_rn(r_scale, -__int2float_rn(r_zp)));
   const float s = fmaxf(__fadd_rn(a, b), 0.0f);
   const int q = __float2int_rn(__fmul_rn(s, inv_scale)) + zp;
   return min(max(q, 0), 255);
@@ -146,7 +149,8 @@ constexpr float kRoundMagic = 12582912.0f;   // 1.5 * 2^23: (x + M) - M == rint(
 struct AddReluConst {
   float lo_f, hi_f;        // clamp of the conv's own requantised value, relative to its zero point
   float a_scale, r_scale, inv_scale;
-  float r_bias;            // kRoundMagic + res_zp: subtracting it turns (magic | byte) into (byte - res_zp)
+  float pa, pb;            // fl(a_scale * -out_zp), fl(r_scale * -res_zp): addends of ATen's fused dequantisation
+  float lo_q, zp_f;        // float(out_lo), float(out_zp)
   int add_zp;
   // fast form (magic-number rounding allowed): integer clamps done by one VIADDMNMX.RELU each
   int c1_add, c1_max;      // clamp(rne(v), lo, hi) - lo == max(min(bits(v + M) + c1_add, c1_max), 0)
@@ -204,20 +208,22 @@ __device__ __forceinline__ uint4 epilogue16_i8_res(const uint32_t (&v)[16], cons
     for (int b = 0; b < 4; ++b) {
       const int i = 4 * j + b;
       float t = __fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[i])), bd[b]), mu[b]);
-      const float rb = __fadd_rn(__uint_as_float(__byte_perm(rw[j], 0x4B400000u, 0x7650 + b)), -k.r_bias);
+      // dequantised residual: (magic | byte) - magic == float(byte), then fma(s_r, byte, fl(s_r * -zp_r)) as ATen does
+      const float rb = __fmaf_rn(k.r_scale, __fadd_rn(__uint_as_float(__byte_perm(rw[j], 0x4B400000u, 0x7650 + b)), -kRoundMagic),
+                                 k.pb);
       if (kFast) {
         // Integer clamps after the magic-number rounding: rne commutes with clamping to integer bounds, and
         // max(s, 0) before the final scaling equals clamping the rounded value at 0 (the scale is positive), so
         // each clamp pair is ONE add-min-relu instruction instead of two FMNMX (the ALU pipe issues at half rate).
         const int tq = __viaddmin_s32_relu(__float_as_int(__fadd_rn(t, kRoundMagic)), k.c1_add, k.c1_max);   // q2 - lo
-        const float a = __fmul_rn(__fadd_rn(__int2float_rn(tq), k.lo_f), k.a_scale);                        // (q2 - zp2) * s2
-        const float u = __fmul_rn(__fadd_rn(a, __fmul_rn(rb, k.r_scale)), k.inv_scale);
+        const float a = __fmaf_rn(k.a_scale, __fadd_rn(__int2float_rn(tq), k.lo_q), k.pa);                  // fma(s2, q2, fl(s2 * -zp2))
+        const float u = __fmul_rn(__fadd_rn(a, rb), k.inv_scale);
         q[i] = __viaddmin_s32_relu(__float_as_int(__fadd_rn(u, kRoundMagic)), k.c2_add, k.c2_max);          // q - add_zp
       } else {
         t = fminf(fmaxf(t, k.lo_f), k.hi_f);
         t = __fadd_rn(__fadd_rn(t, kRoundMagic), -kRoundMagic);          // == float(q2 - zp2)
-        const float a = __fmul_rn(t, k.a_scale);
-        const float s = fmaxf(__fadd_rn(a, __fmul_rn(rb, k.r_scale)), 0.0f);
+        const float a = __fmaf_rn(k.a_scale, __fadd_rn(t, k.zp_f), k.pa);
+        const float s = fmaxf(__fadd_rn(a, rb), 0.0f);
         q[i] = __float2int_rn(__fmul_rn(s, k.inv_scale)) + k.add_zp;
       }
     }
@@ -586,7 +592,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     k.a_scale = p.a_scale;
     k.r_scale = p.res_scale;
     k.inv_scale = p.inv_add_scale;
-    k.r_bias = kRoundMagic + static_cast<float>(p.res_zp);
+    k.pa = __fmul_rn(p.a_scale, -static_cast<float>(p.out_zp));
+    k.pb = __fmul_rn(p.res_scale, -static_cast<float>(p.res_zp));
+    k.lo_q = static_cast<float>(p.out_lo);
+    k.zp_f = static_cast<float>(p.out_zp);
     k.add_zp = p.add_zp;
     k.c1_add = -kRoundMagicBits - (p.out_lo - p.out_zp);
     k.c1_max = 255 - p.out_lo;

@@ -189,7 +189,6 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvWtParams p)
     griddep_wait();                                // before the first residual read / output store
     // fused add_relu constants (see conv_tc.cuh)
     const float lo_f = static_cast<float>(p.out_lo - p.out_zp), hi_f = static_cast<float>(255 - p.out_zp);
-    const float r_bias = static_cast<float>(p.res_zp);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
@@ -233,8 +232,10 @@ conv_wt_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvWtParams p)
           } else {
             float t = fminf(fmaxf(t0, lo_f), hi_f);
             t = __fadd_rn(__fadd_rn(t, kRoundMagic), -kRoundMagic);                  // == float(q2 - zp2)
-            const float a = __fmul_rn(t, p.a_scale);
-            const float rb = __fmul_rn(__fadd_rn(__uint2float_rn(rq[j]), -r_bias), p.res_scale);
+            // ATen's fused dequantisation, as in conv_tc.cuh: fma(scale, float(q), fl(scale * -zp))
+            const float a = __fmaf_rn(p.a_scale, __fadd_rn(t, static_cast<float>(p.out_zp)),
+                                      __fmul_rn(p.a_scale, -static_cast<float>(p.out_zp)));
+            const float rb = __fmaf_rn(p.res_scale, __uint2float_rn(rq[j]), __fmul_rn(p.res_scale, -static_cast<float>(p.res_zp)));
             const float s = fmaxf(__fadd_rn(a, rb), 0.0f);
             const float u = __fmul_rn(s, p.inv_add_scale);
             q = p.fast_round ? round_add<true>(u, p.add_zp) : round_add<false>(u, p.add_zp);

@@ -24,6 +24,7 @@
 #include "frontend_fused.cuh"
 #include "frontend_v2.cuh"
 #include "conv_wt.cuh"
+#include "observe.cuh"
 
 namespace {
 
@@ -197,6 +198,13 @@ struct ievm_handle {
   std::vector<void*> buffers;
   std::vector<size_t> buffer_bytes;
   std::vector<void*> owned;            // device allocations freed at destroy
+  // calibration observers (observe.cuh): per ievm_observe call one record of (min, max) pairs, order-encoded u32
+  uint32_t* obs_log = nullptr;         // [kObsMaxRecords][obs_points()][2]
+  int obs_records = 0;
+  __half* obs_pooled = nullptr;        // avgpool output of the last forward, [max_batch][head cin]; null = not calibrating
+  __half* obs_pooled_alloc = nullptr;
+  const void* last_x = nullptr;        // caller's buffers of the last forward (network input / logits)
+  const void* last_logits = nullptr;
   int conv_impl = 0;
   int keep_tensors = 0;
   int use_graph = 0;
@@ -286,6 +294,22 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
       L.wo = (tin.w + 2 - 3) / 2 + 1;
       tout.h = L.ho;
       tout.w = L.wo;
+      tout.c = tin.c;
+      tout.pitch = tin.pitch;
+      continue;
+    }
+    if (d.op == IEVM_OP_ADD_RELU) {
+      if (h->dtype != IEVM_DTYPE_F16) return fail(IEVM_ERR_UNSUPPORTED, "layer %d: a stand-alone add_relu exists for F16 only "
+                                                                       "(INT8: fused into the conv, res_tensor)", i);
+      if (d.res_tensor < 0 || d.res_tensor > max_id) return fail(IEVM_ERR_BAD_ARG, "layer %d: add_relu needs res_tensor", i);
+      const TensorInfo& tr = h->tensors[d.res_tensor];
+      if (d.in_tensor == 0 || d.res_tensor == 0 || tr.h != tin.h || tr.w != tin.w || tr.c != tin.c || tr.pitch != tin.pitch ||
+          tin.pitch % 8 != 0)
+        return fail(IEVM_ERR_BAD_ARG, "layer %d: add_relu operands differ in shape", i);
+      L.ho = tin.h;
+      L.wo = tin.w;
+      tout.h = tin.h;
+      tout.w = tin.w;
       tout.c = tin.c;
       tout.pitch = tin.pitch;
       continue;
@@ -1193,6 +1217,13 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
       if (int rc = launch_conv(h, L, n, s, nullptr)) return rc;
     } else if (d.op == IEVM_OP_MAXPOOL) {
       if (int rc = launch_maxpool(h, L, tensor_ptr(h, d.in_tensor), tensor_ptr(h, d.out_tensor), n, s)) return rc;
+    } else if (d.op == IEVM_OP_ADD_RELU) {
+      const TensorInfo& tin = h->tensors[d.in_tensor];
+      const long long nvec = static_cast<long long>(n) * tin.h * tin.w * tin.pitch / 8;
+      add_relu_f16_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, 0, s>>>(
+          static_cast<const uint4*>(tensor_ptr(h, d.in_tensor)), static_cast<const uint4*>(tensor_ptr(h, d.res_tensor)),
+          static_cast<uint4*>(tensor_ptr(h, d.out_tensor)), nvec);
+      CUDA_TRY(cudaGetLastError());
     } else {   // head
       const TensorInfo& tin = h->tensors[d.in_tensor];
       if (i8) {
@@ -1207,6 +1238,7 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
         HeadF16Params hp;
         hp.hw = tin.h * tin.w; hp.c = tin.c; hp.cpad = tin.pitch; hp.classes = d.cout;
         hp.w = static_cast<const __half*>(L.w_packed); hp.bias = L.ep0;
+        hp.pooled = h->obs_pooled;           // non-null only while calibrating (ievm_observe)
         CUDA_TRY(launch_kernel(head_f16_kernel, n, kHeadThreads, 0, s, h->opt_pdl != 0,
                                static_cast<const __half*>(tensor_ptr(h, d.in_tensor)), static_cast<__half*>(logits), hp));
       }
@@ -1214,6 +1246,8 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     }
   }
   h->last_n = n;
+  h->last_x = x;
+  h->last_logits = logits;
   if (prof) {
     CUDA_TRY(cudaEventRecord(h->prof_events[h->layers.size() + 1], s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -1252,6 +1286,8 @@ int forward_common(ievm_handle* h, int want_dtype, const void* x, int n, void* l
   }
   CUDA_TRY(cudaGraphLaunch(it->second, s));
   h->last_n = n;
+  h->last_x = x;
+  h->last_logits = logits;
   return IEVM_OK;
 }
 
@@ -1649,7 +1685,96 @@ int ievm_set_option(ievm_handle* h, const char* name, int value) {
     if (int rc = assign_buffers(h)) return rc;
     return encode_maps(h);
   }
+  if (!strcmp(name, "observe")) {
+    // calibration mode (observe.cuh): (re)start the observer log; the head also writes its avgpool output
+    if (h->dtype != IEVM_DTYPE_F16) return fail(IEVM_ERR_UNSUPPORTED, "observers run on the FP16 engine (the float forward of PTQ calibration)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);   // the pooled-output pointer is baked into captured launches
+    h->graphs.clear();
+    h->obs_records = 0;
+    if (!value) {
+      h->obs_pooled = nullptr;
+      return IEVM_OK;
+    }
+    if (!h->obs_log) {
+      void* p = nullptr;
+      CUDA_TRY(cudaMalloc(&p, static_cast<size_t>(kObsMaxRecords) * (h->tensors.size() + 2) * 2 * sizeof(uint32_t)));
+      h->owned.push_back(p);
+      h->obs_log = static_cast<uint32_t*>(p);
+    }
+    if (!h->obs_pooled) {
+      int head_cin = 0;
+      for (const LayerPlan& L : h->layers)
+        if (L.d.op == IEVM_OP_HEAD) head_cin = L.d.cin;
+      void* p = nullptr;
+      CUDA_TRY(cudaMalloc(&p, std::max<size_t>(static_cast<size_t>(h->max_batch) * head_cin * sizeof(__half), 16)));
+      h->owned.push_back(p);
+      h->obs_pooled_alloc = static_cast<__half*>(p);
+    }
+    h->obs_pooled = h->obs_pooled_alloc;
+    return IEVM_OK;
+  }
   return fail(IEVM_ERR_BAD_ARG, "unknown option '%s'", name);
+}
+
+int ievm_observer_points(const ievm_handle* h) { return h ? static_cast<int>(h->tensors.size()) + 2 : 0; }
+
+int ievm_observe(ievm_handle* h, const float* x_f32, void* stream) {
+  if (!h) return fail(IEVM_ERR_BAD_ARG, "null argument");
+  if (!h->obs_log || !h->obs_pooled) return fail(IEVM_ERR_BAD_ARG, "ievm_observe: set option observe=1 first");
+  if (!h->keep_tensors) return fail(IEVM_ERR_BAD_ARG, "ievm_observe: needs keep_tensors=1 (every tensor in its own buffer)");
+  if (h->last_n <= 0 || !h->last_x || !h->last_logits) return fail(IEVM_ERR_BAD_ARG, "ievm_observe: no forward to observe");
+  if (h->obs_records >= kObsMaxRecords) return fail(IEVM_ERR_OOM, "ievm_observe: observer log full (%d records)", kObsMaxRecords);
+  const void* x0 = x_f32 ? static_cast<const void*>(x_f32) : h->last_x;
+  if (reinterpret_cast<uintptr_t>(x0) % 16 != 0 || reinterpret_cast<uintptr_t>(h->last_logits) % 16 != 0)
+    return fail(IEVM_ERR_BAD_ARG, "ievm_observe: input / logits buffers must be 16-byte aligned");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int T = static_cast<int>(h->tensors.size());
+  const int points = T + 2;
+  const int n = h->last_n;
+  uint32_t* rec = h->obs_log + static_cast<size_t>(h->obs_records) * points * 2;
+  observe_init_kernel<<<(2 * points + 255) / 256, 256, 0, s>>>(rec, points);
+  // streaming reductions: enough blocks to keep every SM's memory pipeline busy, grid-stride beyond that
+  auto blocks = [&](long long count, int lanes) {
+    const long long want = (count / lanes + 255) / 256;
+    return static_cast<unsigned>(std::min<long long>(std::max<long long>(want, 1), static_cast<long long>(h->num_sms) * 8));
+  };
+  const long long in_count = static_cast<long long>(n) * h->in_c * h->in_h * h->in_w;
+  if (x_f32) observe_minmax_kernel<float><<<blocks(in_count, 4), 256, 0, s>>>(x_f32, in_count, 1, 1, rec);
+  else observe_minmax_kernel<__half><<<blocks(in_count, 8), 256, 0, s>>>(static_cast<const __half*>(h->last_x), in_count, 1, 1, rec);
+  for (int id = 1; id < T; ++id) {
+    const TensorInfo& t = h->tensors[id];
+    if (t.buffer < 0 || t.elem != 2) continue;      // stays "nothing observed" (NaN)
+    const long long count = static_cast<long long>(n) * t.h * t.w * t.pitch;
+    observe_minmax_kernel<__half><<<blocks(count, 8), 256, 0, s>>>(static_cast<const __half*>(tensor_ptr(h, id)), count, t.pitch,
+                                                                   t.c, rec + 2 * id);
+  }
+  int head_cin = 0;
+  for (const LayerPlan& L : h->layers)
+    if (L.d.op == IEVM_OP_HEAD) head_cin = L.d.cin;
+  const long long pooled_count = static_cast<long long>(n) * head_cin;
+  observe_minmax_kernel<__half><<<blocks(pooled_count, 8), 256, 0, s>>>(h->obs_pooled, pooled_count, 1, 1, rec + 2 * T);
+  const long long logit_count = static_cast<long long>(n) * h->classes;
+  observe_minmax_kernel<__half><<<blocks(logit_count, 8), 256, 0, s>>>(static_cast<const __half*>(h->last_logits), logit_count, 1, 1,
+                                                                       rec + 2 * (T + 1));
+  CUDA_TRY(cudaGetLastError());
+  ++h->obs_records;
+  return IEVM_OK;
+}
+
+int ievm_observer_read(ievm_handle* h, float* minmax_host, int max_records) {
+  if (!h || !minmax_host || max_records < 0) return fail(IEVM_ERR_BAD_ARG, "ievm_observer_read: bad arguments");
+  const int nrec = std::min(h->obs_records, max_records);
+  if (nrec == 0) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = check_stuck(h, cudaDeviceSynchronize(), "observer_read sync")) return rc;
+  const size_t words = static_cast<size_t>(nrec) * (h->tensors.size() + 2) * 2;
+  std::vector<uint32_t> enc(words);
+  CUDA_TRY(cudaMemcpy(enc.data(), h->obs_log, words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < words; ++i) minmax_host[i] = obs_decode(enc[i]);
+  return nrec;
 }
 
 int ievm_num_tensors(const ievm_handle* h) { return h ? static_cast<int>(h->tensors.size()) : 0; }

@@ -299,6 +299,7 @@ struct HeadF16Params {
   int hw, c, cpad, classes;
   const __half* w;   // [classes][cpad]
   const float* bias;
+  __half* pooled = nullptr;   // calibration only (observe.cuh): the avgpool output, [n][c]
 };
 
 __global__ void __launch_bounds__(kHeadThreads)
@@ -341,7 +342,9 @@ head_f16_kernel(const __half* __restrict__ in, __half* __restrict__ logits, cons
   for (int c = threadIdx.x; c < p.c; c += kHeadThreads) {
     float sc = 0.f;
     for (int k = 0; k < ph_count; ++k) sc += s_sum[k * p.cpad + c];
-    const float m = __half2float(__float2half_rn(sc * inv));
+    const __half mh = __float2half_rn(sc * inv);
+    if (p.pooled) p.pooled[static_cast<long long>(img) * p.c + c] = mh;
+    const float m = __half2float(mh);
     for (int o = 0; o < p.classes; ++o) acc[o] += m * __half2float(p.w[o * p.cpad + c]);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -12,6 +12,11 @@ Three producers are accepted, exactly the three the reference hands to ``model(i
 * ``from_half_module(m)`` -- the ``.half()``-cast torchvision ResNet (quantization/engines.py:84-93,
   quantization/main.py:256-262) with BasicBlock (student) or Bottleneck (ResNet-50 teacher,
   knowledge_distillation/utils.py:28-38) blocks; eval-mode BatchNorm is folded into the conv in fp32.
+
+For calibration on the GPU a fourth walker, ``from_prepared(prepared)``, flattens the
+observer-instrumented float ``GraphModule`` that ``prepare_fx`` returns (quantization/engines.py:109,
+quantization/main.py:232) into an FP16 network whose residual adds stay separate ``OP_ADD_RELU`` layers, together
+with the observer plan: which observer module sees which tensor, in call order.
 """
 from __future__ import annotations
 
@@ -21,7 +26,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-OP_CONV, OP_MAXPOOL, OP_HEAD = 0, 1, 2
+OP_CONV, OP_MAXPOOL, OP_HEAD, OP_ADD_RELU = 0, 1, 2, 3
 DTYPE_I8, DTYPE_F16 = 0, 1
 
 
@@ -77,6 +82,8 @@ class NetSpec:
                 shape[L.out_tensor] = (oh, ow)
             elif L.op == OP_MAXPOOL:
                 shape[L.out_tensor] = ((ih - 1) // 2 + 1, (iw - 1) // 2 + 1)
+            elif L.op == OP_ADD_RELU:
+                shape[L.out_tensor] = (ih, iw)
             else:
                 total += L.cin * L.cout
         return total
@@ -357,3 +364,127 @@ def from_half_module(model, in_hw=(224, 224)) -> NetSpec:
                                 weight=np.ascontiguousarray(fc.weight.detach().half().numpy()),
                                 bias=fc.bias.detach().float().numpy().copy()))
     return net
+
+
+# --------------------------------------------------------------------------------- calibration (FP16)
+
+POINT_POOLED, POINT_LOGITS = "pooled", "logits"      # observation points that are not workspace tensors
+
+
+def from_prepared(prepared, in_hw=(224, 224)):
+    """Flatten the observer-instrumented float module returned by ``prepare_fx`` (quantization/engines.py:109,
+    quantization/main.py:232: conv+BN(+ReLU) already fused, one observer call after every quantizable node).
+
+    Returns ``(net, plan)``: ``net`` is an FP16 ``NetSpec`` in which every ``add -> relu`` pair is its own
+    ``OP_ADD_RELU`` layer (so the conv output in front of the add exists as a tensor), and ``plan`` lists the observer
+    calls of one forward in graph order as ``(observer module name, point)`` with ``point`` a tensor id,
+    ``POINT_POOLED`` (the avgpool / flatten output) or ``POINT_LOGITS``.  Observer modules that appear under several
+    names (prepare_fx shares one instance between a max-pool / avg-pool / flatten and its input) are listed once per
+    call, as the reference's calibration forward calls them."""
+    import operator
+
+    import torch.ao.nn.intrinsic as nni
+    from torch.ao.quantization.observer import ObserverBase
+
+    net = NetSpec(dtype=DTYPE_F16, in_h=in_hw[0], in_w=in_hw[1])
+    tid: Dict[str, object] = {}      # fx node name -> tensor id | ("add", a, b) | (POINT_POOLED, src) | POINT_LOGITS
+    ch: Dict[int, int] = {}
+    plan = []
+    nid = 1
+
+    def tensor_of(node):
+        t = tid[node.name]
+        if not isinstance(t, int):
+            raise ValueError(f"{node.name}: expected a feature-map tensor, got {t!r}")
+        return t
+
+    def conv_layer(name, conv, src, relu):
+        nonlocal nid
+        if conv.kernel_size[0] != conv.kernel_size[1] or conv.groups != 1 or tuple(conv.dilation) != (1, 1) \
+                or conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1]:
+            raise ValueError(f"{name}: unsupported conv geometry")
+        bias = conv.bias.detach().float().numpy().copy() if conv.bias is not None else np.zeros(conv.out_channels, np.float32)
+        L = LayerSpec(op=OP_CONV, name=name, in_tensor=src, out_tensor=nid, cin=conv.in_channels, cout=conv.out_channels,
+                      ksize=conv.kernel_size[0], stride=conv.stride[0], pad=conv.padding[0], relu=relu,
+                      weight=np.ascontiguousarray(conv.weight.detach().half().numpy()), bias=bias)
+        net.layers.append(L)
+        net.tensor_names[nid] = name
+        ch[nid] = conv.out_channels
+        nid += 1
+        return L.out_tensor
+
+    def add_relu_layer(name, pending):
+        nonlocal nid
+        _, a, b = pending
+        net.layers.append(LayerSpec(op=OP_ADD_RELU, name=name, in_tensor=a, res_tensor=b, out_tensor=nid, cin=ch[a], cout=ch[a],
+                                    relu=True))
+        net.tensor_names[nid] = name
+        ch[nid] = ch[a]
+        nid += 1
+        return nid - 1
+
+    for node in prepared.graph.nodes:
+        if node.op == "placeholder":
+            tid[node.name] = 0
+            ch[0] = net.in_c
+            net.tensor_names[0] = node.name
+        elif node.op == "output":
+            pass
+        elif node.op == "call_module":
+            mod = prepared.get_submodule(node.target)     # (named_modules() lists a shared observer once)
+            src = tid[node.args[0].name]
+            if isinstance(mod, ObserverBase):
+                point = src if isinstance(src, int) else (src[0] if isinstance(src, tuple) else src)
+                if point == "add":
+                    raise ValueError(f"{node.target}: an observer on a bare add (no ReLU behind it) is not supported")
+                plan.append((node.target, point))
+                tid[node.name] = src
+            elif isinstance(mod, nni.ConvReLU2d):
+                tid[node.name] = conv_layer(node.target, mod[0], tensor_of(node.args[0]), True)
+            elif isinstance(mod, torch.nn.Conv2d):
+                tid[node.name] = conv_layer(node.target, mod, tensor_of(node.args[0]), False)
+            elif isinstance(mod, torch.nn.MaxPool2d):
+                k = mod.kernel_size if isinstance(mod.kernel_size, int) else mod.kernel_size[0]
+                st = mod.stride if isinstance(mod.stride, int) else mod.stride[0]
+                pd = mod.padding if isinstance(mod.padding, int) else mod.padding[0]
+                if (k, st, pd) != (3, 2, 1):
+                    raise ValueError("only MaxPool2d(3, 2, 1) is supported")
+                t = tensor_of(node.args[0])
+                net.layers.append(LayerSpec(op=OP_MAXPOOL, name=node.target, in_tensor=t, out_tensor=nid, cin=ch[t], cout=ch[t]))
+                net.tensor_names[nid] = node.target
+                ch[nid] = ch[t]
+                tid[node.name] = nid
+                nid += 1
+            elif isinstance(mod, torch.nn.ReLU):
+                if not (isinstance(src, tuple) and src[0] == "add"):
+                    raise ValueError(f"{node.target}: a ReLU that is neither fused into a conv nor behind an add")
+                tid[node.name] = add_relu_layer(node.name, src)
+            elif isinstance(mod, torch.nn.AdaptiveAvgPool2d):
+                tid[node.name] = (POINT_POOLED, tensor_of(node.args[0]))
+            elif isinstance(mod, torch.nn.Linear):
+                if not (isinstance(src, tuple) and src[0] == POINT_POOLED):
+                    raise ValueError("Linear without a preceding AdaptiveAvgPool2d")
+                net.num_classes = mod.out_features
+                net.layers.append(LayerSpec(op=OP_HEAD, name=node.target, in_tensor=src[1], cin=mod.in_features,
+                                            cout=mod.out_features,
+                                            weight=np.ascontiguousarray(mod.weight.detach().half().numpy()),
+                                            bias=mod.bias.detach().float().numpy().copy()))
+                tid[node.name] = POINT_LOGITS
+            else:
+                raise ValueError(f"unsupported module {type(mod).__name__} at {node.target} (was the model in eval() mode "
+                                 "when prepare_fx fused conv + BN?)")
+        elif node.op == "call_function" and node.target in (operator.add, operator.iadd, torch.add):
+            tid[node.name] = ("add", tensor_of(node.args[0]), tensor_of(node.args[1]))
+        elif node.op == "call_function" and node.target in (torch.relu, torch.nn.functional.relu):
+            src = tid[node.args[0].name]
+            if not (isinstance(src, tuple) and src[0] == "add"):
+                raise ValueError(f"{node.name}: a ReLU that is neither fused into a conv nor behind an add")
+            tid[node.name] = add_relu_layer(node.name, src)
+        elif node.op == "call_function" and node.target is torch.flatten:
+            tid[node.name] = tid[node.args[0].name]
+        else:
+            raise ValueError(f"unsupported graph node {node.op}:{node.target}")
+    if not net.layers or net.layers[-1].op != OP_HEAD:
+        raise ValueError("the prepared graph does not end in AdaptiveAvgPool2d + Linear")
+    _check_order(net)
+    return net, plan

@@ -115,6 +115,44 @@ def static_quantize_fbgemm(model: nn.Module, calib=None) -> nn.Module:
     return quantize_fx.convert_fx(prepared)       # engines.py:118
 
 
+def minmax_qconfig_mapping():
+    """The qconfig of the reference's stage-4 script (quantization/main.py:187-222): per-channel symmetric min/max weight
+    observers, moving-average min/max activation observers over the full 0..255 range (no ``reduce_range``)."""
+    from torch.ao.quantization import QConfig, QConfigMapping
+    from torch.ao.quantization.observer import MovingAverageMinMaxObserver, PerChannelMinMaxObserver
+
+    weight_observer = PerChannelMinMaxObserver.with_args(dtype=torch.qint8, qscheme=torch.per_channel_symmetric, ch_axis=0)
+    activation_observer = MovingAverageMinMaxObserver.with_args(dtype=torch.quint8, qscheme=torch.per_tensor_affine,
+                                                                averaging_constant=0.01)
+    qc = QConfig(activation=activation_observer, weight=weight_observer)
+    return (QConfigMapping().set_global(qc).set_object_type(nn.Conv2d, qc).set_object_type(nn.Linear, qc)
+            .set_object_type(nn.ReLU, qc).set_object_type(nn.BatchNorm2d, qc))
+
+
+def prepare_minmax(model: nn.Module, qconfig_mapping=None) -> nn.Module:
+    """``prepare_fx`` as quantization/main.py:224-234 calls it (deep copy first: main.py:179).  The execution engine is
+    pinned to fbgemm -- the reference's script selects qnnpack at :187, but the contract of this repo is fbgemm
+    arithmetic and the observers do not depend on the engine."""
+    from torch.ao.quantization import quantize_fx
+
+    torch.backends.quantized.engine = "fbgemm"
+    work = copy.deepcopy(model).eval()
+    prepared = quantize_fx.prepare_fx(work, qconfig_mapping or minmax_qconfig_mapping(), (torch.randn(1, 3, 224, 224),))
+    return prepared.eval()
+
+
+def static_quantize_minmax(model: nn.Module, calib=None) -> nn.Module:
+    """Restates the static_int8 branch of quantization/main.py:185-242 (CPU calibration loop at :236-239)."""
+    from torch.ao.quantization import quantize_fx
+
+    calib = calibration_batches() if calib is None else calib
+    prepared = prepare_minmax(model)
+    with torch.no_grad():
+        for images, _ in calib:
+            prepared(images.to("cpu"))
+    return quantize_fx.convert_fx(prepared)
+
+
 def cast_fp16(model: nn.Module) -> nn.Module:
     """Restates quantization/engines.py:84-93."""
     return copy.deepcopy(model).half().eval()

@@ -17,7 +17,7 @@ arithmetic so that int32 accumulators (which torch never exposes) are available 
                         v   = (float(acc) + bias/(x_s*w_s[c])) * ((x_s*w_s[c]) / out_s)   (fbgemm ReQuantizeOutput, float bias)
                         q   = clamp(rne(v) + out_zp, lo, 255), lo = out_zp if relu else 0
   quantized max_pool2d  integer max over the window (padding ignored), qparams pass through
-  quantized::add_relu   a = (aq - a_zp) * a_s ; b = (bq - b_zp) * b_s
+  quantized::add_relu   a = fma(a_s, aq, fl(a_s * -a_zp)) ; b = fma(b_s, bq, fl(b_s * -b_zp))   (ATen's vector path)
                         q = clamp(rne(max(a + b, 0) * (1/s)) + zp, 0, 255)
   adaptive_avg_pool2d   q = clamp(rne(float(sum) / count), 0, 255)           (zp == 0 on this path)
   dequantize            y = (q - zp) * s
@@ -153,9 +153,21 @@ def maxpool3x3s2(xq: np.ndarray) -> np.ndarray:
     return F.max_pool2d(t, 3, 2, 1).numpy().astype(np.uint8)    # -inf padding == padding ignored
 
 
+def _dequant_fma(q: np.ndarray, scale: float, zp: int) -> np.ndarray:
+    """ATen's vectorised dequantisation inside qadd (aten/src/ATen/native/quantized/cpu/kernels/QuantizedOpKernels.cpp
+    ``qadd_kernel``: ``Vectorized<c10::quint8>::dequantize(scale, zero_point, scale_zp_premul)``):
+    ``fma(scale, float(q), fl32(scale * -zp))`` -- one rounding on top of a pre-rounded product, not ``(q - zp) * scale``.
+    The two forms differ by an ulp on many elements and by one output LSB on about 1e-5 of them when both operands have a
+    large zero point (observed: layer4.0's add of the quantization/main.py qconfig flavour; tests/test_calibration.py).
+    float64 holds ``q * scale + premul`` exactly (8 + 24 bits against 24 bits), so one cast to float32 is the fma."""
+    s32 = np.float32(scale)
+    premul = np.float32(s32 * np.float32(-zp))
+    return (q.astype(np.float64) * np.float64(s32) + np.float64(premul)).astype(np.float32)
+
+
 def add_relu(aq, a_scale, a_zp, bq, b_scale, b_zp, out_scale, out_zp) -> np.ndarray:
-    a = (aq.astype(np.float32) - np.float32(a_zp)) * np.float32(a_scale)
-    b = (bq.astype(np.float32) - np.float32(b_zp)) * np.float32(b_scale)
+    a = _dequant_fma(aq, a_scale, a_zp)
+    b = _dequant_fma(bq, b_scale, b_zp)
     s = np.maximum((a + b).astype(np.float32), np.float32(0))
     inv = np.float32(1.0) / np.float32(out_scale)
     q = _rne((s * inv).astype(np.float32)) + np.float32(out_zp)

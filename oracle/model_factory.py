@@ -6,5 +6,6 @@ functions so that every tier sees the same seeded models.
 """
 from ievm_b200.synthetic import *  # noqa: F401,F403
 from ievm_b200.synthetic import (DEFAULT_CFG_WIDTHS, NUM_CLASSES, PRUNED_WIDTHS, UNPRUNED_WIDTHS,  # noqa: F401
-                                 calibration_batches, cast_fp16, make_student, make_teacher,
+                                 calibration_batches, cast_fp16, make_student, make_teacher, minmax_qconfig_mapping,
+                                 prepare_minmax, static_quantize_minmax,
                                  static_quantize_fbgemm, synthetic_images)
