@@ -136,25 +136,37 @@ int ievm_debug_resize(ievm_handle* h, const uint8_t* x_dev, int n, uint8_t* out_
 
 /* calibration statistics on the device.  An FP16 engine built from the observer-instrumented float
  * model (ievm_b200.netdesc.from_prepared: residual adds as IEVM_OP_ADD_RELU layers) with options keep_tensors = 1 and
- * observe = 1 records, per ievm_observe call, what a min/max-family observer (MinMaxObserver,
- * MovingAverageMinMaxObserver: quantization/main.py:196-207) keeps of a batch -- the pair torch.aminmax(x) -- for
- * every observation point of the LAST forward, on the caller's stream, without synchronising:
+ * observe = 1 | 2 records, per ievm_observe call, what the reference's observers keep of a batch, for every observation
+ * point of the LAST forward, on the caller's stream, without synchronising (two or three launches in all):
  *   point 0              the network input; x_f32 (device f32 [n][c][h][w], the un-rounded batch) when given, else the
  *                        f16 buffer the forward read
  *   point id, 1 <= id < T  tensor `id` over its real channels (T = ievm_num_tensors)
  *   point T              the AdaptiveAvgPool2d output (rounded to f16)
  *   point T + 1          the logits
- * ievm_observer_read synchronises and copies the log as f32 [records][points][2] = {min, max} (NaN = nothing observed)
- * and returns the number of records; ievm_set_option(h, "observe", 1) clears the log.  The host replays the pairs into
- * the prepared module's observers (ievm_b200.calibration.calibrate), after which convert_fx runs unchanged. */
+ * observe = 1: the pair torch.aminmax(x) (MinMaxObserver, MovingAverageMinMaxObserver: quantization/main.py:196-207).
+ * observe = 2: additionally torch.histc(x, 2048, min = lo, max = hi) over the running range [lo, hi] of the point's
+ *   observer after this batch (HistogramObserver.forward; default fbgemm qconfig, quantization/engines.py:103), as exact
+ *   integer counts.  prepare_fx lets several graph nodes share one observer instance; ievm_observer_set_groups maps
+ *   every point to its observer (default: one observer per point) so that the running range is the observer's.
+ * ievm_observer_read synchronises and copies the (min, max) log as f32 [records][points][2] (NaN = nothing observed),
+ * ievm_observer_read_hist the histogram log as u32 [records][points][2048] plus, when range_host is not NULL, the
+ * running (min, max) of all 64 observer groups as f32 [64][2]; both return the number of records.
+ * ievm_observer_capacity is the number of records the log holds (4096, or 64 with histograms); ievm_observer_clear
+ * empties the log but keeps the running ranges (a caller drains a full log and goes on); ievm_set_option(h, "observe",
+ * mode) restarts everything.  The host replays the records into the prepared module's own observers
+ * (ievm_b200.calibration.calibrate), after which convert_fx runs unchanged. */
 int ievm_observer_points(const ievm_handle* h);
+int ievm_observer_capacity(const ievm_handle* h);
+int ievm_observer_set_groups(ievm_handle* h, const int32_t* group_of_point, int points);
 int ievm_observe(ievm_handle* h, const float* x_f32, void* stream);
 int ievm_observer_read(ievm_handle* h, float* minmax_host, int max_records);
+int ievm_observer_read_hist(ievm_handle* h, uint32_t* hist_host, float* range_host, int max_records);
+int ievm_observer_clear(ievm_handle* h);
 
 /* Engine options: "conv_impl" 0 = tcgen05 tensor-core kernels (default), 1 = direct CUDA-core
  * cross-check kernels (tests only); "use_graph" 1 = replay forward() from a CUDA graph cached per
  * (n, x, logits) triple; "keep_tensors" 1 = one buffer per tensor (parity hooks); "profile" 1 =
- * per-launch event timing (see ievm_profile_read); "observe" 1 = (re)start the calibration observer log (F16 engines). */
+ * per-launch event timing (see ievm_profile_read); "observe" 1 | 2 = (re)start the calibration observer log (F16 engines; 2 = with histograms), 0 = off. */
 int ievm_set_option(ievm_handle* h, const char* name, int value);
 
 /* Introspection used by the benchmark and tests. */

@@ -27,7 +27,8 @@ EXPORTS = [
     "ievm_last_error", "ievm_build_info", "ievm_probe_im2col", "ievm_profile_read", "ievm_probe_patch",
     "ievm_debug_frontend", "ievm_set_input_lut", "ievm_forward_u8", "ievm_forward_u8_host",
     "ievm_count_correct", "ievm_set_resize", "ievm_forward_u8_resize", "ievm_forward_u8_resize_host", "ievm_debug_resize",
-    "ievm_observer_points", "ievm_observe", "ievm_observer_read",
+    "ievm_observer_points", "ievm_observe", "ievm_observer_read", "ievm_observer_capacity", "ievm_observer_set_groups",
+    "ievm_observer_read_hist", "ievm_observer_clear",
 ]
 
 
@@ -141,6 +142,14 @@ def load():
     lib.ievm_observe.restype = C.c_int
     lib.ievm_observer_read.argtypes = [H, C.c_void_p, C.c_int]
     lib.ievm_observer_read.restype = C.c_int
+    lib.ievm_observer_capacity.argtypes = [H]
+    lib.ievm_observer_capacity.restype = C.c_int
+    lib.ievm_observer_set_groups.argtypes = [H, C.c_void_p, C.c_int]
+    lib.ievm_observer_set_groups.restype = C.c_int
+    lib.ievm_observer_read_hist.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int]
+    lib.ievm_observer_read_hist.restype = C.c_int
+    lib.ievm_observer_clear.argtypes = [H]
+    lib.ievm_observer_clear.restype = C.c_int
     for name in ("ievm_forward_i8", "ievm_forward_f16", "ievm_forward_i8_host", "ievm_forward_f16_host",
                  "ievm_set_option", "ievm_num_tensors", "ievm_tensor_shape", "ievm_launches_per_forward",
                  "ievm_debug_read_tensor", "ievm_debug_conv_acc", "ievm_kd_loss"):

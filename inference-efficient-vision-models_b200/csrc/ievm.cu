@@ -199,7 +199,11 @@ struct ievm_handle {
   std::vector<size_t> buffer_bytes;
   std::vector<void*> owned;            // device allocations freed at destroy
   // calibration observers (observe.cuh): per ievm_observe call one record of (min, max) pairs, order-encoded u32
-  uint32_t* obs_log = nullptr;         // [kObsMaxRecords][obs_points()][2]
+  uint32_t* obs_log = nullptr;         // [kObsMaxRecords][points][2]
+  uint32_t* obs_run = nullptr;         // [kObsMaxPoints][2] running (min, max) per observer group
+  uint32_t* obs_hist = nullptr;        // [kObsHistRecords][points][kObsBins] (observe = 2)
+  int obs_group[kObsMaxPoints] = {};   // point -> observer group (ievm_observer_set_groups; default: its own)
+  int obs_mode = 0;                    // 0 off, 1 min/max, 2 min/max + histograms
   int obs_records = 0;
   __half* obs_pooled = nullptr;        // avgpool output of the last forward, [max_batch][head cin]; null = not calibrating
   __half* obs_pooled_alloc = nullptr;
@@ -1686,33 +1690,45 @@ int ievm_set_option(ievm_handle* h, const char* name, int value) {
     return encode_maps(h);
   }
   if (!strcmp(name, "observe")) {
-    // calibration mode (observe.cuh): (re)start the observer log; the head also writes its avgpool output
+    // calibration mode (observe.cuh): 0 = off, 1 = (min, max) per batch, 2 = additionally torch.histc over the running
+    // range (HistogramObserver).  (Re)starts the log and the running ranges; the head also writes its avgpool output.
     if (h->dtype != IEVM_DTYPE_F16) return fail(IEVM_ERR_UNSUPPORTED, "observers run on the FP16 engine (the float forward of PTQ calibration)");
+    if (value < 0 || value > 2) return fail(IEVM_ERR_BAD_ARG, "observe must be 0, 1 or 2");
+    const int points = static_cast<int>(h->tensors.size()) + 2;
+    if (points > kObsMaxPoints) return fail(IEVM_ERR_UNSUPPORTED, "more than %d observation points", kObsMaxPoints);
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
     for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);   // the pooled-output pointer is baked into captured launches
     h->graphs.clear();
     h->obs_records = 0;
+    h->obs_mode = value;
     if (!value) {
       h->obs_pooled = nullptr;
       return IEVM_OK;
     }
+    auto alloc = [&](size_t bytes, void** out) -> int {
+      CUDA_TRY(cudaMalloc(out, std::max<size_t>(bytes, 16)));
+      h->owned.push_back(*out);
+      return IEVM_OK;
+    };
     if (!h->obs_log) {
-      void* p = nullptr;
-      CUDA_TRY(cudaMalloc(&p, static_cast<size_t>(kObsMaxRecords) * (h->tensors.size() + 2) * 2 * sizeof(uint32_t)));
-      h->owned.push_back(p);
-      h->obs_log = static_cast<uint32_t*>(p);
+      if (int rc = alloc(static_cast<size_t>(kObsMaxRecords) * points * 2 * sizeof(uint32_t), reinterpret_cast<void**>(&h->obs_log))) return rc;
+      if (int rc = alloc(static_cast<size_t>(kObsMaxPoints) * 2 * sizeof(uint32_t), reinterpret_cast<void**>(&h->obs_run))) return rc;
+      for (int i = 0; i < kObsMaxPoints; ++i) h->obs_group[i] = i;
     }
-    if (!h->obs_pooled) {
+    if (value == 2 && !h->obs_hist)
+      if (int rc = alloc(static_cast<size_t>(kObsHistRecords) * points * kObsBins * sizeof(uint32_t), reinterpret_cast<void**>(&h->obs_hist))) return rc;
+    if (!h->obs_pooled_alloc) {
       int head_cin = 0;
       for (const LayerPlan& L : h->layers)
         if (L.d.op == IEVM_OP_HEAD) head_cin = L.d.cin;
-      void* p = nullptr;
-      CUDA_TRY(cudaMalloc(&p, std::max<size_t>(static_cast<size_t>(h->max_batch) * head_cin * sizeof(__half), 16)));
-      h->owned.push_back(p);
-      h->obs_pooled_alloc = static_cast<__half*>(p);
+      if (int rc = alloc(static_cast<size_t>(h->max_batch) * head_cin * sizeof(__half), reinterpret_cast<void**>(&h->obs_pooled_alloc))) return rc;
     }
     h->obs_pooled = h->obs_pooled_alloc;
+    observe_init_kernel<<<1, 256>>>(h->obs_run, kObsMaxPoints);
+    CUDA_TRY(cudaGetLastError());
+    if (h->obs_hist) CUDA_TRY(cudaMemset(h->obs_hist, 0, static_cast<size_t>(kObsHistRecords) * points * kObsBins * sizeof(uint32_t)));
+    CUDA_TRY(cudaDeviceSynchronize());
     return IEVM_OK;
   }
   return fail(IEVM_ERR_BAD_ARG, "unknown option '%s'", name);
@@ -1720,12 +1736,30 @@ int ievm_set_option(ievm_handle* h, const char* name, int value) {
 
 int ievm_observer_points(const ievm_handle* h) { return h ? static_cast<int>(h->tensors.size()) + 2 : 0; }
 
+int ievm_observer_capacity(const ievm_handle* h) {
+  if (!h || !h->obs_mode) return 0;
+  return h->obs_mode == 2 ? kObsHistRecords : kObsMaxRecords;
+}
+
+int ievm_observer_set_groups(ievm_handle* h, const int32_t* group_of_point, int points) {
+  if (!h || !group_of_point) return fail(IEVM_ERR_BAD_ARG, "null argument");
+  if (!h->obs_log) return fail(IEVM_ERR_BAD_ARG, "ievm_observer_set_groups: set option observe first");
+  if (points != static_cast<int>(h->tensors.size()) + 2) return fail(IEVM_ERR_BAD_ARG, "expected %zu points", h->tensors.size() + 2);
+  if (h->obs_records != 0) return fail(IEVM_ERR_BAD_ARG, "ievm_observer_set_groups: the log is not empty");
+  for (int i = 0; i < points; ++i) {
+    if (group_of_point[i] < 0 || group_of_point[i] >= kObsMaxPoints) return fail(IEVM_ERR_BAD_ARG, "group %d out of range", group_of_point[i]);
+    h->obs_group[i] = group_of_point[i];
+  }
+  return IEVM_OK;
+}
+
 int ievm_observe(ievm_handle* h, const float* x_f32, void* stream) {
   if (!h) return fail(IEVM_ERR_BAD_ARG, "null argument");
-  if (!h->obs_log || !h->obs_pooled) return fail(IEVM_ERR_BAD_ARG, "ievm_observe: set option observe=1 first");
+  if (!h->obs_mode || !h->obs_log || !h->obs_pooled) return fail(IEVM_ERR_BAD_ARG, "ievm_observe: set option observe first");
   if (!h->keep_tensors) return fail(IEVM_ERR_BAD_ARG, "ievm_observe: needs keep_tensors=1 (every tensor in its own buffer)");
   if (h->last_n <= 0 || !h->last_x || !h->last_logits) return fail(IEVM_ERR_BAD_ARG, "ievm_observe: no forward to observe");
-  if (h->obs_records >= kObsMaxRecords) return fail(IEVM_ERR_OOM, "ievm_observe: observer log full (%d records)", kObsMaxRecords);
+  const int cap = h->obs_mode == 2 ? kObsHistRecords : kObsMaxRecords;
+  if (h->obs_records >= cap) return fail(IEVM_ERR_OOM, "ievm_observe: observer log full (%d records): read and clear it", cap);
   const void* x0 = x_f32 ? static_cast<const void*>(x_f32) : h->last_x;
   if (reinterpret_cast<uintptr_t>(x0) % 16 != 0 || reinterpret_cast<uintptr_t>(h->last_logits) % 16 != 0)
     return fail(IEVM_ERR_BAD_ARG, "ievm_observe: input / logits buffers must be 16-byte aligned");
@@ -1734,31 +1768,40 @@ int ievm_observe(ievm_handle* h, const float* x_f32, void* stream) {
   const int T = static_cast<int>(h->tensors.size());
   const int points = T + 2;
   const int n = h->last_n;
-  uint32_t* rec = h->obs_log + static_cast<size_t>(h->obs_records) * points * 2;
-  observe_init_kernel<<<(2 * points + 255) / 256, 256, 0, s>>>(rec, points);
-  // streaming reductions: enough blocks to keep every SM's memory pipeline busy, grid-stride beyond that
-  auto blocks = [&](long long count, int lanes) {
-    const long long want = (count / lanes + 255) / 256;
-    return static_cast<unsigned>(std::min<long long>(std::max<long long>(want, 1), static_cast<long long>(h->num_sms) * 8));
-  };
-  const long long in_count = static_cast<long long>(n) * h->in_c * h->in_h * h->in_w;
-  if (x_f32) observe_minmax_kernel<float><<<blocks(in_count, 4), 256, 0, s>>>(x_f32, in_count, 1, 1, rec);
-  else observe_minmax_kernel<__half><<<blocks(in_count, 8), 256, 0, s>>>(static_cast<const __half*>(h->last_x), in_count, 1, 1, rec);
-  for (int id = 1; id < T; ++id) {
-    const TensorInfo& t = h->tensors[id];
-    if (t.buffer < 0 || t.elem != 2) continue;      // stays "nothing observed" (NaN)
-    const long long count = static_cast<long long>(n) * t.h * t.w * t.pitch;
-    observe_minmax_kernel<__half><<<blocks(count, 8), 256, 0, s>>>(static_cast<const __half*>(tensor_ptr(h, id)), count, t.pitch,
-                                                                   t.c, rec + 2 * id);
-  }
   int head_cin = 0;
   for (const LayerPlan& L : h->layers)
     if (L.d.op == IEVM_OP_HEAD) head_cin = L.d.cin;
-  const long long pooled_count = static_cast<long long>(n) * head_cin;
-  observe_minmax_kernel<__half><<<blocks(pooled_count, 8), 256, 0, s>>>(h->obs_pooled, pooled_count, 1, 1, rec + 2 * T);
-  const long long logit_count = static_cast<long long>(n) * h->classes;
-  observe_minmax_kernel<__half><<<blocks(logit_count, 8), 256, 0, s>>>(static_cast<const __half*>(h->last_logits), logit_count, 1, 1,
-                                                                       rec + 2 * (T + 1));
+  // one table for all points; every point gets blocks in proportion to its size (a thread streams ~4 vectors)
+  ObsTable tab;
+  memset(&tab, 0, sizeof(tab));
+  int nblocks = 0;
+  auto add = [&](const void* data, long long count, int pitch, int c_real, bool f32) {
+    ObsPoint& P = tab.pt[tab.n];
+    P.data = data;
+    P.count = data ? count : 0;
+    P.pitch = pitch;
+    P.c_real = c_real;
+    P.is_f32 = f32 ? 1 : 0;
+    P.group = h->obs_group[tab.n];
+    P.first_block = nblocks;
+    const long long nvec = P.count / (f32 ? 4 : 8);
+    nblocks += static_cast<int>(std::min<long long>(std::max<long long>((nvec + 1023) / 1024, 1), 4LL * h->num_sms));
+    ++tab.n;
+  };
+  add(x0, static_cast<long long>(n) * h->in_c * h->in_h * h->in_w, 1, 1, x_f32 != nullptr);
+  for (int id = 1; id < T; ++id) {
+    const TensorInfo& t = h->tensors[id];
+    const bool ok = t.buffer >= 0 && t.elem == 2;
+    add(ok ? tensor_ptr(h, id) : nullptr, static_cast<long long>(n) * t.h * t.w * t.pitch, t.pitch, t.c, false);   // null: "nothing observed"
+  }
+  add(h->obs_pooled, static_cast<long long>(n) * head_cin, 1, 1, false);
+  add(h->last_logits, static_cast<long long>(n) * h->classes, 1, 1, false);
+  tab.total_blocks = nblocks;
+  uint32_t* rec = h->obs_log + static_cast<size_t>(h->obs_records) * points * 2;
+  observe_init_kernel<<<(2 * points + 255) / 256, 256, 0, s>>>(rec, points);
+  observe_minmax_multi_kernel<<<nblocks, 256, 0, s>>>(tab, rec, h->obs_run);
+  if (h->obs_mode == 2)
+    observe_hist_multi_kernel<<<nblocks, 256, 0, s>>>(tab, h->obs_run, h->obs_hist + static_cast<size_t>(h->obs_records) * points * kObsBins);
   CUDA_TRY(cudaGetLastError());
   ++h->obs_records;
   return IEVM_OK;
@@ -1775,6 +1818,34 @@ int ievm_observer_read(ievm_handle* h, float* minmax_host, int max_records) {
   CUDA_TRY(cudaMemcpy(enc.data(), h->obs_log, words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < words; ++i) minmax_host[i] = obs_decode(enc[i]);
   return nrec;
+}
+
+int ievm_observer_read_hist(ievm_handle* h, uint32_t* hist_host, float* range_host, int max_records) {
+  if (!h || !hist_host || max_records < 0) return fail(IEVM_ERR_BAD_ARG, "ievm_observer_read_hist: bad arguments");
+  if (h->obs_mode != 2 || !h->obs_hist) return fail(IEVM_ERR_BAD_ARG, "ievm_observer_read_hist: set option observe=2 first");
+  const int nrec = std::min(h->obs_records, max_records);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (int rc = check_stuck(h, cudaDeviceSynchronize(), "observer_read_hist sync")) return rc;
+  if (range_host) {       // running (min, max) per observer group, as of the last record
+    uint32_t enc[2 * kObsMaxPoints];
+    CUDA_TRY(cudaMemcpy(enc, h->obs_run, sizeof(enc), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 2 * kObsMaxPoints; ++i) range_host[i] = obs_decode(enc[i]);
+  }
+  if (nrec == 0) return 0;
+  const size_t words = static_cast<size_t>(nrec) * (h->tensors.size() + 2) * kObsBins;
+  CUDA_TRY(cudaMemcpy(hist_host, h->obs_hist, words * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return nrec;
+}
+
+int ievm_observer_clear(ievm_handle* h) {
+  if (!h) return fail(IEVM_ERR_BAD_ARG, "null argument");
+  if (!h->obs_mode) return fail(IEVM_ERR_BAD_ARG, "ievm_observer_clear: set option observe first");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (h->obs_hist && h->obs_records > 0)
+    CUDA_TRY(cudaMemset(h->obs_hist, 0, static_cast<size_t>(h->obs_records) * (h->tensors.size() + 2) * kObsBins * sizeof(uint32_t)));
+  h->obs_records = 0;
+  return IEVM_OK;
 }
 
 int ievm_num_tensors(const ievm_handle* h) { return h ? static_cast<int>(h->tensors.size()) : 0; }

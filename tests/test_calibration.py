@@ -34,9 +34,10 @@ def interpret(net, x):
     raise AssertionError("no head")
 
 
-def recorded_stats(prepared, plan, num_tensors, batches):
-    """What the device log would hold if activations were the reference's own fp32 ones: aminmax of every observer call
-    of the reference's CPU calibration forward, batch by batch, filed under the plan's observation points."""
+def recorded_stats(prepared, plan, num_tensors, batches, with_hist=False):
+    """What the device logs would hold if activations were the reference's own fp32 ones: aminmax (and, for histogram
+    observers, torch.histc over the running range of the point's observer group) of every observer call of the
+    reference's CPU calibration forward, batch by batch, filed under the plan's observation points."""
     probe = copy.deepcopy(prepared)
     calls = []
     seen = set()
@@ -44,16 +45,26 @@ def recorded_stats(prepared, plan, num_tensors, batches):
         obs = probe.get_submodule(name)
         if id(obs) not in seen:                         # shared instances: one hook, fires once per call
             seen.add(id(obs))
-            obs.register_forward_pre_hook(lambda m, inp: calls.append(tuple(float(v) for v in torch.aminmax(inp[0]))))
+            obs.register_forward_pre_hook(lambda m, inp: calls.append(inp[0].detach().clone()))
+    groups = calibration.point_groups(prepared, plan, num_tensors)
     stats = np.full((len(batches), num_tensors + 2, 2), np.nan, np.float32)
+    hists = np.zeros((len(batches), num_tensors + 2, calibration.HIST_BINS), np.uint32)
+    run = {}
     with torch.no_grad():
         for r, (images, _) in enumerate(batches):
             calls.clear()
             probe(images)
             assert len(calls) == len(plan)
-            for (_, point), mm in zip(plan, calls):
-                stats[r, calibration.point_index(point, num_tensors)] = mm
-    return stats
+            cols = [calibration.point_index(point, num_tensors) for _, point in plan]
+            for c, x in zip(cols, calls):
+                stats[r, c] = [float(v) for v in torch.aminmax(x)]
+                lo, hi = run.get(int(groups[c]), (np.inf, -np.inf))
+                run[int(groups[c])] = (min(lo, stats[r, c, 0]), max(hi, stats[r, c, 1]))
+            if with_hist:                                # the device bins after the whole batch's (min, max) pass
+                for c, x in zip(cols, calls):
+                    lo, hi = run[int(groups[c])]
+                    hists[r, c] = torch.histc(x.float(), calibration.HIST_BINS, min=float(lo), max=float(hi)).numpy().astype(np.uint32)
+    return (stats, hists) if with_hist else stats
 
 
 def test_prepared_graph_flattens_to_an_unfused_fp16_net():
@@ -129,11 +140,68 @@ def test_interpreter_statistics_match_the_plan_points():
         assert np.allclose(got, want, rtol=2e-2, atol=2e-2), (point, got, want)
 
 
-def test_histogram_observers_are_refused_not_approximated():
-    from torch.ao.quantization import get_default_qconfig_mapping
-    prepared = mf.prepare_minmax(mf.make_student((16, 24, 32, 40)), get_default_qconfig_mapping("fbgemm"))   # engines.py:103
+def test_histc_restatement_equals_torch_histc():
+    """oracle/observers.py (the formula the CUDA histogram kernel implements) against torch.histc itself."""
+    from oracle.observers import histc_counts
+    g = torch.Generator().manual_seed(0)
+    for trial in range(24):
+        n = int(torch.randint(1000, 200000, (1,), generator=g))
+        x = torch.randn(n, generator=g) * float(torch.rand(1, generator=g) * 5 + 0.01)
+        if trial % 2:
+            x = torch.relu(x)
+        if trial % 3 == 0:
+            x = x.half().float()
+        lo = float(x.min() - (torch.rand(1, generator=g) if trial % 4 == 0 else 0))
+        hi = float(x.max() + (torch.rand(1, generator=g) * 2 if trial % 5 == 0 else 0))
+        ref = torch.histc(x, 2048, min=lo, max=hi).numpy().astype(np.int64)
+        assert np.array_equal(histc_counts(x.numpy(), lo, hi), ref), trial
+    x = torch.full((100,), 3.0)
+    assert np.array_equal(histc_counts(x.numpy(), 3.0, 3.0, 8), torch.histc(x, 8, min=3.0, max=3.0).numpy().astype(np.int64))
+
+
+def test_replaying_histograms_equals_the_reference_fbgemm_calibration():
+    """The default fbgemm qconfig of QuantizationEngine.static_quantize (quantization/engines.py:103: HistogramObserver,
+    reduce_range): replaying per-batch (min, max) and histc counts over the observers' running ranges leaves the prepared
+    module in exactly the state the reference's CPU loop (engines.py:123-133) leaves it in -- identical histograms,
+    identical converted network."""
+    from torch.ao.quantization import get_default_qconfig_mapping, quantize_fx
+    from torch.ao.quantization.observer import HistogramObserver
+    m = mf.make_student((16, 24, 32, 40))
+    gen = torch.Generator().manual_seed(5)
+    scales = (1.0, 2.5, 0.5, 2.5)                       # widening, then inside the running range
+    batches = [(torch.randn(3, 3, 64, 64, generator=gen) * sc, torch.zeros(3, dtype=torch.long)) for sc in scales]
+    ref = mf.prepare_minmax(m, get_default_qconfig_mapping("fbgemm"))
+    ours = copy.deepcopy(ref)
+    with torch.no_grad():
+        for images, _ in batches:
+            ref(images)
+    net, plan = ievm_b200.from_prepared(ours, in_hw=(64, 64))
+    assert calibration.observer_mode(ours, plan) == 2
+    num_tensors = 1 + max(L.out_tensor for L in net.layers)
+    groups = calibration.point_groups(ours, plan, num_tensors)
+    assert groups[2] == 1 and groups[num_tensors] == groups[num_tensors - 1] == num_tensors - 1      # the shared instances
+    stats, hists = recorded_stats(ours, plan, num_tensors, batches, with_hist=True)
+    with pytest.raises(ValueError, match="histogram log"):
+        ievm_b200.replay_observers(copy.deepcopy(ours), plan, stats, num_tensors)
+    ievm_b200.replay_observers(ours, plan, stats, num_tensors, hists)
+    for name, _ in plan:
+        a, b = ref.get_submodule(name), ours.get_submodule(name)
+        assert isinstance(a, HistogramObserver)
+        assert torch.equal(a.min_val, b.min_val) and torch.equal(a.max_val, b.max_val), name
+        assert torch.equal(a.histogram, b.histogram), name
+    qa = ievm_b200.from_converted(quantize_fx.convert_fx(ref), in_hw=(64, 64))
+    qb = ievm_b200.from_converted(quantize_fx.convert_fx(ours), in_hw=(64, 64))
+    for la, lb in zip(qa.layers, qb.layers):
+        assert (la.out_scale, la.out_zp, la.add_scale, la.add_zp) == (lb.out_scale, lb.out_zp, lb.add_scale, lb.add_zp), la.name
+
+
+def test_other_observer_classes_are_refused_not_approximated():
+    from torch.ao.quantization import QConfig, QConfigMapping
+    from torch.ao.quantization.observer import PerChannelMinMaxObserver, default_weight_observer
+    qc = QConfig(activation=PerChannelMinMaxObserver.with_args(dtype=torch.quint8, ch_axis=1), weight=default_weight_observer)
+    prepared = mf.prepare_minmax(mf.make_student((16, 24, 32, 40)), QConfigMapping().set_global(qc))
     _, plan = ievm_b200.from_prepared(prepared)
-    with pytest.raises(NotImplementedError, match="histogram"):
+    with pytest.raises(NotImplementedError, match="PerChannelMinMaxObserver"):
         calibration.check_observers(prepared, plan)
 
 

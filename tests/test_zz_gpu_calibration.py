@@ -46,40 +46,48 @@ def test_main_py_qconfig_flavour_is_bit_exact_on_the_engine():
     eng.close()
 
 
-def test_device_observers_equal_torch_aminmax_of_the_engine_tensors():
+def test_device_observers_equal_torch_aminmax_and_histc_of_the_engine_tensors():
     import ievm_b200
     from ievm_b200 import calibration
     from ievm_b200.netdesc import OP_ADD_RELU, POINT_LOGITS, POINT_POOLED
     prepared = _prepared()
     net, plan = ievm_b200.from_prepared(prepared)
-    eng = ievm_b200.CalibrationEngine(net, device=0, max_batch=8)
-    assert eng.num_points == eng.num_tensors + 2 == len(net.tensor_names) + 2
-    stats_all = []
-    for n, seed in ((5, 3), (8, 4)):                                    # ragged, then full batch
-        x32 = (mf.synthetic_images(n, seed=seed) * 1.7).cuda()
+    T = 1 + max(L.out_tensor for L in net.layers)
+    groups = calibration.point_groups(prepared, plan, T)
+    assert groups[2] == 1 and groups[T] == T - 1                        # (conv1, maxpool), (last relu, avgpool) share
+    eng = ievm_b200.CalibrationEngine(net, mode=2, groups=groups, device=0, max_batch=8)
+    assert eng.num_points == eng.num_tensors + 2 == T + 2 and eng.capacity == 64
+    run = {}
+    for r, (n, seed, gain) in enumerate(((5, 3, 1.7), (8, 4, 0.6), (3, 6, 2.4))):   # ragged; inside the range; widening
+        x32 = (mf.synthetic_images(n, seed=seed) * gain).cuda()
         logits = eng(x32.half())
         eng.observe(x32)
         torch.cuda.synchronize()
-        stats = eng.read_observations()
-        assert stats.shape == (len(stats_all) + 1, eng.num_points, 2)
-        rec = stats[-1]
-        stats_all.append(rec)
-        assert rec[0, 0] == float(x32.min()) and rec[0, 1] == float(x32.max())          # un-rounded f32 input
-        lg = logits.float().cpu().numpy()
-        assert rec[eng.num_tensors + 1, 0] == lg.min() and rec[eng.num_tensors + 1, 1] == lg.max()
-        tensors = {}
-        for tid in range(1, eng.num_tensors):
+        stats, hists = eng.read_observations(), eng.read_histograms()
+        assert stats.shape == (r + 1, eng.num_points, 2) and hists.shape == (r + 1, eng.num_points, 2048)
+        rec, hist = stats[-1], hists[-1]
+        lg = logits.float().cpu()
+        tensors = {0: x32.cpu(), T + 1: lg}
+        for tid in range(1, T):
             t = eng.read_tensor(tid)                                     # NCHW over the real channels, f16
-            tensors[tid] = t
             assert t.shape[0] == n
-            assert rec[tid, 0] == np.float32(t.min()) and rec[tid, 1] == np.float32(t.max()), (tid, net.tensor_names[tid])
+            tensors[tid] = torch.from_numpy(t.astype(np.float32))
+        for c, t in tensors.items():                                     # (min, max): exact
+            assert rec[c, 0] == float(t.min()) and rec[c, 1] == float(t.max()), (c, net.tensor_names.get(c))
+        for c in range(eng.num_points):                                  # the running range of every observer group
+            lo, hi = run.get(int(groups[c]), (np.inf, -np.inf))
+            run[int(groups[c])] = (min(lo, float(rec[c, 0])), max(hi, float(rec[c, 1])))
+        for c, t in tensors.items():                                     # histc over that range: exact counts
+            lo, hi = run[int(groups[c])]
+            want = torch.histc(t, 2048, min=lo, max=hi).numpy().astype(np.int64)
+            assert np.array_equal(hist[c].astype(np.int64), want), (r, c, net.tensor_names.get(c))
+        assert int(hist[T].sum()) == n * net.layers[-1].cin              # avgpool output: every value binned once
         for L in net.layers:                                             # the un-fused residual add: one rounding
             if L.op == OP_ADD_RELU:
-                want = np.maximum(tensors[L.in_tensor].astype(np.float32) + tensors[L.res_tensor].astype(np.float32), 0)
-                assert np.array_equal(tensors[L.out_tensor], want.astype(np.float16)), L.name
-        last = tensors[net.layers[-1].in_tensor].astype(np.float32)
-        pooled = last.mean(axis=(2, 3))
-        assert np.allclose(rec[eng.num_tensors], [pooled.min(), pooled.max()], rtol=2e-3, atol=1e-3)
+                want = torch.relu(tensors[L.in_tensor] + tensors[L.res_tensor]).half().float()
+                assert torch.equal(tensors[L.out_tensor], want), L.name
+        pooled = tensors[net.layers[-1].in_tensor].mean(dim=(2, 3))
+        assert np.allclose(rec[T], [float(pooled.min()), float(pooled.max())], rtol=2e-3, atol=1e-3)
     # without the f32 batch the f16 input is observed; the log restarts with the option
     eng.reset_observations()
     x16 = mf.synthetic_images(4, seed=5).half().cuda()
@@ -87,13 +95,17 @@ def test_device_observers_equal_torch_aminmax_of_the_engine_tensors():
     eng.observe()
     rec = eng.read_observations()
     assert rec.shape[0] == 1 and rec[0, 0, 0] == float(x16.min()) and rec[0, 0, 1] == float(x16.max())
+    # a full log is drained to the host transparently
+    for _ in range(eng.capacity + 3):
+        eng.observe()
+    more = eng.read_observations()
+    assert more.shape[0] == eng.capacity + 4 and np.array_equal(more[-1], more[0])
     # the un-fused calibration net computes the same function as the fused FP16 engine (one extra rounding per block)
     fused = ievm_b200.B200HalfResNet.from_half_module(mf.cast_fp16(mf.make_student(mf.PRUNED_WIDTHS)), device=0, max_batch=8)
     a, b = eng(x16).float().cpu().numpy(), fused(x16).float().cpu().numpy()
     assert (np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1.0)).max() < 1e-2
     fused.close()
     eng.close()
-    # point bookkeeping used by the replay
     assert calibration.point_index(POINT_POOLED, 31) == 31 and calibration.point_index(POINT_LOGITS, 31) == 32
 
 
@@ -134,6 +146,45 @@ def test_gpu_calibration_matches_the_reference_cpu_calibration():
     agree = float((y_ref.argmax(1) == y_ours.argmax(1)).mean())
     print(f"top-1 agreement GPU-calibrated vs CPU-calibrated INT8 network: {agree:.4f}; "
           f"max |logit difference| {np.abs(y_ref - y_ours).max():.3f}")
+    assert agree >= TOP1_AGREE
+    e_ref.close()
+    e_ours.close()
+
+
+def test_gpu_histogram_calibration_matches_the_reference_fbgemm_calibration():
+    """The default flavour of QuantizationEngine.static_quantize (quantization/engines.py:95-121: default fbgemm qconfig,
+    HistogramObserver): calibrate() in place of _calibrate (engines.py:123-133), convert_fx as the reference."""
+    import ievm_b200
+    from torch.ao.quantization import get_default_qconfig_mapping, quantize_fx
+    calib = mf.calibration_batches(n_batches=3, batch=8, seed=1)
+    ref = mf.prepare_minmax(mf.make_student(mf.PRUNED_WIDTHS), get_default_qconfig_mapping("fbgemm"))
+    ours = copy.deepcopy(ref)
+    with torch.no_grad():
+        for images, _ in calib:
+            ref(images)
+    ievm_b200.calibrate(ours, calib, device=0)
+    _, plan = ievm_b200.from_prepared(ours)
+    x0 = ours.get_submodule(plan[0][0]), ref.get_submodule(plan[0][0])       # the f32 input: exact state
+    assert torch.equal(x0[0].min_val, x0[1].min_val) and torch.equal(x0[0].histogram, x0[1].histogram)
+    for name, _ in plan:
+        a, b = ref.get_submodule(name), ours.get_submodule(name)
+        assert float(a.histogram.sum()) == float(b.histogram.sum()), name    # every element binned
+    na = ievm_b200.from_converted(quantize_fx.convert_fx(ref))
+    nb = ievm_b200.from_converted(quantize_fx.convert_fx(ours))
+    assert (na.in_scale, na.in_zp) == (nb.in_scale, nb.in_zp)
+    worst = 0.0
+    for la, lb in zip(na.layers, nb.layers):
+        assert np.array_equal(la.weight, lb.weight)
+        worst = max(worst, abs(lb.out_scale / la.out_scale - 1), abs(lb.add_scale / la.add_scale - 1) if la.res_tensor >= 0 else 0)
+        assert abs(lb.out_zp - la.out_zp) <= 3, la.name
+    print(f"histogram flavour: worst relative scale deviation {worst:.2e}")
+    assert worst < 3e-2
+    e_ref = ievm_b200.B200QuantizedResNet(na, device=0, max_batch=128)
+    e_ours = ievm_b200.B200QuantizedResNet(nb, device=0, max_batch=128)
+    x = mf.synthetic_images(128, seed=21).cuda()
+    y_ref, y_ours = e_ref(x).cpu().numpy(), e_ours(x).cpu().numpy()
+    agree = float((y_ref.argmax(1) == y_ours.argmax(1)).mean())
+    print(f"histogram flavour: top-1 agreement GPU-calibrated vs CPU-calibrated INT8 network {agree:.4f}")
     assert agree >= TOP1_AGREE
     e_ref.close()
     e_ours.close()
