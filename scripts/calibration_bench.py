@@ -37,22 +37,48 @@ gpu_s = time.perf_counter() - t0
 
 # the device part alone: batches resident on the GPU, one engine, events around forwards + observer passes
 net, plan = ievm_b200.from_prepared(ours)
-eng = ievm_b200.CalibrationEngine(net, device=0, max_batch=args.batch)
+from ievm_b200 import calibration
+groups = calibration.point_groups(ours, plan, 1 + max(L.out_tensor for L in net.layers))
 dev_batches = [x.cuda() for x, _ in calib]
 halves = [x.half() for x in dev_batches]
-for x32, x16 in zip(dev_batches[:2], halves[:2]):
-    eng(x16); eng.observe(x32)
-eng.reset_observations()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-torch.cuda.synchronize()
-e0.record()
-for x32, x16 in zip(dev_batches, halves):
-    out = eng(x16)
-    eng.observe(x32)
-e1.record()
-torch.cuda.synchronize()
-dev_ms = e0.elapsed_time(e1)
-eng.close()
+
+
+def device_only(mode):
+    eng = ievm_b200.CalibrationEngine(net, mode=mode, groups=groups, device=0, max_batch=args.batch)
+    for x32, x16 in zip(dev_batches[:2], halves[:2]):
+        eng(x16); eng.observe(x32)
+    eng.reset_observations()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    e[0].record()
+    for x32, x16 in zip(dev_batches, halves):
+        out = eng(x16)
+        eng.observe(x32)
+    e[1].record()
+    for x32, x16 in zip(dev_batches, halves):          # the forwards alone, for the share of the observer passes
+        out = eng(x16)
+    e[2].record()
+    torch.cuda.synchronize()
+    total, fwd = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+    # bytes one observer pass reads: every observed tensor once (f32 input, f16 tensors over their channel pitch)
+    nbytes = 0
+    for x32 in dev_batches:
+        n = x32.shape[0]
+        nbytes += x32.numel() * 4 + n * (net.layers[-1].cin + net.num_classes) * 2
+        for tid in range(1, eng.num_tensors):
+            _, h, w, _, pitch, elem = eng.tensor_shape(tid)
+            nbytes += n * h * w * pitch * elem
+    eng.close()
+    passes = 1 if mode == 1 else 2
+    return {"ms": total, "forward_ms": fwd, "observer_ms": total - fwd, "images_per_s": args.images / total * 1e3,
+            "observer_bytes": nbytes * passes, "observer_gbs": nbytes * passes / max(total - fwd, 1e-6) / 1e6,
+            "what": "forwards + observer passes (%s), batches resident in HBM, CUDA events" %
+                    ("min/max" if mode == 1 else "min/max + histograms")}
+
+
+dev1 = device_only(1)
+dev2 = device_only(2)
+dev_ms = dev1["ms"]
 
 worst = 0.0
 for name, _ in plan:
@@ -66,8 +92,7 @@ line = {"workload": "PTQ calibration, pruned ResNet-18 [57,115,230,460], main.py
         "b200_calibrate": {"seconds": gpu_s, "images_per_s": args.images / gpu_s,
                            "what": "ievm_b200.calibrate from pinned host batches: engine build, H2D, fp16 forwards (un-fused "
                                    "adds, one buffer per tensor), device min/max passes, host replay"},
-        "b200_device_only": {"ms": dev_ms, "images_per_s": args.images / dev_ms * 1e3,
-                             "what": "forwards + observer passes, batches resident in HBM, CUDA events"},
+        "b200_device_only": dev1, "b200_device_only_histograms": dev2,
         "observer_state_worst_relative_deviation": worst, "records": int(stats.shape[0]), "points": int(stats.shape[1])}
 print(json.dumps(line))
 if args.out:

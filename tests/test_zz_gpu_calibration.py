@@ -168,7 +168,8 @@ def test_gpu_histogram_calibration_matches_the_reference_fbgemm_calibration():
     assert torch.equal(x0[0].min_val, x0[1].min_val) and torch.equal(x0[0].histogram, x0[1].histogram)
     for name, _ in plan:
         a, b = ref.get_submodule(name), ours.get_submodule(name)
-        assert float(a.histogram.sum()) == float(b.histogram.sum()), name    # every element binned
+        # every element binned (float32 histograms: sums above 2^24 and the up-scaling of _combine_histograms round)
+        assert abs(float(a.histogram.sum()) / float(b.histogram.sum()) - 1) < 1e-5, name
     na = ievm_b200.from_converted(quantize_fx.convert_fx(ref))
     nb = ievm_b200.from_converted(quantize_fx.convert_fx(ours))
     assert (na.in_scale, na.in_zp) == (nb.in_scale, nb.in_zp)
