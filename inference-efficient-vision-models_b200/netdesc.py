@@ -68,6 +68,53 @@ class NetSpec:
     layers: List[LayerSpec] = field(default_factory=list)
     tensor_names: Dict[int, str] = field(default_factory=dict)   # tensor id -> reference graph node name
 
+    # ---- engine blob ("an export of our packed/padded weight blob for fast start") -------------
+    _SCALARS = ("op", "name", "in_tensor", "out_tensor", "res_tensor", "cin", "cout", "ksize", "stride", "pad", "relu",
+                "in_scale", "in_zp", "out_scale", "out_zp", "res_scale", "res_zp", "add_scale", "add_zp")
+
+    def save(self, path) -> None:
+        """Write the flattened network as one ``.npz`` (no pickle): a JSON header with every scalar field plus the
+        weight / bias / scale arrays.  ``NetSpec.load`` + the engine constructor then start without torch.ao, FX or
+        the reference's module classes.  float32 scalars are stored as their exact decimal repr (round-trip safe)."""
+        import json
+        head = {"format": "ievm-netspec-1", "dtype": self.dtype, "in_c": self.in_c, "in_h": self.in_h, "in_w": self.in_w,
+                "num_classes": self.num_classes, "in_scale": repr(float(self.in_scale)), "in_zp": int(self.in_zp),
+                "tensor_names": {str(k): v for k, v in self.tensor_names.items()}, "layers": []}
+        arrays = {}
+        for i, L in enumerate(self.layers):
+            row = {}
+            for f in self._SCALARS:
+                v = getattr(L, f)
+                row[f] = repr(float(v)) if isinstance(v, float) else (bool(v) if isinstance(v, (bool, np.bool_)) else
+                                                                       (v if isinstance(v, str) else int(v)))
+            head["layers"].append(row)
+            for f in ("weight", "bias", "w_scale"):
+                a = getattr(L, f)
+                if a is not None:
+                    arrays[f"L{i}.{f}"] = np.ascontiguousarray(a)
+        arrays["header"] = np.frombuffer(json.dumps(head).encode(), dtype=np.uint8)
+        with open(path, "wb") as fh:
+            np.savez(fh, **arrays)
+
+    @classmethod
+    def load(cls, path) -> "NetSpec":
+        import json
+        with np.load(path, allow_pickle=False) as z:
+            head = json.loads(bytes(z["header"]).decode())
+            if head.get("format") != "ievm-netspec-1":
+                raise ValueError(f"{path}: not an ievm NetSpec blob")
+            net = cls(dtype=int(head["dtype"]), in_c=int(head["in_c"]), in_h=int(head["in_h"]), in_w=int(head["in_w"]),
+                      num_classes=int(head["num_classes"]), in_scale=float(head["in_scale"]), in_zp=int(head["in_zp"]),
+                      tensor_names={int(k): v for k, v in head["tensor_names"].items()})
+            for i, row in enumerate(head["layers"]):
+                kw = {f: (float(v) if f.endswith("_scale") else v) for f, v in row.items()}
+                for f in ("weight", "bias", "w_scale"):
+                    key = f"L{i}.{f}"
+                    kw[f] = np.array(z[key]) if key in z.files else None
+                net.layers.append(LayerSpec(**kw))
+        _check_order(net)
+        return net
+
     def conv_macs_per_image(self) -> int:
         """Algorithmic MACs per image on real (un-padded) channels."""
         h, w = self.in_h, self.in_w

@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from .engine import B200HalfResNet, B200QuantizedResNet, _B200Engine
-from .netdesc import DTYPE_F16
+from .netdesc import DTYPE_F16, NetSpec
 
 
 def _widths_from_float_state_dict(sd):
@@ -49,11 +49,18 @@ def load_engine(path_or_obj, max_batch: int = 256, device: Optional[int] = None)
     * float / half ResNet state dict                            -> ``B200HalfResNet`` (FP16 cast, engines.py:84-93)
     * whole pickled ``nn.Module`` (``pruned_model.pth``)        -> ``B200HalfResNet`` of ``model.half()``
     * converted ``GraphModule``                                 -> ``B200QuantizedResNet``
+    * ``.npz`` engine blob written by ``save_engine`` / ``NetSpec.save`` -> the engine it describes (no torch.ao needed)
     """
     obj = path_or_obj
-    if isinstance(obj, (str, bytes)) or hasattr(obj, "__fspath__"):
-        obj = torch.load(obj, map_location="cpu", weights_only=False)
     kw = dict(max_batch=max_batch, device=device)
+    if isinstance(obj, (str, bytes)) or hasattr(obj, "__fspath__"):
+        import os
+        if os.fspath(obj).endswith(".npz" if isinstance(os.fspath(obj), str) else b".npz"):
+            obj = NetSpec.load(obj)
+        else:
+            obj = torch.load(obj, map_location="cpu", weights_only=False)
+    if isinstance(obj, NetSpec):
+        return (B200HalfResNet if obj.dtype == DTYPE_F16 else B200QuantizedResNet)(obj, **kw)
     if isinstance(obj, dict):
         if "conv1_input_scale_0" in obj:
             return B200QuantizedResNet.from_quantized_state_dict(obj, **kw)
@@ -66,6 +73,13 @@ def load_engine(path_or_obj, max_batch: int = 256, device: Optional[int] = None)
         import copy
         return B200HalfResNet.from_half_module(copy.deepcopy(obj).eval().half(), **kw)
     raise TypeError(f"cannot build an engine from {type(obj).__name__}")
+
+
+def save_engine(engine_or_net, path) -> None:
+    """Export the flattened network of an engine (or a ``NetSpec``) as a single ``.npz`` blob for fast start:
+    ``load_engine(path)`` rebuilds the same engine without the producer's torch.ao module."""
+    net = engine_or_net if isinstance(engine_or_net, NetSpec) else engine_or_net.net
+    net.save(path)
 
 
 def evaluate_accuracy(model, data_loader, device="cuda") -> float:

@@ -124,6 +124,35 @@ def test_on_disk_formats_are_recognised(tmp_path):
         pipeline.load_engine(3.14)
 
 
+def test_engine_blob_round_trips_exactly(tmp_path):
+    """SURVEY 8(f)-2 export: NetSpec -> .npz -> NetSpec is the identity (every scalar, every array and its dtype), for
+    the INT8 and the FP16 network; load_engine dispatches a .npz path to the engine constructor."""
+    from ievm_b200 import pipeline
+    specs = [ievm_b200.from_converted(cached_quantized(mf.PRUNED_WIDTHS)),
+             ievm_b200.from_half_module(mf.cast_fp16(mf.make_student((24, 40, 56, 72))))]
+    for i, a in enumerate(specs):
+        path = tmp_path / f"net{i}.npz"
+        pipeline.save_engine(a, path)
+        b = ievm_b200.NetSpec.load(path)
+        assert (a.dtype, a.in_c, a.in_h, a.in_w, a.num_classes, a.in_scale, a.in_zp, a.tensor_names) == \
+               (b.dtype, b.in_c, b.in_h, b.in_w, b.num_classes, b.in_scale, b.in_zp, b.tensor_names)
+        assert len(a.layers) == len(b.layers)
+        for la, lb in zip(a.layers, b.layers):
+            for f in la.__dataclass_fields__:
+                va, vb = getattr(la, f), getattr(lb, f)
+                if isinstance(va, np.ndarray):
+                    assert va.dtype == vb.dtype and np.array_equal(va, vb), (la.name, f)
+                else:
+                    assert va == vb and type(va) is type(vb), (la.name, f)
+        if not torch.cuda.is_available():
+            with pytest.raises(RuntimeError, match="no CPU fallback"):     # reached the engine constructor
+                pipeline.load_engine(str(path))
+    bad = tmp_path / "bad.npz"
+    np.savez(bad, header=np.frombuffer(b'{"format": "other"}', dtype=np.uint8))
+    with pytest.raises(ValueError, match="not an ievm NetSpec blob"):
+        ievm_b200.NetSpec.load(bad)
+
+
 def test_unsupported_graphs_fail_loudly():
     net = ievm_b200.from_converted(cached_quantized(mf.PRUNED_WIDTHS))
     import copy
