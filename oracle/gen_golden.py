@@ -74,6 +74,39 @@ def gen_int8(widths, tag):
     print("wrote int8", tag, y[0])
 
 
+def gen_int8_minmax(widths, tag):
+    """The qconfig flavour of the reference's stage-4 SCRIPT (quantization/main.py:185-242: per-channel symmetric
+    min/max weight observers, MovingAverageMinMaxObserver activations over 0..255).  That code is inline in main() and
+    needs the dataset, so it cannot be imported; ``model_factory.static_quantize_minmax`` restates those lines (same
+    torch.ao calls, same arguments) and every number below is produced by torch's own fbgemm operators on the module
+    ``convert_fx`` returns.  This is the flavour on which quantized::add_relu's fused dequantisation matters."""
+    torch.backends.quantized.engine = "fbgemm"
+    gm = mf.static_quantize_minmax(mf.make_student(widths))
+    x = mf.synthetic_images(N_IMAGES)
+    acts = {}
+    for name, mod in gm.named_modules():
+        if name and not list(mod.children()):
+            mod.register_forward_hook(lambda m_, i, o, name=name: acts.__setitem__(name, o))
+    with torch.no_grad():
+        y = gm(x)
+    out = {"logits": y.numpy(), "widths": np.array(widths), "n_images": np.array(N_IMAGES),
+           "in_scale": np.float32(float(gm.conv1_input_scale_0)), "in_zp": np.int32(int(gm.conv1_input_zero_point_0))}
+    names, digests = [], []
+    for name, o in acts.items():
+        if getattr(o, "is_quantized", False):
+            names.append(name)
+            digests.append(_digest(o.int_repr().contiguous().numpy()))
+    out["node_names"] = np.array(names)
+    out["node_sha256"] = np.array(digests)
+    for i in range(8):                 # quantized.add_relu outputs are graph functions, not modules: read their qparams
+        sfx = "" if i == 0 else f"_{i}"
+        li, bi = 1 + i // 2, i % 2
+        out[f"scale/add_relu{sfx}"] = np.float32(float(getattr(gm, f"layer{li}_{bi}_relu_scale_0")))
+        out[f"zp/add_relu{sfx}"] = np.int32(int(getattr(gm, f"layer{li}_{bi}_relu_zero_point_0")))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"int8_minmax_{tag}.npz"), **out)
+    print("wrote int8 minmax", tag, y[0])
+
+
 def gen_fp16(widths, tag):
     from engines import QuantizationEngine
 
@@ -110,5 +143,6 @@ if __name__ == "__main__":
     gen_int8(mf.PRUNED_WIDTHS, "w57")
     gen_int8(mf.DEFAULT_CFG_WIDTHS, "w60")
     gen_int8(mf.UNPRUNED_WIDTHS, "w64")
+    gen_int8_minmax(mf.PRUNED_WIDTHS, "w57")
     gen_fp16(mf.PRUNED_WIDTHS, "w57")
     gen_teacher()

@@ -9,6 +9,8 @@
 // `taps` different operand tiles in turn).  One CTA per SM on every SM (so that the number is the loaded-chip one),
 // operands are zeros (timing only), accumulators alternate between two TMEM buffers.
 //
+// argv: [iterations = 2000] [interleave = 1]; interleave > 1 sends consecutive instructions to that many independent
+// accumulators, which separates a per-instruction latency on a dependent chain from a throughput limit.
 // Prints clk per MMA, the shared-memory operand bytes per MMA, bytes/clk and MACs/clk per SM.  Round-1 measurements
 // that this generalises: SS M128 N64 ~96 clk (6 KB), TS M128 N64 ~73 clk (conv_wt.cuh).
 //
@@ -25,6 +27,7 @@ struct Case {
   int ts;          // 0 = SS, 1 = TS
   int m, n;
   int row_bytes;   // 64 or 128
+  int interleave;  // consecutive MMAs go round-robin to this many independent accumulators (1 = one dependent chain)
 };
 
 __global__ void __launch_bounds__(128)
@@ -59,19 +62,26 @@ mma_rate_kernel(Case c, int iters, unsigned long long* cycles, unsigned int* fai
   const uint32_t a_lo = smem_desc_lo(smem_u32(sA));
   const uint32_t b_lo = smem_desc_lo(smem_u32(sB));
   const int ksteps = c.row_bytes / 32;
-  const uint32_t acc_cols = c.n <= 128 ? 128u : 256u;     // two buffers when they fit beside the TS operand
-  const uint32_t nbuf = c.n <= 128 ? 2u : 1u;
+  // accumulator buffers of 64 / 128 / 256 columns in columns 0..383 (the TS operand sits behind them)
+  const uint32_t acc_cols = c.n <= 64 ? 64u : (c.n <= 128 ? 128u : 256u);
+  const uint32_t max_buf = 384u / acc_cols;
+  const uint32_t inter = static_cast<uint32_t>(c.interleave) < max_buf ? static_cast<uint32_t>(c.interleave) : max_buf;
+  const uint32_t nbuf = inter > 1 ? inter : (max_buf > 1 ? 2u : 1u);
   const uint32_t a_col = 2u * 128u + 128u;               // TS operand: columns 384.. (8 columns per 32-byte k-step)
   unsigned long long t0 = 0, t1 = 0;
   if (threadIdx.x == 0) {
     t0 = clock64();
     uint32_t buf = 0;
     for (int it = 0; it < iters; ++it) {
+      uint32_t seq = 0;
       for (int tap = 0; tap < kTaps; ++tap) {
         const uint32_t boff = static_cast<uint32_t>((tap & 1) * b_tile) >> 4;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t d = tmem + buf * acc_cols;
-          const uint32_t acc = (tap | ks) ? 1u : 0u;
+        for (int ks = 0; ks < ksteps; ++ks, ++seq) {
+          // inter == 1: the whole iteration accumulates into one buffer (a tile's K loop), buffers alternate per iteration;
+          // inter > 1: consecutive instructions go to different buffers (several tiles' K loops interleaved)
+          const uint32_t b = inter > 1 ? seq % inter : buf;
+          const uint32_t d = tmem + b * acc_cols;
+          const uint32_t acc = (inter > 1 ? seq >= inter : seq > 0) ? 1u : 0u;
           if (c.ts) umma_ts<0>(d, tmem + a_col + static_cast<uint32_t>(ks) * 8u, b_lo + boff + 2u * ks, hi, idesc, acc);
           else umma_i8_lohi(d, a_lo + 2u * ks, b_lo + boff + 2u * ks, hi, idesc, acc);
         }
@@ -96,6 +106,7 @@ mma_rate_kernel(Case c, int iters, unsigned long long* cycles, unsigned int* fai
 
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 2000;
+  const int interleave = argc > 2 ? atoi(argv[2]) : 1;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, 0) != cudaSuccess || prop.major != 10) {
     fprintf(stderr, "needs an sm_100 device\n");
@@ -109,12 +120,13 @@ int main(int argc, char** argv) {
   cudaMalloc(&d_cycles, sms * sizeof(unsigned long long));
   cudaMalloc(&d_fail, sizeof(unsigned int));
   std::vector<unsigned long long> h(sms);
+  printf("interleave = %d independent accumulators\n", interleave);
   printf("%-4s %4s %4s %5s | %9s %10s %8s %9s\n", "form", "M", "N", "rowB", "clk/MMA", "smem B/MMA", "B/clk", "MAC/clk");
   for (int ts = 0; ts <= 1; ++ts)
     for (int m : {128, 64})
       for (int n : {64, 128, 160, 256})
         for (int rb : {64, 128}) {
-          Case c{ts, m, n, rb};
+          Case c{ts, m, n, rb, interleave};
           cudaMemset(d_fail, 0, sizeof(unsigned int));
           for (int rep = 0; rep < 2; ++rep)                 // first launch warms up
             mma_rate_kernel<<<sms, 128, smem>>>(c, iters, d_cycles, d_fail);
