@@ -40,6 +40,25 @@ def test_oracle_matches_reference_golden(tag, golden_dir):
         assert np.array_equal(net.trace[name][0, :8, :4, :4], g[f"slice/{name}"])
 
 
+def test_oracle_matches_the_main_py_flavour_golden(golden_dir):
+    """Fixture of the stage-4 script's qconfig (quantization/main.py:185-242; oracle/gen_golden.py::gen_int8_minmax):
+    full-range activations, zero points up to 158 -- the flavour on which quantized::add_relu's fused dequantisation
+    (oracle/int8_forward.py::_dequant_fma) is observable."""
+    g = np.load(os.path.join(golden_dir, "int8_minmax_w57.npz"))
+    gm = mf.static_quantize_minmax(mf.make_student(mf.PRUNED_WIDTHS))
+    net = O.extract_qnet(gm)
+    assert np.float32(net.in_scale) == g["in_scale"] and net.in_zp == int(g["in_zp"])
+    assert np.float32(net.blocks[6].add_scale) == g["scale/add_relu_6"] and net.blocks[6].add_zp == int(g["zp/add_relu_6"])
+    logits = O.forward(net, mf.synthetic_images(int(g["n_images"])).numpy(), keep=True)
+    assert np.array_equal(logits, g["logits"])
+    checked = 0
+    for name, d in zip((str(s) for s in g["node_names"]), (str(s) for s in g["node_sha256"])):
+        if name in net.trace:
+            assert _sha(net.trace[name]) == d, f"activation digest mismatch at {name}"
+            checked += 1
+    assert checked >= 20
+
+
 def test_oracle_matches_live_fbgemm_nodes():
     gm = cached_quantized(mf.PRUNED_WIDTHS)
     net = O.extract_qnet(gm)
