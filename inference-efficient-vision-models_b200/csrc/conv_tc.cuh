@@ -91,6 +91,10 @@ struct ConvTcParams {
   int32_t* dump_acc;   // debug: raw accumulators [m_total][dump_pitch] (bit pattern for f16)
   int dump_pitch;
   unsigned int* stuck_flag;   // mapped host word; written before a bounded wait gives up
+#ifdef IEVM_EXP_HALFK
+  int half_k;          // A/B experiment: 128-byte shared-memory rows holding <= 64 bytes of channels
+                       // (IEVM_HALO_RB128=1): issue only the two k-steps that hold data
+#endif
 };
 
 // n / d.  magic = ceil(2^32 / d) is exact while n * d < 2^32; the host passes magic = 0 (plain division) when
@@ -492,7 +496,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // Everything the issuing thread needs per instruction is reduced to one add on a precomputed
     // descriptor low word: with N = 64 an MMA occupies the tensor pipe for only ~32 cycles, so the
     // single-thread issue loop is the critical path.
+#ifdef IEVM_EXP_HALFK
+    const bool wide = p.kc_bytes == 128 && !p.half_k;
+#else
     const bool wide = p.kc_bytes == 128;
+#endif
     const uint32_t hi = smem_desc_hi(static_cast<uint32_t>(p.kc_bytes));
     const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA));
     const uint32_t b_lo0 = smem_desc_lo(smem_u32(sB));
@@ -525,6 +533,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       wait_or_die(&tempty_bar[acc], acc_phase ^ 1u, 0x200u | acc, p.stuck_flag);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
+#ifdef IEVM_EXP_INTERLEAVE
+      // A/B experiment: issue the K loops of TWO consecutive tiles of this CTA interleaved, instruction
+      // by instruction, into two TMEM buffers, so that a dependent accumulate chain never waits on itself.  Both patch
+      // stages and both accumulators are acquired first; all four barriers are committed after the last instruction.
+      if (kMode == kModeHalo && kCluster == 1 && tile + tile_step < total_tiles && p.stages >= 2 && p.nacc >= 2) {
+        int acc2 = acc + 1;
+        uint32_t acc_phase2 = acc_phase;
+        if (acc2 == p.nacc) {
+          acc2 = 0;
+          acc_phase2 ^= 1u;
+        }
+        int stage2 = stage + 1;
+        uint32_t phase2 = phase;
+        if (stage2 == p.stages) {
+          stage2 = 0;
+          phase2 ^= 1u;
+        }
+        const int tile2 = tile + tile_step;
+        wait_or_die(&tempty_bar[acc2], acc_phase2 ^ 1u, 0x200u | acc2, p.stuck_flag);
+        const uint32_t d_tmem2 = tmem_base + static_cast<uint32_t>(acc2 * p.acc_stride);
+        const int p0a = (tile - fast_div(tile, p.tiles_per_img, p.tpi_magic) * p.tiles_per_img) * kTileM;
+        const int x0a = p0a - fast_div(p0a, p.wp, p.wp_magic) * p.wp;
+        const int p0b = (tile2 - fast_div(tile2, p.tiles_per_img, p.tpi_magic) * p.tiles_per_img) * kTileM;
+        const int x0b = p0b - fast_div(p0b, p.wp, p.wp_magic) * p.wp;
+        wait_or_die(&full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
+        wait_or_die(&full_bar[stage2], phase2, 0x300u | stage2, p.stuck_flag);
+        tc_fence_after();
+        const uint32_t a1 = a_lo0 + static_cast<uint32_t>(stage) * a_step + static_cast<uint32_t>(x0a) * row16;
+        const uint32_t a2 = a_lo0 + static_cast<uint32_t>(stage2) * a_step + static_cast<uint32_t>(x0b) * row16;
+        if (elect_one()) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t b = b_lo0 + static_cast<uint32_t>(tap) * b_step;
+            const uint32_t first = tap != 0 ? 1u : 0u;
+            mma(d_tmem, a1 + tap_off[tap], b, first);
+            mma(d_tmem2, a2 + tap_off[tap], b, first);
+            mma(d_tmem, a1 + tap_off[tap] + 2, b + 2, 1u);
+            mma(d_tmem2, a2 + tap_off[tap] + 2, b + 2, 1u);
+            if (wide) {
+              mma(d_tmem, a1 + tap_off[tap] + 4, b + 4, 1u);
+              mma(d_tmem2, a2 + tap_off[tap] + 4, b + 4, 1u);
+              mma(d_tmem, a1 + tap_off[tap] + 6, b + 6, 1u);
+              mma(d_tmem2, a2 + tap_off[tap] + 6, b + 6, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&empty_bar[stage2]);
+          umma_commit(&tfull_bar[acc]);
+          umma_commit(&tfull_bar[acc2]);
+        }
+        __syncwarp();
+        stage = stage2 + 1;
+        phase = phase2;
+        if (stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        acc = acc2 + 1;
+        acc_phase = acc_phase2;
+        if (acc == p.nacc) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+        tile += tile_step;                 // two tiles consumed (the loop header advances once more)
+        continue;
+      }
+#endif
       if (kMode == kModeHalo) {
         const int p0 = (tile - fast_div(tile, p.tiles_per_img, p.tpi_magic) * p.tiles_per_img) * kTileM;
         const int x0 = p0 - fast_div(p0, p.wp, p.wp_magic) * p.wp;

@@ -854,6 +854,9 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   p.dump_acc = dump_acc;
   p.dump_pitch = L.cout_pad;
   p.stuck_flag = h->stuck_dev;
+#ifdef IEVM_EXP_HALFK
+  p.half_k = (L.mode == kModeHalo && L.kc_bytes == 128 && L.cin_pitch * h->elem <= 64) ? 1 : 0;
+#endif
   return p;
 }
 

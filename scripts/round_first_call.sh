@@ -20,3 +20,14 @@ cut -c1-300 gpurun_out/${TAG}_bench.json
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file gpurun_out/${TAG}_ncu_launches_bench.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${TAG}_ncu.log 2>&1
 echo "ncu rc=$?"
+# 5. A/B builds prepared at the end of round 1 (default-build SASS is unaffected by
+#    them): parity first (golden logits, every tensor + accumulator, ragged batches, batch 64 vs the direct conv), then speed.
+for v in interleave halfk interleave_halfk; do
+  [ -f ab/lib_$v.so ] || continue
+  extra=""; case $v in *halfk*) extra="IEVM_HALO_RB128=1";; esac
+  env IEVM_LIB_PATH=ab/lib_$v.so $extra timeout 150 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider \
+    -k "golden or every_tensor or ragged or direct_conv or fp16_student" > gpurun_out/${TAG}_ab_${v}_tests.log 2>&1
+  echo "A/B $v parity rc=$?"; grep -E "passed|failed" gpurun_out/${TAG}_ab_${v}_tests.log | tail -1
+  env IEVM_LIB_PATH=ab/lib_$v.so $extra timeout 60 python scripts/layer_times.py 256 ${TAG}_ab_$v > gpurun_out/${TAG}_ab_${v}_layers.txt 2>&1
+  tail -3 gpurun_out/${TAG}_ab_${v}_layers.txt
+done
