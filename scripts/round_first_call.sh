@@ -20,7 +20,7 @@ cut -c1-300 gpurun_out/${TAG}_bench.json
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
   --log-file gpurun_out/${TAG}_ncu_launches_bench.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${TAG}_ncu.log 2>&1
 echo "ncu rc=$?"
-# 5. A/B builds prepared at the end of round 1 (default-build SASS is unaffected by
+# 5. A/B builds prepared at the end of round 1 (build them in the container first: python scripts/build_ab.py) (default-build SASS is unaffected by
 #    them): parity first (golden logits, every tensor + accumulator, ragged batches, batch 64 vs the direct conv), then speed.
 for v in interleave halfk interleave_halfk; do
   [ -f ab/lib_$v.so ] || continue
