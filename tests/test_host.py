@@ -34,6 +34,25 @@ def test_sass_contains_blackwell_instructions():
         assert mnemonic in out, f"{mnemonic} missing from SASS"
 
 
+def test_hot_kernels_do_not_spill():
+    """The tensor-core kernels run at their register caps (96 for the conv kernels, 128 for the fused front end): a
+    spill (STACK / LOCAL bytes in cuobjdump -res-usage) in any of them is a silent performance regression."""
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib.build()], capture_output=True, text=True).stdout
+    found = 0
+    lines = out.splitlines()
+    for i, line in enumerate(lines):
+        m = re.search(r"Function (\S+):", line)
+        if not m or i + 1 >= len(lines):
+            continue
+        name, usage = m.group(1), lines[i + 1]
+        if any(k in name for k in ("conv_tc_kernel", "frontend2_kernel", "head_i8_kernel", "head_f16_kernel")):
+            found += 1
+            assert "STACK:0 " in usage and "LOCAL:0 " in usage, f"{name}: {usage.strip()}"
+            regs = int(re.search(r"REG:(\d+)", usage).group(1))
+            assert regs <= (128 if "frontend2" in name else 96), f"{name}: {regs} registers"
+    assert found >= 17          # 12 conv_tc instantiations, 3 front ends, 2 heads
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     net = ievm_b200.from_converted(cached_quantized(mf.PRUNED_WIDTHS))
