@@ -91,6 +91,9 @@ struct ConvTcParams {
   int32_t* dump_acc;   // debug: raw accumulators [m_total][dump_pitch] (bit pattern for f16)
   int dump_pitch;
   unsigned int* stuck_flag;   // mapped host word; written before a bounded wait gives up
+#ifdef IEVM_EXP_TIMING
+  int timing_slot;     // A/B instrumentation: where this launch's per-CTA role timers go (g_exp_timing)
+#endif
 #ifdef IEVM_EXP_HALFK
   int half_k;          // A/B experiment: 128-byte shared-memory rows holding <= 64 bytes of channels
                        // (IEVM_HALO_RB128=1): issue only the two k-steps that hold data
@@ -117,6 +120,21 @@ __device__ __forceinline__ void wait_or_die(uint64_t* bar, uint32_t parity, uint
     }
   }
 }
+
+#ifdef IEVM_EXP_TIMING
+// [slot][cta][16]: 0 mma loop clk, 1 mma wait tempty, 2 mma wait full, 3 mma loop ns, 4 producer loop clk, 5 producer wait empty,
+// 6 epilogue(warp 2) loop clk, 7 epilogue wait tfull, 8 tiles of this CTA, 9 whole-kernel clk (warp 1), 10 whole-kernel ns
+constexpr int kExpSlots = 32, kExpCtas = 160, kExpWords = 16;
+__device__ unsigned long long g_exp_timing[kExpSlots * kExpCtas * kExpWords];
+#define IEVM_TIMED_WAIT(acc, ...)                 \
+  do {                                            \
+    const long long t__ = clock64();              \
+    wait_or_die(__VA_ARGS__);                     \
+    acc += clock64() - t__;                       \
+  } while (0)
+#else
+#define IEVM_TIMED_WAIT(acc, ...) wait_or_die(__VA_ARGS__)
+#endif
 
 // ---- INT8 epilogue arithmetic: float32, no FMA contraction, round-half-even (== fbgemm/ATen) ----
 // Scalar forms (used by the CUDA-core kernels and as the definition the fast forms must equal).
@@ -410,6 +428,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int tile_first = kCluster > 1 ? static_cast<int>(blockIdx.x) / kCluster : static_cast<int>(blockIdx.x);
   const int tile_step = kCluster > 1 ? static_cast<int>(gridDim.x) / kCluster : static_cast<int>(gridDim.x);
   const int hw = p.ho * p.wo;
+#ifdef IEVM_EXP_TIMING
+  long long tm_wait_a = 0, tm_wait_b = 0;
+  const long long tm_t0 = clock64();
+  const unsigned long long tm_ns0 = globaltimer_ns();
+  unsigned long long* tm_out = g_exp_timing + (static_cast<size_t>(p.timing_slot) * kExpCtas + blockIdx.x) * kExpWords;
+  int tm_tiles = 0;
+#endif
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -429,7 +454,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int img = fast_div(tile, p.tiles_per_img, p.tpi_magic);
         const int p0 = (tile - img * p.tiles_per_img) * kTileM;
         const int oy_first = fast_div(p0, p.wp, p.wp_magic);
-        wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
+        IEVM_TIMED_WAIT(tm_wait_a, &empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
         if (elect_one()) {
 #ifdef IEVM_EXP_NOTMA
           mbar_arrive(&full_bar[stage]);                         // timing experiment: no activation loads
@@ -459,7 +484,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int ty = 0; ty < p.ksize; ++ty) {
         for (int tx = 0; tx < p.ksize; ++tx) {
           for (int ch = 0; ch < p.kchunks; ++ch, ++kb) {
-            wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
+            IEVM_TIMED_WAIT(tm_wait_a, &empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
             if (elect_one()) {
               if (kCluster > 1) {
                 // both CTAs fill their own stage and complete bytes on the leader's barrier; the leader arms it
@@ -486,6 +511,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
+#ifdef IEVM_EXP_TIMING
+    if (lane == 0 && blockIdx.x < kExpCtas) {
+      tm_out[4] = clock64() - tm_t0;
+      tm_out[5] = tm_wait_a;
+    }
+#endif
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     int stage = 0;
@@ -530,7 +561,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>((tap / 3) * p.wp + (tap % 3)) * row16;
     if (p.resident_b) wait_or_die(bres_bar, 0, 0x500u, p.stuck_flag);
     for (int tile = tile_first; leader && tile < total_tiles; tile += tile_step) {   // the peer CTA issues no MMAs
-      wait_or_die(&tempty_bar[acc], acc_phase ^ 1u, 0x200u | acc, p.stuck_flag);
+      IEVM_TIMED_WAIT(tm_wait_a, &tempty_bar[acc], acc_phase ^ 1u, 0x200u | acc, p.stuck_flag);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
 #ifdef IEVM_EXP_INTERLEAVE
@@ -603,7 +634,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (kMode == kModeHalo) {
         const int p0 = (tile - fast_div(tile, p.tiles_per_img, p.tpi_magic) * p.tiles_per_img) * kTileM;
         const int x0 = p0 - fast_div(p0, p.wp, p.wp_magic) * p.wp;
-        wait_or_die(&full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
+        IEVM_TIMED_WAIT(tm_wait_b, &full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step + static_cast<uint32_t>(x0) * row16;
         if (elect_one()) {
@@ -622,7 +653,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       } else {
         for (int kb = 0; kb < num_kb; ++kb) {
-          wait_or_die(&full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
+          IEVM_TIMED_WAIT(tm_wait_b, &full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step;
           const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(p.resident_b ? kb : stage) * b_step;
@@ -648,6 +679,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         acc_phase ^= 1u;
       }
     }
+#ifdef IEVM_EXP_TIMING
+    if (lane == 0 && blockIdx.x < kExpCtas) {
+      tm_out[0] = clock64() - tm_t0;
+      tm_out[1] = tm_wait_a;
+      tm_out[2] = tm_wait_b;
+      tm_out[3] = globaltimer_ns() - tm_ns0;
+    }
+#endif
   } else {
     // ================================ epilogue ================================
     const int quad = warp & 3;
@@ -687,6 +726,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         acc_phase_next ^= 1u;
       }
       if ((seq & (groups - 1)) != group) continue;
+#ifdef IEVM_EXP_TIMING
+      ++tm_tiles;
+#endif
       int m, n0;
       bool valid;
       if (kMode == kModeHalo) {
@@ -710,7 +752,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
       int c = sub;
       if (kResI8 && c < nchunks) ra = load_res16_i8(p, m, valid, n0 + c * 16);   // does not depend on the MMA
-      wait_or_die(&tfull_bar[acc], acc_phase, 0x400u | acc, p.stuck_flag);
+      IEVM_TIMED_WAIT(tm_wait_a, &tfull_bar[acc], acc_phase, 0x400u | acc, p.stuck_flag);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * p.acc_stride);
@@ -747,8 +789,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   }
 
+#ifdef IEVM_EXP_TIMING
+  if (warp == 2 && lane == 0 && blockIdx.x < kExpCtas) {
+    tm_out[6] = clock64() - tm_t0;
+    tm_out[7] = tm_wait_a;
+    tm_out[8] = tm_tiles;
+  }
+#endif
   tc_fence_before();
   __syncthreads();
+#ifdef IEVM_EXP_TIMING
+  if (warp == 1 && lane == 0 && blockIdx.x < kExpCtas) {
+    tm_out[9] = clock64() - tm_t0;
+    tm_out[10] = globaltimer_ns() - tm_ns0;
+  }
+#endif
   if (kCluster > 1) cluster_sync_all();     // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();

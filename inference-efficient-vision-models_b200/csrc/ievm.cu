@@ -854,6 +854,9 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   p.dump_acc = dump_acc;
   p.dump_pitch = L.cout_pad;
   p.stuck_flag = h->stuck_dev;
+#ifdef IEVM_EXP_TIMING
+  p.timing_slot = static_cast<int>(&L - h->layers.data()) % kExpSlots;
+#endif
 #ifdef IEVM_EXP_HALFK
   p.half_k = (L.mode == kModeHalo && L.kc_bytes == 128 && L.cin_pitch * h->elem <= 64) ? 1 : 0;
 #endif
@@ -2006,6 +2009,20 @@ int ievm_probe_patch(const void* in_dev, int n, int h, int w, int c_pitch, int r
   if (e != cudaSuccess) return fail(IEVM_ERR_CUDA, "probe_patch: %s (stuck code 0x%x)", cudaGetErrorString(e), code);
   return IEVM_OK;
 }
+
+#ifdef IEVM_EXP_TIMING
+// A/B instrumentation only (never in the default build): per-layer, per-CTA role timers of conv_tc_kernel.
+int ievm_exp_timing_read(unsigned long long* host, int clear) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(host, g_exp_timing, sizeof(g_exp_timing)));
+  if (clear) {
+    void* sym = nullptr;
+    CUDA_TRY(cudaGetSymbolAddress(&sym, g_exp_timing));
+    CUDA_TRY(cudaMemset(sym, 0, sizeof(g_exp_timing)));
+  }
+  return kExpSlots * kExpCtas * kExpWords;
+}
+#endif
 
 int ievm_count_correct(const void* logits, int dtype, const int64_t* labels, int n, int classes, uint64_t* counters2,
                        void* stream) {
