@@ -41,13 +41,34 @@ constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 enum : int { kDtypeI8 = 0, kDtypeF16 = 1 };
 // A-operand feeding modes.
 //  kModeIm2col: one im2col TMA per (filter tap, channel chunk) -- any 1x1/3x3, stride 1|2.
-//  kModeHalo  : 3x3 stride-1 pad-1 convs whose pixel fits one smem row (<= 128 B): the tile is 128
-//               consecutive positions of the image's halo-extended row-major space (rows of W+2), ONE tiled
-//               TMA box brings the (rows+2) x (W+2) input patch with zero-filled borders, and the nine
-//               taps are nine row-shifted views of that patch (descriptor start + (ky*(W+2)+kx) rows).
-//               Cuts shared-memory fill traffic ~4.5x versus per-tap loads; the W+2-W junk columns are
-//               computed and discarded.
+//  kModeHalo  : 3x3 stride-1 pad-1 convs whose pixel fits one smem row (<= 128 B).  The image is cut into BANDS of
+//               S sub-tiles; a sub-tile is R = floor(128 / (W+2)) whole output rows = R*(W+2) consecutive positions
+//               of the halo-extended row-major space (<= 128 MMA rows, the remainder are junk lanes).  ONE tiled
+//               TMA box brings the band's (S*R+2) x (W+2) input patch with zero-filled borders; every sub-tile's
+//               nine taps are nine row-shifted views of that patch (descriptor start + (sub*R*(W+2) + ky*(W+2)+kx)
+//               rows), all with compile-time-like constant offsets because sub-tiles are row aligned.
+//               Why bands: a tcgen05.mma queue is only ~1-2 instructions deep and every mbarrier test by the issuing
+//               thread costs ~150 clk of idle tensor pipe (profiles/r02_mma_convlike.txt); with S sub-tiles per
+//               patch the issuer pays one batched barrier test per S*9*ksteps instructions, the patch is re-read
+//               (S*R+2)/(S*R) times instead of 2.7x, and one TMA replaces S.
 enum : int { kModeIm2col = 0, kModeHalo = 1 };
+constexpr int kMaxBandSubs = 4;
+constexpr int kEpConst = 128;
+// Halo-mode shape classes.  For the shapes the networks of this path actually have, (W+2, row bytes, N) are template
+// constants, so that every descriptor offset of a sub-tile's 18 / 36 instructions is an immediate added to ONE uniform
+// base register.  With run-time offsets ptxas keeps the nine tap offsets in vector registers and pays ~20 R2UR moves
+// (~200 cycles of idle tensor pipe) per sub-tile.  Class 0 is the generic run-time fallback.
+//   1: 56x56 x 64-byte pixels, N = 64 (INT8 layer 1)     2: 28x28 x 128-byte pixels, N = 128 (INT8 layer 2)
+//   3: 56x56 x 128-byte pixels, N = 64 (FP16 layer 1)
+constexpr int kHaloShapes = 4;
+__host__ __device__ constexpr int halo_shape_wp(int s) { return s == 1 ? 58 : s == 2 ? 30 : s == 3 ? 58 : 0; }
+__host__ __device__ constexpr int halo_shape_rb(int s) { return s == 1 ? 64 : s == 2 ? 128 : s == 3 ? 128 : 0; }
+__host__ __device__ constexpr int halo_shape_bn(int s) { return s == 1 ? 64 : s == 2 ? 128 : s == 3 ? 64 : 0; }
+inline int halo_shape_class(int wp, int rb, int bn) {
+  for (int s = 1; s < kHaloShapes; ++s)
+    if (halo_shape_wp(s) == wp && halo_shape_rb(s) == rb && halo_shape_bn(s) == bn) return s;
+  return 0;
+}
 
 struct ConvTcParams {
   // implicit-GEMM geometry
@@ -63,10 +84,15 @@ struct ConvTcParams {
   int resident_b;      // 1: all weight k-blocks stay in shared memory (n_tiles == 1)
   int a_stage_bytes;   // distance between A stages in shared memory
   int a_tx_bytes;      // bytes one A-operand TMA delivers
-  // halo mode
+  int kb_group;        // im2col mode: k-blocks per pipeline stage (one full/empty barrier pair per group)
+  // halo (band) mode
   int h_in, w_in, wp;  // input height / width, wp = w_in + 2
-  int tiles_per_img;
-  uint32_t tpi_magic, wp_magic, hw_magic, wo_magic;   // ceil(2^32 / d), or 0 = divide normally: see fast_div
+  int sub_rows;        // R: output rows per sub-tile
+  int sub_pos;         // R * wp: MMA rows of a sub-tile that are real positions
+  int subs_per_img;    // T = ceil(h_in / R)
+  int band_subs;       // S: sub-tiles per band (<= kMaxBandSubs, <= nacc)
+  int total_subs;      // n * T
+  uint32_t spi_magic, wp_magic, hw_magic, wo_magic;   // ceil(2^32 / d), or 0 = divide normally: see fast_div
   int tmem_cols;       // power of two >= 32 covering the accumulator ring
   int acc_stride;      // column distance between accumulator buffers (power of two >= bn)
   int nacc;            // accumulator buffers in the ring (2 .. kMaxAcc)
@@ -91,12 +117,13 @@ struct ConvTcParams {
   int32_t* dump_acc;   // debug: raw accumulators [m_total][dump_pitch] (bit pattern for f16)
   int dump_pitch;
   unsigned int* stuck_flag;   // mapped host word; written before a bounded wait gives up
+  // The same per-channel tables as ep0 / ep1 inside the kernel-parameter block (filled when cout_pad <= kEpConst): the
+  // statically shaped halo kernels unroll their chunk loop, so every table entry becomes a constant-bank operand of the
+  // FADD / FMUL that uses it -- no shared-memory loads (and no short-scoreboard stalls behind them) in the epilogue.
+  float epc0[128];
+  float epc1[128];
 #ifdef IEVM_EXP_TIMING
   int timing_slot;     // A/B instrumentation: where this launch's per-CTA role timers go (g_exp_timing)
-#endif
-#ifdef IEVM_EXP_HALFK
-  int half_k;          // A/B experiment: 128-byte shared-memory rows holding <= 64 bytes of channels
-                       // (IEVM_HALO_RB128=1): issue only the two k-steps that hold data
 #endif
 };
 
@@ -357,10 +384,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
 // deep K (layers 3-4) are bound by how fast an SM can ingest operands (~40 B/clk), and the pair ingests
 // (128 + bn/2) instead of (128 + bn) rows per k-block for the same MMA work.  Only the leader (even) CTA issues
 // MMAs; full barriers live in the leader, empty / tmem-full barriers are signalled in both CTAs by the commit.
-template <int kDtype, bool kHasRes, int kMode, int kCluster>
+template <int kDtype, bool kHasRes, int kMode, int kCluster, int kShape = 0>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const ConvTcParams p) {
+               const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (required by the 128B swizzle atoms) in the shared address space.
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -369,9 +396,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int num_kb = p.ksize * p.ksize * p.kchunks;
   const int a_bytes = p.a_stage_bytes;
   const int b_bytes = (p.bn / kCluster) * p.kc_bytes;      // a pair CTA holds half of the weight k-block
-  const int b_slots = p.resident_b ? num_kb : p.stages;
+  const int slots = p.stages * p.kb_group;                  // im2col: kb_group k-blocks share one barrier pair
+  const int b_slots = p.resident_b ? num_kb : slots;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + p.stages * a_bytes;
+  uint8_t* sB = smem + slots * a_bytes;
   float* s_ep0 = reinterpret_cast<float*>(sB + b_slots * b_bytes);
   float* s_ep1 = s_ep0 + p.cout_pad;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ep1 + p.cout_pad);
@@ -421,13 +449,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   griddep_launch_dependents();          // the next kernel may begin its prologue as SMs free up
 
-  // Tile schedule.  Work item `tile` of stride `tile_step` starting at `tile_first`:
-  //   single CTA : tile -> (m_tile = tile / n_tiles, n_tile = tile % n_tiles)
-  //   cluster    : tile is a cluster tile -> (m_tile = (tile / n_tiles) * kCluster + rank, n_tile = tile % n_tiles)
+  // Work schedule.
+  //   im2col : work item `tile` of stride `tile_step` starting at `tile_first`:
+  //              single CTA : tile -> (m_tile = tile / n_tiles, n_tile = tile % n_tiles)
+  //              cluster    : tile is a cluster tile -> (m_tile = (tile / n_tiles) * kCluster + rank, n_tile = tile % n_tiles)
+  //   halo   : the sub-tiles (img, s) = (t / T, t % T) are numbered t = 0 .. n*T-1; CTA b owns the CONTIGUOUS range
+  //            [t_begin, t_end) (sizes differ by at most one sub-tile) and walks it in bands of up to S sub-tiles of the
+  //            same image.  All three roles derive the same band sequence from (t_begin, t_end).
   const int total_tiles = kCluster > 1 ? ((p.m_tiles + kCluster - 1) / kCluster) * p.n_tiles : p.m_tiles * p.n_tiles;
   const int tile_first = kCluster > 1 ? static_cast<int>(blockIdx.x) / kCluster : static_cast<int>(blockIdx.x);
   const int tile_step = kCluster > 1 ? static_cast<int>(gridDim.x) / kCluster : static_cast<int>(gridDim.x);
   const int hw = p.ho * p.wo;
+  int t_begin = 0, t_end = 0;
+  if (kMode == kModeHalo) {
+    const int q = p.total_subs / static_cast<int>(gridDim.x), r = p.total_subs - q * static_cast<int>(gridDim.x);
+    const int b = static_cast<int>(blockIdx.x);
+    t_begin = b * q + (b < r ? b : r);
+    t_end = t_begin + q + (b < r ? 1 : 0);
+  }
 #ifdef IEVM_EXP_TIMING
   long long tm_wait_a = 0, tm_wait_b = 0;
   const long long tm_t0 = clock64();
@@ -449,18 +488,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t tx_bytes = static_cast<uint32_t>(p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-      if (kMode == kModeHalo) {
-        const int img = fast_div(tile, p.tiles_per_img, p.tpi_magic);
-        const int p0 = (tile - img * p.tiles_per_img) * kTileM;
-        const int oy_first = fast_div(p0, p.wp, p.wp_magic);
+    if (kMode == kModeHalo) {
+      int img = fast_div(t_begin, p.subs_per_img, p.spi_magic);
+      int s0 = t_begin - img * p.subs_per_img;
+      for (int t = t_begin; t < t_end;) {
+        const int ns = min(p.band_subs, min(p.subs_per_img - s0, t_end - t));
         IEVM_TIMED_WAIT(tm_wait_a, &empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
         if (elect_one()) {
 #ifdef IEVM_EXP_NOTMA
           mbar_arrive(&full_bar[stage]);                         // timing experiment: no activation loads
 #else
           mbar_expect_tx(&full_bar[stage], tx_bytes);
-          tma_load_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], 0, -1, oy_first - 1, img);
+          tma_load_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], 0, -1, s0 * p.sub_rows - 1, img);
 #endif
         }
         __syncwarp();
@@ -468,44 +507,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           stage = 0;
           phase ^= 1u;
         }
-        continue;
+        t += ns;
+        s0 += ns;
+        if (s0 == p.subs_per_img) {
+          s0 = 0;
+          ++img;
+        }
       }
-      const int m_group = tile / p.n_tiles;
-      const int n_tile = tile - m_group * p.n_tiles;
-      const int m_tile = kCluster > 1 ? m_group * kCluster + static_cast<int>(crank) : m_group;
-      const int m0 = m_tile * kTileM;
-      const int img = fast_div(m0, hw, p.hw_magic);
-      const int rem = m0 - img * hw;
-      const int oy = fast_div(rem, p.wo, p.wo_magic);
-      const int ox = rem - oy * p.wo;
-      const int base_w = ox * p.stride - p.pad;
-      const int base_h = oy * p.stride - p.pad;
-      int kb = 0;
-      for (int ty = 0; ty < p.ksize; ++ty) {
-        for (int tx = 0; tx < p.ksize; ++tx) {
-          for (int ch = 0; ch < p.kchunks; ++ch, ++kb) {
-            IEVM_TIMED_WAIT(tm_wait_a, &empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
-            if (elect_one()) {
-              if (kCluster > 1) {
-                // both CTAs fill their own stage and complete bytes on the leader's barrier; the leader arms it
-                // for the pair's total
-                if (leader) mbar_expect_tx(&full_bar[stage], 2u * tx_bytes);
-                tma_load_im2col_4d_pair(sA + stage * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h,
-                                        img, static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
-                tma_load_2d_pair(sB + stage * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems,
-                                 n_tile * p.bn + static_cast<int>(crank) * (p.bn / kCluster));
-              } else {
-                mbar_expect_tx(&full_bar[stage], tx_bytes);
-                tma_load_im2col_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h, img,
-                                   static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
-                if (!p.resident_b)
-                  tma_load_2d(sB + stage * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems, n_tile * p.bn);
+    } else {
+      const int G = p.kb_group;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const int m_group = tile / p.n_tiles;
+        const int n_tile = tile - m_group * p.n_tiles;
+        const int m_tile = kCluster > 1 ? m_group * kCluster + static_cast<int>(crank) : m_group;
+        const int m0 = m_tile * kTileM;
+        const int img = fast_div(m0, hw, p.hw_magic);
+        const int rem = m0 - img * hw;
+        const int oy = fast_div(rem, p.wo, p.wo_magic);
+        const int ox = rem - oy * p.wo;
+        const int base_w = ox * p.stride - p.pad;
+        const int base_h = oy * p.stride - p.pad;
+        int kb = 0, g = 0;
+        for (int ty = 0; ty < p.ksize; ++ty) {
+          for (int tx = 0; tx < p.ksize; ++tx) {
+            for (int ch = 0; ch < p.kchunks; ++ch, ++kb) {
+              if (g == 0) IEVM_TIMED_WAIT(tm_wait_a, &empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
+              const int slot = stage * G + g;
+              if (elect_one()) {
+                if (kCluster > 1) {
+                  // both CTAs fill their own stage and complete bytes on the leader's barrier; the leader arms it
+                  // for the pair's total
+                  if (leader && g == 0) mbar_expect_tx(&full_bar[stage], 2u * tx_bytes * static_cast<uint32_t>(G));
+                  tma_load_im2col_4d_pair(sA + slot * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h,
+                                          img, static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
+                  tma_load_2d_pair(sB + slot * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems,
+                                   n_tile * p.bn + static_cast<int>(crank) * (p.bn / kCluster));
+                } else {
+                  if (g == 0) mbar_expect_tx(&full_bar[stage], tx_bytes * static_cast<uint32_t>(G));
+                  tma_load_im2col_4d(sA + slot * a_bytes, &tmap_a, &full_bar[stage], ch * p.kc_elems, base_w, base_h, img,
+                                     static_cast<uint16_t>(tx), static_cast<uint16_t>(ty));
+                  if (!p.resident_b)
+                    tma_load_2d(sB + slot * b_bytes, &tmap_b, &full_bar[stage], kb * p.kc_elems, n_tile * p.bn);
+                }
               }
-            }
-            __syncwarp();
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
+              __syncwarp();
+              if (++g == G) {
+                g = 0;
+                if (++stage == p.stages) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
             }
           }
         }
@@ -524,14 +576,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     // One tcgen05.mma consumes 32 bytes of K per row: 2 (64-byte rows) or 4 (128-byte rows) per k-block.
-    // Everything the issuing thread needs per instruction is reduced to one add on a precomputed
-    // descriptor low word: with N = 64 an MMA occupies the tensor pipe for only ~32 cycles, so the
-    // single-thread issue loop is the critical path.
-#ifdef IEVM_EXP_HALFK
-    const bool wide = p.kc_bytes == 128 && !p.half_k;
-#else
+    // Everything the issuing thread needs per instruction is reduced to one add on a precomputed descriptor low
+    // word, and barrier tests are batched: the tensor unit's instruction queue is only one or two instructions
+    // deep, so whatever the issuing thread does between two instructions beyond ~50 cycles is idle tensor time
+    // (one mbarrier test is ~150).
     const bool wide = p.kc_bytes == 128;
-#endif
     const uint32_t hi = smem_desc_hi(static_cast<uint32_t>(p.kc_bytes));
     const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA));
     const uint32_t b_lo0 = smem_desc_lo(smem_u32(sB));
@@ -556,115 +605,133 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mma(d, a_lo + 6, b_lo + 6, 1u);
       }
     };
-    uint32_t tap_off[9];
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>((tap / 3) * p.wp + (tap % 3)) * row16;
     if (p.resident_b) wait_or_die(bres_bar, 0, 0x500u, p.stuck_flag);
-    for (int tile = tile_first; leader && tile < total_tiles; tile += tile_step) {   // the peer CTA issues no MMAs
-      IEVM_TIMED_WAIT(tm_wait_a, &tempty_bar[acc], acc_phase ^ 1u, 0x200u | acc, p.stuck_flag);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
-#ifdef IEVM_EXP_INTERLEAVE
-      // A/B experiment: issue the K loops of TWO consecutive tiles of this CTA interleaved, instruction
-      // by instruction, into two TMEM buffers, so that a dependent accumulate chain never waits on itself.  Both patch
-      // stages and both accumulators are acquired first; all four barriers are committed after the last instruction.
-      if (kMode == kModeHalo && kCluster == 1 && tile + tile_step < total_tiles && p.stages >= 2 && p.nacc >= 2) {
-        int acc2 = acc + 1;
-        uint32_t acc_phase2 = acc_phase;
-        if (acc2 == p.nacc) {
-          acc2 = 0;
-          acc_phase2 ^= 1u;
-        }
-        int stage2 = stage + 1;
-        uint32_t phase2 = phase;
-        if (stage2 == p.stages) {
-          stage2 = 0;
-          phase2 ^= 1u;
-        }
-        const int tile2 = tile + tile_step;
-        wait_or_die(&tempty_bar[acc2], acc_phase2 ^ 1u, 0x200u | acc2, p.stuck_flag);
-        const uint32_t d_tmem2 = tmem_base + static_cast<uint32_t>(acc2 * p.acc_stride);
-        const int p0a = (tile - fast_div(tile, p.tiles_per_img, p.tpi_magic) * p.tiles_per_img) * kTileM;
-        const int x0a = p0a - fast_div(p0a, p.wp, p.wp_magic) * p.wp;
-        const int p0b = (tile2 - fast_div(tile2, p.tiles_per_img, p.tpi_magic) * p.tiles_per_img) * kTileM;
-        const int x0b = p0b - fast_div(p0b, p.wp, p.wp_magic) * p.wp;
-        wait_or_die(&full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
-        wait_or_die(&full_bar[stage2], phase2, 0x300u | stage2, p.stuck_flag);
-        tc_fence_after();
-        const uint32_t a1 = a_lo0 + static_cast<uint32_t>(stage) * a_step + static_cast<uint32_t>(x0a) * row16;
-        const uint32_t a2 = a_lo0 + static_cast<uint32_t>(stage2) * a_step + static_cast<uint32_t>(x0b) * row16;
-        if (elect_one()) {
+    if (kMode == kModeHalo) {
+      constexpr bool kStatic = kShape != 0;
+      const uint32_t row16v = kStatic ? static_cast<uint32_t>(halo_shape_rb(kShape) / 16) : row16;
+      const uint32_t wp16 = kStatic ? static_cast<uint32_t>(halo_shape_wp(kShape) * (halo_shape_rb(kShape) / 16))
+                                    : static_cast<uint32_t>(p.wp) * row16;
+      const uint32_t bstep = kStatic ? static_cast<uint32_t>(halo_shape_bn(kShape) * halo_shape_rb(kShape) / 16) : b_step;
+      const bool widev = kStatic ? halo_shape_rb(kShape) == 128 : wide;
+      const uint32_t sub_step = static_cast<uint32_t>(p.sub_pos) * row16;
+      int s0 = t_begin - fast_div(t_begin, p.subs_per_img, p.spi_magic) * p.subs_per_img;
+      for (int t = t_begin; t < t_end;) {
+        const int ns = min(p.band_subs, min(p.subs_per_img - s0, t_end - t));
+        // ONE batched test of the band's barriers (patch landed, its ns accumulators drained): the tests are issued back
+        // to back, so the batch costs one round trip instead of ns + 1
+        {
+          uint64_t* bars[kMaxBandSubs + 1];
+          uint32_t par[kMaxBandSubs + 1];
+          bars[0] = &full_bar[stage];
+          par[0] = phase;
+          int a = acc;
+          uint32_t ph = acc_phase;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t b = b_lo0 + static_cast<uint32_t>(tap) * b_step;
-            const uint32_t first = tap != 0 ? 1u : 0u;
-            mma(d_tmem, a1 + tap_off[tap], b, first);
-            mma(d_tmem2, a2 + tap_off[tap], b, first);
-            mma(d_tmem, a1 + tap_off[tap] + 2, b + 2, 1u);
-            mma(d_tmem2, a2 + tap_off[tap] + 2, b + 2, 1u);
-            if (wide) {
-              mma(d_tmem, a1 + tap_off[tap] + 4, b + 4, 1u);
-              mma(d_tmem2, a2 + tap_off[tap] + 4, b + 4, 1u);
-              mma(d_tmem, a1 + tap_off[tap] + 6, b + 6, 1u);
-              mma(d_tmem2, a2 + tap_off[tap] + 6, b + 6, 1u);
+          for (int j = 0; j < kMaxBandSubs; ++j) {
+            if (j < ns) {
+              bars[j + 1] = &tempty_bar[a];
+              par[j + 1] = ph ^ 1u;
+              if (++a == p.nacc) {
+                a = 0;
+                ph ^= 1u;
+              }
+            } else {
+              bars[j + 1] = bars[j];
+              par[j + 1] = par[j];
             }
           }
-          umma_commit(&empty_bar[stage]);
-          umma_commit(&empty_bar[stage2]);
-          umma_commit(&tfull_bar[acc]);
-          umma_commit(&tfull_bar[acc2]);
-        }
-        __syncwarp();
-        stage = stage2 + 1;
-        phase = phase2;
-        if (stage == p.stages) {
-          stage = 0;
-          phase ^= 1u;
-        }
-        acc = acc2 + 1;
-        acc_phase = acc_phase2;
-        if (acc == p.nacc) {
-          acc = 0;
-          acc_phase ^= 1u;
-        }
-        tile += tile_step;                 // two tiles consumed (the loop header advances once more)
-        continue;
-      }
+#ifdef IEVM_EXP_TIMING
+          const long long tw0 = clock64();
 #endif
-      if (kMode == kModeHalo) {
-        const int p0 = (tile - fast_div(tile, p.tiles_per_img, p.tpi_magic) * p.tiles_per_img) * kTileM;
-        const int x0 = p0 - fast_div(p0, p.wp, p.wp_magic) * p.wp;
-        IEVM_TIMED_WAIT(tm_wait_b, &full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
+          if (!mbar_try_wait5(bars[0], par[0], bars[1], par[1], bars[2], par[2], bars[3], par[3], bars[4], par[4])) {
+            // not there yet: repeat the batched test (one round trip per attempt) instead of five blocking waits in a row
+            const uint64_t t0 = globaltimer_ns();
+            uint32_t spins = 0;
+            while (!mbar_try_wait5(bars[0], par[0], bars[1], par[1], bars[2], par[2], bars[3], par[3], bars[4], par[4])) {
+              if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > IEVM_WAIT_LIMIT_NS) {
+                wait_or_die(bars[0], par[0], 0x300u | stage, p.stuck_flag);      // names the barrier that is stuck, then traps
+#pragma unroll
+                for (int j = 1; j <= kMaxBandSubs; ++j) wait_or_die(bars[j], par[j], 0x200u | j, p.stuck_flag);
+              }
+            }
+          }
+#ifdef IEVM_EXP_TIMING
+          tm_wait_b += clock64() - tw0;
+#endif
+        }
         tc_fence_after();
-        const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step + static_cast<uint32_t>(x0) * row16;
+        const uint32_t a_band = a_lo0 + static_cast<uint32_t>(stage) * a_step;
         if (elect_one()) {
+          int a2 = acc;
+#ifdef IEVM_EXP_TIMING
+          const long long ti0 = clock64();
+#endif
+#pragma unroll 1
+          for (int j = 0; j < ns; ++j) {
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a2 * p.acc_stride);
+            const uint32_t a_lo = a_band + static_cast<uint32_t>(j) * sub_step;
+            // opaque to the optimiser: the 18 / 36 weight descriptors are then base + immediate (one uniform add each)
+            // instead of loop-invariant values parked in vector registers and moved back with R2UR before every use
+            uint32_t b_base = b_lo0;
+            asm volatile("" : "+r"(b_base));
 #ifndef IEVM_EXP_NOMMA
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap)
-            mma_kblock(d_tmem, a_lo + tap_off[tap], b_lo0 + static_cast<uint32_t>(tap) * b_step, tap != 0 ? 1u : 0u);
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t ao = a_lo + static_cast<uint32_t>(tap / 3) * wp16 + static_cast<uint32_t>(tap % 3) * row16v;
+              const uint32_t bo = b_base + static_cast<uint32_t>(tap) * bstep;
+              mma(d_tmem, ao, bo, tap != 0 ? 1u : 0u);
+              mma(d_tmem, ao + 2, bo + 2, 1u);
+              if (widev) {
+                mma(d_tmem, ao + 4, bo + 4, 1u);
+                mma(d_tmem, ao + 6, bo + 6, 1u);
+              }
+            }
 #endif
+            umma_commit(&tfull_bar[a2]);
+            if (++a2 == p.nacc) a2 = 0;
+          }
           umma_commit(&empty_bar[stage]);
-          umma_commit(&tfull_bar[acc]);
+#ifdef IEVM_EXP_TIMING
+          tm_wait_a += clock64() - ti0;      // halo mode: slot 1 = cycles inside the issue region (tempty waits are in slot 2)
+#endif
         }
         __syncwarp();
+        {
+          const int adv = acc + ns;
+          acc_phase ^= (adv >= p.nacc) ? 1u : 0u;
+          acc = adv >= p.nacc ? adv - p.nacc : adv;
+        }
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
         }
-      } else {
-        for (int kb = 0; kb < num_kb; ++kb) {
+        t += ns;
+        s0 += ns;
+        if (s0 == p.subs_per_img) s0 = 0;
+      }
+    } else {
+      const int G = p.kb_group;
+      const int groups_per_tile = num_kb / G;
+      for (int tile = tile_first; leader && tile < total_tiles; tile += tile_step) {   // the peer CTA issues no MMAs
+        IEVM_TIMED_WAIT(tm_wait_a, &tempty_bar[acc], acc_phase ^ 1u, 0x200u | acc, p.stuck_flag);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
+        for (int kg = 0; kg < groups_per_tile; ++kg) {
           IEVM_TIMED_WAIT(tm_wait_b, &full_bar[stage], phase, 0x300u | stage, p.stuck_flag);
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage) * a_step;
-          const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(p.resident_b ? kb : stage) * b_step;
           if (elect_one()) {
-            mma_kblock(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
+            for (int g = 0; g < G; ++g) {
+              const int kb = kg * G + g;
+              const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(stage * G + g) * a_step;
+              const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(p.resident_b ? kb : stage * G + g) * b_step;
+              mma_kblock(d_tmem, a_lo, b_lo, kb != 0 ? 1u : 0u);
+            }
             if (kCluster > 1) {
               umma_commit_pair(&empty_bar[stage]);          // frees the stage in both CTAs
-              if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[acc]);
+              if (kg == groups_per_tile - 1) umma_commit_pair(&tfull_bar[acc]);
             } else {
-              umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
-              if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+              umma_commit(&empty_bar[stage]);               // smem slots reusable once these MMAs retire
+              if (kg == groups_per_tile - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
             }
           }
           __syncwarp();
@@ -673,13 +740,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             phase ^= 1u;
           }
         }
-      }
-      if (++acc == p.nacc) {
-        acc = 0;
-        acc_phase ^= 1u;
+        if (++acc == p.nacc) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
     }
 #ifdef IEVM_EXP_TIMING
+    for (int o = 16; o > 0; o >>= 1) {      // the issue-region timer lives in the elected lane
+      const long long other = __shfl_xor_sync(0xffffffffu, tm_wait_a, o);
+      tm_wait_a = other > tm_wait_a ? other : tm_wait_a;
+    }
     if (lane == 0 && blockIdx.x < kExpCtas) {
       tm_out[0] = clock64() - tm_t0;
       tm_out[1] = tm_wait_a;
@@ -716,39 +787,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     k.c2_add = -kRoundMagicBits;
     k.c2_max = 255 - p.add_zp;
     k.zp4 = static_cast<uint32_t>(p.add_zp) * 0x01010101u;
-    int acc_next = 0, seq = 0;
-    uint32_t acc_phase_next = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++seq) {
-      const int acc = acc_next;
-      const uint32_t acc_phase = acc_phase_next;
-      if (++acc_next == p.nacc) {
-        acc_next = 0;
-        acc_phase_next ^= 1u;
-      }
-      if ((seq & (groups - 1)) != group) continue;
-#ifdef IEVM_EXP_TIMING
-      ++tm_tiles;
-#endif
-      int m, n0;
-      bool valid;
-      if (kMode == kModeHalo) {
-        // warp-uniform divisions for the tile's first position, then a short walk to this thread's row
-        const int img = fast_div(tile, p.tiles_per_img, p.tpi_magic);
-        const int pos = (tile - img * p.tiles_per_img) * kTileM + row;
-        const int oy = fast_div(pos, p.wp, p.wp_magic);
-        const int x = pos - oy * p.wp;
-        valid = x < p.w_in && oy < p.h_in;
-        m = (img * p.h_in + oy) * p.w_in + x;
-        n0 = 0;
-      } else {
-        const int m_group = tile / p.n_tiles;
-        const int n_tile = tile - m_group * p.n_tiles;
-        const int m_tile = kCluster > 1 ? m_group * kCluster + static_cast<int>(crank) : m_group;
-        m = m_tile * kTileM + row;
-        valid = m < p.m_total;
-        n0 = n_tile * p.bn;
-      }
-      constexpr bool kResI8 = kHasRes && kDtype == kDtypeI8;
+    // this thread's place inside a halo sub-tile (fixed: sub-tiles are row aligned)
+    const int sub_row = kMode == kModeHalo ? fast_div(row, p.wp, p.wp_magic) : 0;
+    const int sub_x = row - sub_row * p.wp;
+    const bool sub_ok = kMode == kModeHalo && row < p.sub_pos && sub_x < p.w_in;
+    constexpr bool kResI8 = kHasRes && kDtype == kDtypeI8;
+    // One tile (accumulator buffer `acc`) of output rows starting at pixel index m (valid = this thread's row exists).
+    auto drain = [&](int acc, uint32_t acc_phase, int m, bool valid, int n0) {
       uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
       int c = sub;
       if (kResI8 && c < nchunks) ra = load_res16_i8(p, m, valid, n0 + c * 16);   // does not depend on the MMA
@@ -785,6 +830,91 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (lane == 0) {
         if (kCluster > 1 && !leader) mbar_arrive_remote(&tempty_bar[acc], 0u);   // the leader's MMA warp waits for both
         else mbar_arrive(&tempty_bar[acc]);
+      }
+    };
+    // The same for a statically shaped halo layer: one warp per quadrant owns the tile (four groups), the chunk loop is
+    // unrolled and the per-channel tables are constant-bank operands (ConvTcParams::epc0 / epc1).
+    auto drain_static = [&](int acc, uint32_t acc_phase, int m, bool valid) {
+      constexpr int kNch = kShape != 0 ? halo_shape_bn(kShape) / 16 : 1;
+      uint4 rr[2];
+      rr[0] = rr[1] = make_uint4(0u, 0u, 0u, 0u);
+      if (kResI8) rr[0] = load_res16_i8(p, m, valid, 0);
+      IEVM_TIMED_WAIT(tm_wait_a, &tfull_bar[acc], acc_phase, 0x400u | acc, p.stuck_flag);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(acc * p.acc_stride);
+      uint32_t vv[2][16];
+#ifndef IEVM_EXP_EPI_NONE
+      tmem_ld_32x32b_x16(t_row, vv[0]);
+      if (kNch <= 4) {
+#pragma unroll
+        for (int c = 0; c < kNch; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < kNch) {
+            tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 1) * 16), vv[(c + 1) & 1]);
+            if (kResI8) rr[(c + 1) & 1] = load_res16_i8(p, m, valid, (c + 1) * 16);
+          }
+          epilogue_chunk<kDtype, kHasRes>(p, vv[c & 1], rr[c & 1], m, valid, c * 16, p.epc0, p.epc1, k);
+        }
+      } else {
+        // wide layers: the chunk loop stays a loop over chunk PAIRS (register pressure), the tables are still read from
+        // the constant bank, now through a uniform index
+#pragma unroll 1
+        for (int c = 0; c < kNch; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 1) * 16), vv[1]);
+          if (kResI8) rr[1] = load_res16_i8(p, m, valid, (c + 1) * 16);
+          epilogue_chunk<kDtype, kHasRes>(p, vv[0], rr[0], m, valid, c * 16, p.epc0, p.epc1, k);
+          tmem_ld_wait();
+          if (c + 2 < kNch) {
+            tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 2) * 16), vv[0]);
+            if (kResI8) rr[0] = load_res16_i8(p, m, valid, (c + 2) * 16);
+          }
+          epilogue_chunk<kDtype, kHasRes>(p, vv[1], rr[1], m, valid, (c + 1) * 16, p.epc0, p.epc1, k);
+        }
+      }
+#endif
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    };
+    if (kMode == kModeHalo) {
+      // group g owns the CTA's tiles g, g + groups, ... ; the accumulator ring position follows from the tile's sequence
+      // number (nacc is a power of two)
+      const int nacc_shift = 31 - __clz(p.nacc);
+      for (int t = t_begin + group; t < t_end; t += groups) {
+        const int seq = t - t_begin;
+        const int acc = seq & (p.nacc - 1);
+        const uint32_t acc_phase = static_cast<uint32_t>(seq >> nacc_shift) & 1u;
+#ifdef IEVM_EXP_TIMING
+        ++tm_tiles;
+#endif
+        const int img = fast_div(t, p.subs_per_img, p.spi_magic);
+        const int oy = (t - img * p.subs_per_img) * p.sub_rows + sub_row;
+        const bool valid = sub_ok && oy < p.h_in;
+        const int m = (img * p.h_in + oy) * p.w_in + sub_x;
+        if (kShape != 0) drain_static(acc, acc_phase, m, valid);
+        else drain(acc, acc_phase, m, valid, 0);
+      }
+    } else {
+      int acc_next = 0, seq = 0;
+      uint32_t acc_phase_next = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++seq) {
+        const int acc = acc_next;
+        const uint32_t acc_phase = acc_phase_next;
+        if (++acc_next == p.nacc) {
+          acc_next = 0;
+          acc_phase_next ^= 1u;
+        }
+        if ((seq & (groups - 1)) != group) continue;
+#ifdef IEVM_EXP_TIMING
+        ++tm_tiles;
+#endif
+        const int m_group = tile / p.n_tiles;
+        const int n_tile = tile - m_group * p.n_tiles;
+        const int m_tile = kCluster > 1 ? m_group * kCluster + static_cast<int>(crank) : m_group;
+        const int m = m_tile * kTileM + row;
+        drain(acc, acc_phase, m, m < p.m_total, n_tile * p.bn);
       }
     }
   }

@@ -21,9 +21,7 @@
 #include "conv_tc.cuh"
 #include "simt_kernels.cuh"
 #include "stem_tc.cuh"
-#include "frontend_fused.cuh"
 #include "frontend_v2.cuh"
-#include "conv_wt.cuh"
 #include "observe.cuh"
 
 namespace {
@@ -136,13 +134,11 @@ struct LayerPlan {
   int stages = 0, tmem_cols = 0, resident_b = 0;
   int mode = 0;                 // kModeIm2col | kModeHalo
   int fast_round = 0;           // see ConvTcParams::fast_round
-  // weights-stationary kernel (conv_wt.cuh) for narrow 3x3 stride-1 INT8 layers
-  int wt = 0, wt_stages = 0, wt_stage_bytes = 0, wt_tx_bytes = 0;
-  void* w_wt = nullptr;         // [128][768] weight operand (two output rows stacked in M)
-  CUtensorMap tmap_wt;
   int cluster = 1;              // CTAs per cluster sharing the weight tile by TMA multicast
   int max_clusters = 0;         // co-resident clusters the device can hold (cluster > 1)
-  int wp = 0, patch_rows = 0, tiles_per_img = 0, a_stage_bytes = 0, a_tx_bytes = 0;
+  int wp = 0, patch_rows = 0, a_stage_bytes = 0, a_tx_bytes = 0;
+  int sub_rows = 0, subs_per_img = 0, band_subs = 0;   // halo (band) mode, conv_tc.cuh
+  int kb_group = 1;             // im2col mode: k-blocks per barrier pair
   size_t smem_bytes = 0;
   // device operands
   void* w_packed = nullptr;     // tensor-core layout [cout_pad][taps][cin_w]
@@ -154,6 +150,7 @@ struct LayerPlan {
   size_t stem_smem = 0;
   float* ep0 = nullptr;
   float* ep1 = nullptr;
+  std::vector<float> ep0_host, ep1_host;   // copies for the kernel-parameter block (ConvTcParams::epc0 / epc1)
   CUtensorMap tmap_a, tmap_b;
 };
 
@@ -167,11 +164,7 @@ struct ievm_handle {
   int num_sms = 0;
   int smem_optin = 0;
   int opt_halo = 1;        // IEVM_HALO=0 disables the halo-patch mode (all convs use per-tap im2col TMA)
-  int opt_halo_rb128 = 0;
   int opt_fused_front = 1; // IEVM_FUSED_FRONT=0: separate quantize / stem / maxpool kernels
-  int opt_wt = 0;          // IEVM_WT=1: narrow 3x3 layers use the weights-stationary kernel of conv_wt.cuh (experiment:
-                           // correct, but slower than conv_tc.cuh -- see the header of conv_wt.cuh)
-  int opt_front_v2 = 1;    // IEVM_FRONT_V2=0: first-generation fused front end (INT8) / separate kernels (FP16)
   int front2_ok = 0;       // the network's front end fits frontend_v2.cuh (224-wide input, <= 64 stem channels)
   int front_tpu = 0;       // IEVM_FRONT_TPU: pooled rows per work unit (0 = heuristic)
   uint8_t* lut_dev = nullptr;   // u8 input mode: [3][256] level -> quantised value (ievm_set_input_lut)
@@ -184,7 +177,6 @@ struct ievm_handle {
   uint8_t* rs_tmp = nullptr;    // [max_batch][rs_in_h][in_w][3]
   uint8_t* rs_out = nullptr;    // [max_batch][in_h][in_w][3]
   size_t stage_in_bytes = 0;
-  size_t fe_smem = 0;
   int opt_cluster = 1;     // IEVM_CLUSTER=0: no 2-CTA clusters / weight multicast
   int opt_pdl = 1;         // IEVM_PDL=0: no programmatic dependent launch
   int opt_fixed_bn = 0;    // IEVM_FIXED_BN=1: one N tile per <=256 channels (disables the tile-width heuristic)
@@ -345,43 +337,64 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
       if (tr.h != L.ho || tr.w != L.wo || tr.c != d.cout || tr.pitch != L.cout_pad)
         return fail(IEVM_ERR_BAD_ARG, "layer %d: residual shape mismatch", i);
     }
-    if (h->opt_wt && h->dtype == IEVM_DTYPE_I8 && d.ksize == 3 && d.stride == 1 && d.pad == 1 && L.cin_pitch == 64 &&
-        L.cout_pad == 64 && L.h % 2 == 0 && L.w + 2 <= 64 && L.w >= 4) {
-      const int wp = L.w + 2;
-      L.wt = 1;
-      L.wt_tx_bytes = 4 * wp * 64;
-      L.wt_stage_bytes = round_up((3 * wp + 2 + 64) * 64, 1024);     // the last taps' views run past the patch (junk columns)
-      L.wt_stages = std::min(kWtMaxStages, (h->smem_optin - 2048) / L.wt_stage_bytes);
-      if (L.wt_stages < 2) L.wt = 0;
-    }
     const int row_bytes = L.cin_pitch * h->elem;
     constexpr int kMaxStages = 16;
     const int fixed = 1024 /*alignment slack*/ + 2 * L.cout_pad * 4 + (2 * kMaxStages + 2 * kMaxAcc + 1) * 8 + 16;
     const int avail = h->smem_optin - fixed;
     L.tmem_cols = 32;
     while (L.tmem_cols < 2 * L.bn) L.tmem_cols *= 2;
-    // ---- halo mode: 3x3 stride-1 convs whose pixel fits one shared-memory row, weights resident ----
-    if (h->opt_halo && d.ksize == 3 && d.stride == 1 && d.pad == 1 && L.n_tiles == 1 && row_bytes <= 128) {
-      const int rb = (row_bytes <= 64 && !h->opt_halo_rb128) ? 64 : 128;
+    // ---- halo (band) mode: 3x3 stride-1 convs whose pixel fits one shared-memory row, weights resident ----
+    if (h->opt_halo && d.ksize == 3 && d.stride == 1 && d.pad == 1 && L.n_tiles == 1 && row_bytes <= 128 && L.w + 2 <= kTileM) {
+      const int rb = row_bytes <= 64 ? 64 : 128;
       const int wp = L.w + 2;
-      const int patch_rows = (wp + 126) / wp + 3;
-      const int a_tx = patch_rows * wp * rb;
-      const int a_stage = round_up(a_tx + wp * rb, 1024);
+      const int R = kTileM / wp;                        // whole output rows per sub-tile (row aligned)
+      const int T = (L.h + R - 1) / R;
+      int acc_stride = 32;
+      while (acc_stride < L.bn) acc_stride *= 2;
+      const int nacc = std::max(2, std::min(kMaxAcc, 512 / acc_stride));
       const int b_all = 9 * L.bn * rb;
-      if (b_all + 2 * a_stage <= avail && wp <= 256) {
+      // largest band (sub-tiles per patch) that leaves the epilogue half of the accumulator ring and >= 2 patch stages
+      int best_s = 0, best_stages = 0, best_stage_bytes = 0;
+      for (int S = std::min({kMaxBandSubs, nacc / 2 > 0 ? nacc / 2 : 1, T}); S >= 1; --S) {
+        const int a_tx = (S * R + 2) * wp * rb;
+        const int a_stage = round_up(a_tx, 1024);
+        // the last sub-tile's tap views run up to (130 - R * wp) rows past the patch: keep that much behind the last stage
+        const int slack = round_up((130 - R * wp > 0 ? 130 - R * wp : 0) * rb, 1024);
+        const int stages = std::min(8, (avail - b_all - slack) / a_stage);
+        if (stages >= 2) {
+          best_s = S;
+          best_stages = stages;
+          best_stage_bytes = a_stage;
+          break;
+        }
+      }
+      if (const char* e = getenv("IEVM_BAND_SUBS")) {     // diagnostics: force the band size
+        const int S = std::max(1, std::min({atoi(e), kMaxBandSubs, nacc, T}));
+        const int a_stage = round_up((S * R + 2) * wp * rb, 1024);
+        const int stages = std::min(8, (avail - b_all - 2048) / a_stage);
+        if (stages >= 2) {
+          best_s = S;
+          best_stages = stages;
+          best_stage_bytes = a_stage;
+        }
+      }
+      if (best_s > 0) {
         L.mode = kModeHalo;
         L.kc_bytes = rb;
         L.kc_elems = rb / h->elem;
         L.kchunks = 1;
         L.cin_w = L.kc_elems;
         L.wp = wp;
-        L.patch_rows = patch_rows;
-        L.a_tx_bytes = a_tx;
-        L.a_stage_bytes = a_stage;
-        L.tiles_per_img = (L.h * wp + kTileM - 1) / kTileM;
+        L.sub_rows = R;
+        L.subs_per_img = T;
+        L.band_subs = best_s;
+        L.patch_rows = best_s * R + 2;
+        L.a_tx_bytes = L.patch_rows * wp * rb;
+        L.a_stage_bytes = best_stage_bytes;
         L.resident_b = 1;
-        L.stages = std::min(8, (avail - b_all) / a_stage);
-        L.smem_bytes = static_cast<size_t>(L.stages) * a_stage + b_all + fixed;
+        L.stages = best_stages;
+        L.kb_group = 1;
+        L.smem_bytes = static_cast<size_t>(L.stages) * best_stage_bytes + b_all + 2048 + fixed;
         continue;
       }
     }
@@ -441,8 +454,26 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
     if (L.resident_b) L.stages = std::min(kMaxStages, (avail - num_kb * b_bytes) / a_bytes);
     else L.stages = std::min(kMaxStages, avail / (a_bytes + b_bytes));
     if (L.stages < 2) return fail(IEVM_ERR_UNSUPPORTED, "layer %d: tile does not fit in shared memory", i);
-    L.smem_bytes = static_cast<size_t>(L.stages) * a_bytes +
-                   static_cast<size_t>(L.resident_b ? num_kb : L.stages) * b_bytes + fixed;
+    // k-blocks per barrier pair: every mbarrier test by the MMA-issuing thread idles the tensor pipe for ~150 cycles
+    // (conv_tc.cuh), so a stage is a GROUP of k-blocks -- the largest divisor of the k-block count (<= 4) that still
+    // leaves three groups in flight
+    {
+      const int slots = L.stages;
+      int G = 1;
+      for (int g = 4; g >= 2; --g)
+        if (num_kb % g == 0 && slots / g >= 3) {
+          G = g;
+          break;
+        }
+      if (const char* e = getenv("IEVM_KB_GROUP")) {
+        const int g = atoi(e);
+        if (g >= 1 && num_kb % g == 0 && slots / g >= 2) G = g;
+      }
+      L.kb_group = G;
+      L.stages = slots / G;
+    }
+    L.smem_bytes = static_cast<size_t>(L.stages) * L.kb_group * a_bytes +
+                   static_cast<size_t>(L.resident_b ? num_kb : L.stages * L.kb_group) * b_bytes + fixed;
   }
   return IEVM_OK;
 }
@@ -480,6 +511,8 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
   }
   if (int rc = dev_upload(h, ep0, &L.ep0)) return rc;
   if (int rc = dev_upload(h, ep1, &L.ep1)) return rc;
+  L.ep0_host = ep0;
+  L.ep1_host = ep1;
 
   if (L.is_stem) {
     if (L.cout_pad == 64 && h->in_w == kF2W && h->in_h % 4 == 0 && h->in_h >= 8) {
@@ -549,20 +582,6 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
     int8_t* dw = nullptr;
     if (int rc = dev_upload(h, wp, &dw)) return rc;
     L.w_packed = dw;
-    if (L.wt) {
-      // lane m = 64 * r + co (r = parity of the output row), K = (dy * 3 + kx) * 64 + ci, filter row ky = dy - r
-      std::vector<int8_t> wt(static_cast<size_t>(128) * kWtKSteps * 32, 0);
-      for (int r = 0; r < 2; ++r)
-        for (int co = 0; co < d.cout; ++co)
-          for (int ky = 0; ky < 3; ++ky)
-            for (int kx = 0; kx < 3; ++kx)
-              for (int ci = 0; ci < d.cin; ++ci)
-                wt[static_cast<size_t>(64 * r + co) * (kWtKSteps * 32) + ((ky + r) * 3 + kx) * 64 + ci] =
-                    w[(static_cast<size_t>(co) * d.cin + ci) * 9 + ky * 3 + kx];
-      int8_t* dwt = nullptr;
-      if (int rc = dev_upload(h, wt, &dwt)) return rc;
-      L.w_wt = dwt;
-    }
   } else {
     const uint16_t* w = static_cast<const uint16_t*>(d.weight);
     std::vector<uint16_t> wp(static_cast<size_t>(L.cout_pad) * k_total, 0);
@@ -656,7 +675,6 @@ int upload_head_operands(ievm_handle* h, LayerPlan& L) {
 // Workspace: greedy buffer reuse by liveness (or one buffer per tensor with keep_tensors)
 // ----------------------------------------------------------------------------------------------
 bool front_end_is_chunked(const ievm_handle* h);
-bool front_end_is_fused(const ievm_handle* h);
 bool front_end_is_v2(const ievm_handle* h);
 
 int assign_buffers(ievm_handle* h) {
@@ -738,16 +756,6 @@ int encode_maps(ievm_handle* h) {
     if (L.d.op != IEVM_OP_CONV || L.is_stem) continue;
     const CUtensorMapSwizzle sw = L.kc_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const size_t e = h->elem;
-    if (L.wt) {      // conv_wt.cuh: the 4 x (W+2) x 64 B input patch of a row pair
-      cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(L.w), static_cast<cuuint64_t>(L.h), static_cast<cuuint64_t>(h->max_batch)};
-      cuuint64_t strides[3] = {64, static_cast<cuuint64_t>(L.w) * 64, static_cast<cuuint64_t>(L.h) * L.w * 64};
-      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(L.w + 2), 4, 1};
-      cuuint32_t estr[4] = {1, 1, 1, 1};
-      const CUresult r = g_encode_tiled(&L.tmap_wt, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, tensor_ptr(h, L.d.in_tensor), dims, strides,
-                                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled (row-pair patch) failed for layer %zu: CUresult %d", i, (int)r);
-    }
     if (L.mode == kModeHalo) {
       cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cin_pitch), static_cast<cuuint64_t>(L.w),
                             static_cast<cuuint64_t>(L.h), static_cast<cuuint64_t>(h->max_batch)};
@@ -810,22 +818,26 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   p.kc_elems = L.kc_elems;
   p.bn = L.bn;
   p.n_tiles = L.n_tiles;
-  p.m_tiles = L.mode == kModeHalo ? n * L.tiles_per_img : (p.m_total + kTileM - 1) / kTileM;
+  p.m_tiles = L.mode == kModeHalo ? n * L.subs_per_img : (p.m_total + kTileM - 1) / kTileM;
   p.stages = L.stages;
   p.resident_b = L.resident_b;
   p.a_stage_bytes = L.a_stage_bytes;
   p.a_tx_bytes = L.a_tx_bytes;
+  p.kb_group = L.kb_group;
   p.h_in = L.h;
   p.w_in = L.w;
   p.wp = L.wp;
-  p.tiles_per_img = L.tiles_per_img;
+  p.sub_rows = L.sub_rows;
+  p.sub_pos = L.sub_rows * L.wp;
+  p.subs_per_img = L.subs_per_img;
+  p.band_subs = L.band_subs;
+  p.total_subs = n * L.subs_per_img;
   // magic(d, n_max): ceil(2^32 / d) when every dividend n <= n_max satisfies n * d < 2^32, else 0 (plain division)
   auto magic = [](long long d, long long n_max) {
     return (d > 1 && n_max * d < 0x100000000ll) ? static_cast<uint32_t>((0x100000000ull + d - 1) / d) : 0u;
   };
-  const long long tiles_max = L.mode == kModeHalo ? static_cast<long long>(n) * L.tiles_per_img : 0;
-  p.tpi_magic = magic(L.tiles_per_img, tiles_max);
-  p.wp_magic = magic(L.wp, static_cast<long long>(L.tiles_per_img) * kTileM + kTileM);
+  p.spi_magic = magic(L.subs_per_img, static_cast<long long>(n) * L.subs_per_img);
+  p.wp_magic = magic(L.wp, kTileM);
   p.hw_magic = magic(static_cast<long long>(L.ho) * L.wo, static_cast<long long>(p.m_total) + 4 * kTileM);
   p.wo_magic = magic(L.wo, static_cast<long long>(L.ho) * L.wo);
   p.cout_pad = L.cout_pad;
@@ -854,11 +866,12 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   p.dump_acc = dump_acc;
   p.dump_pitch = L.cout_pad;
   p.stuck_flag = h->stuck_dev;
+  if (L.cout_pad <= kEpConst && !L.ep0_host.empty()) {
+    memcpy(p.epc0, L.ep0_host.data(), L.cout_pad * sizeof(float));
+    memcpy(p.epc1, L.ep1_host.data(), L.cout_pad * sizeof(float));
+  }
 #ifdef IEVM_EXP_TIMING
   p.timing_slot = static_cast<int>(&L - h->layers.data()) % kExpSlots;
-#endif
-#ifdef IEVM_EXP_HALFK
-  p.half_k = (L.mode == kModeHalo && L.kc_bytes == 128 && L.cin_pitch * h->elem <= 64) ? 1 : 0;
 #endif
   return p;
 }
@@ -883,52 +896,29 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
     return IEVM_OK;
   }
   const bool has_res = p.res != nullptr;
-  if (L.wt && dump_acc == nullptr) {
-    ConvWtParams q;
-    memset(&q, 0, sizeof(q));
-    q.n = n; q.h = L.h; q.w = L.w; q.wp = L.w + 2;
-    q.tiles_per_img = L.h / 2;
-    q.tiles = n * q.tiles_per_img;
-    q.tpi_magic = (q.tiles_per_img > 1 && static_cast<long long>(q.tiles) * q.tiles_per_img < 0x100000000ll)
-                      ? static_cast<uint32_t>((0x100000000ull + q.tiles_per_img - 1) / q.tiles_per_img) : 0u;
-    q.stages = L.wt_stages; q.stage_bytes = L.wt_stage_bytes; q.tx_bytes = L.wt_tx_bytes;
-    q.cols_per_warp = (L.w + 3) / 4;
-    q.idesc = make_idesc_i8_s8u8(64, 128);
-    q.wpack = static_cast<const uint8_t*>(L.w_wt);
-    q.out = static_cast<uint8_t*>(p.out);
-    q.res = static_cast<const uint8_t*>(p.res);
-    q.ep0 = L.ep0; q.ep1 = L.ep1;
-    q.out_zp = p.out_zp; q.out_lo = p.out_lo;
-    q.a_scale = p.a_scale; q.res_scale = p.res_scale; q.inv_add_scale = p.inv_add_scale;
-    q.res_zp = p.res_zp; q.add_zp = p.add_zp;
-    q.fast_round = L.fast_round;
-    q.stuck_flag = h->stuck_dev;
-    const unsigned wgrid = static_cast<unsigned>(std::min(q.tiles, h->num_sms));
-    const size_t wsmem = 1024 + static_cast<size_t>(q.stages) * q.stage_bytes + (2 * kWtMaxStages + 2 * kWtAcc) * 8 + 16;
-    if (has_res) CUDA_TRY(launch_kernel(conv_wt_kernel<true>, wgrid, kWtThreads, wsmem, s, h->opt_pdl != 0, L.tmap_wt, q));
-    else CUDA_TRY(launch_kernel(conv_wt_kernel<false>, wgrid, kWtThreads, wsmem, s, h->opt_pdl != 0, L.tmap_wt, q));
-    CUDA_TRY(cudaGetLastError());
-    return IEVM_OK;
-  }
   const unsigned cl = static_cast<unsigned>(L.cluster);
   int grid = std::min(p.m_tiles * p.n_tiles, h->num_sms);
   if (cl > 1) {
     const int cluster_tiles = ((p.m_tiles + L.cluster - 1) / L.cluster) * p.n_tiles;
     grid = std::min(cluster_tiles, L.max_clusters > 0 ? L.max_clusters : h->num_sms / L.cluster) * L.cluster;
   }
-#define IEVM_LAUNCH(DT, RES, MODE, CL) \
-  CUDA_TRY(launch_kernel_cluster(conv_tc_kernel<DT, RES, MODE, CL>, grid, kConvThreads, L.smem_bytes, s, h->opt_pdl != 0, \
+#define IEVM_LAUNCH(DT, RES, MODE, CL, SH) \
+  CUDA_TRY(launch_kernel_cluster(conv_tc_kernel<DT, RES, MODE, CL, SH>, grid, kConvThreads, L.smem_bytes, s, h->opt_pdl != 0, \
                                  static_cast<unsigned>(CL), L.tmap_a, L.tmap_b, p))
-#define IEVM_LAUNCH_MODE(DT, RES)                                        \
-  do {                                                                   \
-    if (L.mode == kModeHalo) IEVM_LAUNCH(DT, RES, kModeHalo, 1);         \
-    else if (cl == 2) IEVM_LAUNCH(DT, RES, kModeIm2col, 2);              \
-    else IEVM_LAUNCH(DT, RES, kModeIm2col, 1);                           \
+#define IEVM_LAUNCH_MODE(DT, RES, SH_A, SH_B)                              \
+  do {                                                                     \
+    if (L.mode == kModeHalo) {                                             \
+      if (shape == SH_A) IEVM_LAUNCH(DT, RES, kModeHalo, 1, SH_A);         \
+      else if (shape == SH_B) IEVM_LAUNCH(DT, RES, kModeHalo, 1, SH_B);    \
+      else IEVM_LAUNCH(DT, RES, kModeHalo, 1, 0);                          \
+    } else if (cl == 2) IEVM_LAUNCH(DT, RES, kModeIm2col, 2, 0);           \
+    else IEVM_LAUNCH(DT, RES, kModeIm2col, 1, 0);                          \
   } while (0)
+  const int shape = L.mode == kModeHalo ? halo_shape_class(L.wp, L.kc_bytes, L.bn) : 0;
   if (h->dtype == IEVM_DTYPE_I8) {
-    if (has_res) IEVM_LAUNCH_MODE(kDtypeI8, true); else IEVM_LAUNCH_MODE(kDtypeI8, false);
+    if (has_res) IEVM_LAUNCH_MODE(kDtypeI8, true, 1, 2); else IEVM_LAUNCH_MODE(kDtypeI8, false, 1, 2);
   } else {
-    if (has_res) IEVM_LAUNCH_MODE(kDtypeF16, true); else IEVM_LAUNCH_MODE(kDtypeF16, false);
+    if (has_res) IEVM_LAUNCH_MODE(kDtypeF16, true, 3, 3); else IEVM_LAUNCH_MODE(kDtypeF16, false, 3, 3);
   }
 #undef IEVM_LAUNCH_MODE
 #undef IEVM_LAUNCH
@@ -1012,10 +1002,9 @@ int launch_maxpool(ievm_handle* h, const LayerPlan& L, const void* in, void* out
 // small reused buffers: the stem's 112x112xC output (the largest tensor of the net, 0.8 MB/image)
 // is produced and consumed inside L2 and, because every chunk overwrites the same lines, never has
 // to be written back to HBM.
-// quantize + stem + maxpool in one kernel (frontend_fused.cuh): INT8, tensor-core path, no parity hooks.
 // Second-generation fused front end (frontend_v2.cuh): INT8 and FP16, 224-wide inputs, <= 64 stem channels.
 bool front_end_is_v2(const ievm_handle* h) {
-  return h->front2_ok && h->opt_front_v2 && h->opt_fused_front && h->conv_impl == 0 && !h->keep_tensors &&
+  return h->front2_ok && h->opt_fused_front && h->conv_impl == 0 && !h->keep_tensors &&
          h->layers.size() >= 2 && h->layers[0].is_stem && h->layers[0].w_front2 != nullptr &&
          h->layers[1].d.op == IEVM_OP_MAXPOOL && h->layers[1].d.in_tensor == h->layers[0].d.out_tensor &&
          h->tensors[h->layers[0].d.out_tensor].last_use == 1;
@@ -1096,38 +1085,6 @@ int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32
   return IEVM_OK;
 }
 
-bool front_end_is_fused(const ievm_handle* h) {
-  return h->dtype == IEVM_DTYPE_I8 && h->opt_fused_front && h->conv_impl == 0 && !h->keep_tensors &&
-         h->layers.size() >= 2 && h->layers[0].is_stem && h->layers[1].d.op == IEVM_OP_MAXPOOL &&
-         h->layers[1].d.in_tensor == h->layers[0].d.out_tensor && h->tensors[h->layers[0].d.out_tensor].last_use == 1 &&
-         (h->layers[0].cout_pad == 64 || h->layers[0].cout_pad == 128 || h->layers[0].cout_pad == 256);
-}
-
-int launch_frontend_fused(ievm_handle* h, const float* x, int n, cudaStream_t s) {
-  const LayerPlan& Ls = h->layers[0];
-  const LayerPlan& Lp = h->layers[1];
-  FrontendParams fp;
-  memset(&fp, 0, sizeof(fp));
-  fp.n = n; fp.h = Ls.h; fp.w = Ls.w; fp.ho = Ls.ho; fp.wo = Ls.wo; fp.ph = Lp.ho; fp.pw = Lp.wo;
-  fp.strips = (fp.pw + 6) / 7;
-  fp.tiles_per_strip = (fp.ho + 7) / 8;
-  fp.cpad = Ls.cout_pad;
-  fp.in_zp = h->in_zp;
-  fp.inv_scale = 1.0f / h->in_scale;
-  fp.tmem_cols = Ls.tmem_cols;
-  fp.acc_stride = Ls.tmem_cols / 2;
-  fp.idesc = make_idesc_i8_u8s8(Ls.cout_pad);
-  fp.x = x;
-  fp.out = static_cast<uint8_t*>(tensor_ptr(h, Lp.d.out_tensor));
-  fp.bdiv = Ls.ep0; fp.mult = Ls.ep1; fp.zwsum = Ls.zwsum;
-  fp.out_zp = Ls.d.out_zp; fp.out_lo = Ls.d.relu ? Ls.d.out_zp : 0;
-  fp.stuck_flag = h->stuck_dev;
-  const int grid = std::min(n * fp.strips, h->num_sms);
-  frontend_fused_kernel<<<grid, kFeThreads, h->fe_smem, s>>>(Ls.tmap_b, fp);
-  CUDA_TRY(cudaGetLastError());
-  return IEVM_OK;
-}
-
 bool front_end_is_chunked(const ievm_handle* h) {
   return h->dtype == IEVM_DTYPE_I8 && h->front_chunk > 0 && !h->keep_tensors && h->layers.size() >= 2 &&
          h->layers[0].is_stem && h->layers[1].d.op == IEVM_OP_MAXPOOL &&
@@ -1187,12 +1144,6 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     // profile slots: the fused kernel is attributed to the stem's slot (quantize and maxpool read 0)
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
     if (int rc = launch_frontend2(h, x, n, s, nullptr, u8_input)) return rc;
-    if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[2], s));
-    first_layer = 2;
-  } else if (front_end_is_fused(h)) {
-    // profile slots: the fused kernel is attributed to the stem's slot (quantize and maxpool read 0)
-    if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
-    if (int rc = launch_frontend_fused(h, static_cast<const float*>(x), n, s)) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[2], s));
     first_layer = 2;
   } else if (front_end_is_chunked(h)) {
@@ -1390,15 +1341,12 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   h->in_c = nd->in_c; h->in_h = nd->in_h; h->in_w = nd->in_w; h->classes = nd->num_classes;
   h->in_scale = nd->in_scale; h->in_zp = nd->in_zp;
   if (const char* e = getenv("IEVM_HALO")) h->opt_halo = atoi(e);
-  if (const char* e = getenv("IEVM_HALO_RB128")) h->opt_halo_rb128 = atoi(e);
   if (const char* e = getenv("IEVM_FIXED_BN")) h->opt_fixed_bn = atoi(e);
   if (const char* e = getenv("IEVM_PDL")) h->opt_pdl = atoi(e);
   if (const char* e = getenv("IEVM_CLUSTER")) h->opt_cluster = atoi(e);
   if (const char* e = getenv("IEVM_HOST_CHUNK")) h->host_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
   if (const char* e = getenv("IEVM_FRONT_CHUNK")) h->front_chunk = atoi(e);
-  if (const char* e = getenv("IEVM_FRONT_V2")) h->opt_front_v2 = atoi(e);
-  if (const char* e = getenv("IEVM_WT")) h->opt_wt = atoi(e);
   if (const char* e = getenv("IEVM_FRONT_TPU")) h->front_tpu = atoi(e);
   int rc = plan_shapes(h, nd);
   for (size_t i = 0; rc == IEVM_OK && i < h->layers.size(); ++i) {
@@ -1412,9 +1360,9 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
     for (size_t i = 0; i < h->layers.size(); ++i) {
       const LayerPlan& L = h->layers[i];
       if (L.d.op != IEVM_OP_CONV || L.is_stem) continue;
-      fprintf(stderr, "[ievm] layer %2zu %dx%d s%d %4d->%4d @%dx%d mode=%s kc=%d kchunks=%d bn=%d n_tiles=%d cluster=%d stages=%d residentB=%d fast_round=%d wt=%d smem=%zu\n",
+      fprintf(stderr, "[ievm] layer %2zu %dx%d s%d %4d->%4d @%dx%d mode=%s kc=%d kchunks=%d bn=%d n_tiles=%d cluster=%d stages=%d kb_group=%d band=%dx%d rows residentB=%d fast_round=%d smem=%zu\n",
               i, L.d.ksize, L.d.ksize, L.d.stride, L.d.cin, L.d.cout, L.ho, L.wo, L.mode == kModeHalo ? "halo" : "im2col",
-              L.kc_bytes, L.kchunks, L.bn, L.n_tiles, L.cluster, L.stages, L.resident_b, L.fast_round, L.wt, L.smem_bytes);
+              L.kc_bytes, L.kchunks, L.bn, L.n_tiles, L.cluster, L.stages, L.kb_group, L.band_subs, L.sub_rows, L.resident_b, L.fast_round, L.smem_bytes);
     }
   }
   if (rc == IEVM_OK) rc = assign_buffers(h);
@@ -1428,17 +1376,18 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
       // function attributes are process-wide: always raise the limit to the device maximum so that several
       // engines with different plans can coexist
       const int ms = static_cast<int>(prop.sharedMemPerBlockOptin);
-#define IEVM_ATTR(DT, RES, MODE, CL) \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<DT, RES, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms)
-      IEVM_ATTR(kDtypeI8, false, kModeIm2col, 1); IEVM_ATTR(kDtypeI8, true, kModeIm2col, 1);
-      IEVM_ATTR(kDtypeI8, false, kModeIm2col, 2); IEVM_ATTR(kDtypeI8, true, kModeIm2col, 2);
-      IEVM_ATTR(kDtypeI8, false, kModeHalo, 1);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1);
-      IEVM_ATTR(kDtypeF16, false, kModeIm2col, 1); IEVM_ATTR(kDtypeF16, true, kModeIm2col, 1);
-      IEVM_ATTR(kDtypeF16, false, kModeIm2col, 2); IEVM_ATTR(kDtypeF16, true, kModeIm2col, 2);
-      IEVM_ATTR(kDtypeF16, false, kModeHalo, 1);   IEVM_ATTR(kDtypeF16, true, kModeHalo, 1);
+#define IEVM_ATTR(DT, RES, MODE, CL, SH) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<DT, RES, MODE, CL, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms)
+      IEVM_ATTR(kDtypeI8, false, kModeIm2col, 1, 0); IEVM_ATTR(kDtypeI8, true, kModeIm2col, 1, 0);
+      IEVM_ATTR(kDtypeI8, false, kModeIm2col, 2, 0); IEVM_ATTR(kDtypeI8, true, kModeIm2col, 2, 0);
+      IEVM_ATTR(kDtypeI8, false, kModeHalo, 1, 0);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1, 0);
+      IEVM_ATTR(kDtypeI8, false, kModeHalo, 1, 1);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1, 1);
+      IEVM_ATTR(kDtypeI8, false, kModeHalo, 1, 2);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1, 2);
+      IEVM_ATTR(kDtypeF16, false, kModeIm2col, 1, 0); IEVM_ATTR(kDtypeF16, true, kModeIm2col, 1, 0);
+      IEVM_ATTR(kDtypeF16, false, kModeIm2col, 2, 0); IEVM_ATTR(kDtypeF16, true, kModeIm2col, 2, 0);
+      IEVM_ATTR(kDtypeF16, false, kModeHalo, 1, 0);   IEVM_ATTR(kDtypeF16, true, kModeHalo, 1, 0);
+      IEVM_ATTR(kDtypeF16, false, kModeHalo, 1, 3);   IEVM_ATTR(kDtypeF16, true, kModeHalo, 1, 3);
 #undef IEVM_ATTR
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
       if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       // how many 2-CTA clusters of the heaviest configuration can be co-resident (GPC packing may strand SMs)
       for (LayerPlan& L : h->layers) {
@@ -1455,22 +1404,12 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
         cfg.numAttrs = 1;
         int nc = 0;
         const cudaError_t qe = h->dtype == IEVM_DTYPE_I8
-            ? cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<kDtypeI8, false, kModeIm2col, 2>, &cfg)
-            : cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<kDtypeF16, false, kModeIm2col, 2>, &cfg);
+            ? cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<kDtypeI8, false, kModeIm2col, 2, 0>, &cfg)
+            : cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<kDtypeF16, false, kModeIm2col, 2, 0>, &cfg);
         L.max_clusters = (qe == cudaSuccess && nc > 0) ? std::min(nc, h->num_sms / L.cluster) : h->num_sms / L.cluster;
         if (qe != cudaSuccess) cudaGetLastError();
       }
     }
-  }
-  if (rc == IEVM_OK && h->dtype == IEVM_DTYPE_I8 && h->layers[0].is_stem && h->layers[0].cout_pad % 64 == 0) {
-    const int cp = h->layers[0].cout_pad;
-    h->fe_smem = 1024 + static_cast<size_t>(kFeStages) * 2 * kTileM * 128 + 2 * static_cast<size_t>(cp) * 128 +
-                 static_cast<size_t>(kFeRing) * kFeRowBytes + static_cast<size_t>(kFeDepth) * kFeRawBytes +
-                 (2 * 9 + 1) * 16 * static_cast<size_t>(cp) * 4 + 3 * static_cast<size_t>(cp) * 4 +
-                 (2 * kFeStages + 5) * 8 + 16;
-    if (h->fe_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) h->opt_fused_front = 0;
-    else if (cudaFuncSetAttribute(frontend_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) != cudaSuccess)
-      rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend_fused_kernel) failed");
   }
   if (rc == IEVM_OK && h->front2_ok) {
     const cudaError_t e = h->dtype == IEVM_DTYPE_I8
@@ -1866,7 +1805,7 @@ int ievm_tensor_shape(const ievm_handle* h, int id, int32_t out6[6]) {
 int ievm_launches_per_forward(const ievm_handle* h) {
   if (!h) return 0;
   const int n = h->last_n > 0 ? h->last_n : h->max_batch;
-  if (front_end_is_v2(h) || front_end_is_fused(h)) return static_cast<int>(h->layers.size()) - 1;
+  if (front_end_is_v2(h)) return static_cast<int>(h->layers.size()) - 1;
   if (front_end_is_chunked(h)) return 3 * ((n + h->front_chunk - 1) / h->front_chunk) + static_cast<int>(h->layers.size()) - 2;
   return static_cast<int>(h->layers.size()) + (h->dtype == IEVM_DTYPE_I8 ? 1 : 0);
 }

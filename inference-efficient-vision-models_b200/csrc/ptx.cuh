@@ -95,6 +95,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Five barrier tests issued back to back (no dependent instruction in between), true when ALL phases have completed.
+// An mbarrier test is a ~100-150 cycle round trip; issued together they overlap.  Callers repeat a (barrier, parity)
+// pair to pad the list.  No suspend hint: a miss falls back to the blocking waits.
+__device__ __forceinline__ bool mbar_try_wait5(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2, uint32_t p2,
+                                               uint64_t* b3, uint32_t p3, uint64_t* b4, uint32_t p4) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred q0, q1, q2, q3, q4;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 q2, [%5], %6;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 q3, [%7], %8;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 q4, [%9], %10;\n"
+      "and.pred q0, q0, q1;\n"
+      "and.pred q2, q2, q3;\n"
+      "and.pred q0, q0, q2;\n"
+      "and.pred q0, q0, q4;\n"
+      "selp.u32 %0, 1, 0, q0;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(b0)), "r"(p0), "r"(smem_u32(b1)), "r"(p1), "r"(smem_u32(b2)), "r"(p2), "r"(smem_u32(b3)), "r"(p3),
+        "r"(smem_u32(b4)), "r"(p4)
+      : "memory");
+  return ok != 0;
+}
+
 #ifndef IEVM_WAIT_LIMIT_NS
 #define IEVM_WAIT_LIMIT_NS 2000000000ull   // bounded mbarrier waits: a lost arrival must trap, never hang
 #endif

@@ -185,7 +185,7 @@ void run_case(int iters) {
 // SHIFT = 0: every view starts at the patch origin (aligned), 1: as the product; COMMIT = 1: two tcgen05.commit per tile;
 // ZACC = 1: the first instruction of a tile overwrites the accumulator; NBUF accumulators in rotation.
 template <int N, int ROWB, int SHIFT, int COMMIT, int ZACC, int NBUF, int GAP, int WAITERS>
-__global__ void __launch_bounds__(128 + 32 * WAITERS) convlike_kernel(int tiles, unsigned long long* cycles, unsigned int* fail) {
+__global__ void __launch_bounds__(128 + 32 * WAITERS) convlike_kernel(int tiles, int fill, unsigned long long* cycles, unsigned int* fail) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -196,7 +196,11 @@ __global__ void __launch_bounds__(128 + 32 * WAITERS) convlike_kernel(int tiles,
   uint8_t* sB = smem + ((kATile + 1023) / 1024) * 1024;
   uint64_t* bar = reinterpret_cast<uint64_t*>(sB + kBTile);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 8);
-  for (int i = threadIdx.x; i < (((kATile + 1023) / 1024) * 1024 + kBTile) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  for (int i = threadIdx.x; i < (((kATile + 1023) / 1024) * 1024 + kBTile) / 4; i += blockDim.x) {
+    uint32_t v = static_cast<uint32_t>(i) * 2654435761u + blockIdx.x * 40503u;
+    v ^= v >> 15; v *= 2246822519u; v ^= v >> 13;
+    reinterpret_cast<uint32_t*>(smem)[i] = fill == 0 ? 0u : (fill == 1 ? v : (v & 0x3f3f3f3fu));
+  }
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -292,12 +296,12 @@ __global__ void __launch_bounds__(128 + 32 * WAITERS) convlike_kernel(int tiles,
 }
 
 template <int N, int ROWB, int SHIFT, int COMMIT, int ZACC, int NBUF, int GAP = 0, int WAITERS = 0>
-void run_convlike(int tiles) {
+void run_convlike(int tiles, int fill = 0) {
   const int smem = 1024 + ((7 * 58 * ROWB + 1024 + 1023) / 1024) * 1024 + 9 * N * ROWB + 128;
   auto kern = convlike_kernel<N, ROWB, SHIFT, COMMIT, ZACC, NBUF, GAP, WAITERS>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaMemset(d_fail, 0, sizeof(unsigned int));
-  for (int rep = 0; rep < 2; ++rep) kern<<<g_sms, 128 + 32 * WAITERS, smem>>>(tiles, d_cycles, d_fail);
+  for (int rep = 0; rep < 2; ++rep) kern<<<g_sms, 128 + 32 * WAITERS, smem>>>(tiles, fill, d_cycles, d_fail);
   const cudaError_t e = cudaDeviceSynchronize();
   unsigned int failed = 0;
   cudaMemcpy(&failed, d_fail, sizeof(failed), cudaMemcpyDeviceToHost);
@@ -311,7 +315,7 @@ void run_convlike(int tiles) {
   double sum = 0;
   for (auto v : h) sum += static_cast<double>(v);
   const double per_tile = sum / g_sms / tiles;
-  printf("convlike N=%3d rowB=%3d shift=%d commit=%d zacc=%d nbuf=%d gap=%d waiters=%2d | %8.1f clk/tile %7.1f clk/MMA\n", N, ROWB, SHIFT, COMMIT, ZACC,
+  printf("fill=%d convlike N=%3d rowB=%3d shift=%d commit=%d zacc=%d nbuf=%d gap=%d waiters=%2d | %8.1f clk/tile %7.1f clk/MMA\n", fill, N, ROWB, SHIFT, COMMIT, ZACC,
          NBUF, GAP, WAITERS, per_tile, per_tile / (9 * (ROWB / 32)));
   fflush(stdout);
 }
@@ -328,6 +332,11 @@ int main(int argc, char** argv) {
   cudaMalloc(&d_fail, sizeof(unsigned int));
   if (argc > 2 && atoi(argv[2]) == 1) {
     const int tiles = 2000;
+    for (int fill = 0; fill < 3; ++fill) {
+      run_convlike<64, 64, 1, 1, 1, 8, 0, 0>(tiles, fill);
+      run_convlike<128, 128, 1, 1, 1, 4, 0, 0>(tiles, fill);
+    }
+    return 0;
     run_convlike<64, 64, 1, 1, 1, 8, 1, 0>(tiles);
     run_convlike<64, 64, 1, 1, 1, 8, 2, 0>(tiles);
     run_convlike<64, 64, 1, 1, 1, 8, 3, 0>(tiles);
