@@ -31,7 +31,10 @@
  * describes the last failure on the calling thread.  Device pointers are plain CUDA device
  * pointers owned by the caller; `stream` is a cudaStream_t passed as void*.  Work is enqueued on the
  * caller's stream without synchronising or allocating (CUDA-graph capturable) unless stated.
- * A handle is bound to one device and is not re-entrant.  There is no CPU fallback: creation fails
+ * A handle is bound to one device and is not re-entrant: calls on one handle come from one thread at a time.  All
+ * forwards of a handle share one activation workspace; consecutive calls may use different streams (the engine orders
+ * them with an event recorded at the end of every enqueue), but their work runs one after the other.  Every entry
+ * point restores the calling thread's current CUDA device before it returns.  There is no CPU fallback: creation fails
  * with IEVM_ERR_CUDA when no sm_100 device is present.
  */
 #ifndef IEVM_H_
@@ -110,6 +113,19 @@ int ievm_forward_f16(ievm_handle* h, const void* x_nchw, int n, void* logits, vo
  * the copies asynchronous on the handle's own stream. */
 int ievm_forward_i8_host(ievm_handle* h, const float* x_nchw_host, int n, float* logits_host);
 int ievm_forward_f16_host(ievm_handle* h, const void* x_nchw_host, int n, void* logits_host);
+
+/* Pipelined host entry points for the reference's evaluation loops, which hand over one CPU batch per iteration
+ * (quantization/engines.py:52-63, quantization/main.py:277-290).  ievm_submit_*_host ENQUEUES the H2D copy, the forward
+ * and the D2H copy of the logits and returns a ticket without synchronising: the copy of call i+1 (copy stream)
+ * overlaps the forward of call i (compute stream) through two device staging slots, so at most two tickets are in
+ * flight -- a third submit first waits for the first.  x_host and logits_host must stay valid and untouched until
+ * ievm_wait(ticket) returns (pinned memory makes the copies asynchronous; pageable memory works but serialises).
+ * ievm_wait blocks the calling thread until that ticket's logits are in logits_host. */
+int ievm_submit_i8_host(ievm_handle* h, const float* x_nchw_host, int n, float* logits_host, int64_t* ticket);
+int ievm_submit_f16_host(ievm_handle* h, const void* x_nchw_host, int n, void* logits_host, int64_t* ticket);
+int ievm_submit_u8_host(ievm_handle* h, const uint8_t* x_nhwc_host, int n, float* logits_host, int64_t* ticket);
+int ievm_submit_u8_resize_host(ievm_handle* h, const uint8_t* x_nhwc_host, int n, float* logits_host, int64_t* ticket);
+int ievm_wait(ievm_handle* h, int64_t ticket);
 
 /* SURVEY 8(f)-1, the input pipeline in front of the hot path.  INT8 engines accept decoded 8-bit images,
  * x_nhwc = [n][224][224][3] u8 (RGB interleaved, what PIL / T.Resize hand to T.ToTensor in the reference's
@@ -223,6 +239,18 @@ int ievm_count_correct(const void* logits, int dtype, const int64_t* labels, int
  * total loss = (1 - alpha) * CE + alpha * KL. */
 int ievm_kd_loss(const float* student_logits, const float* teacher_logits, const int64_t* labels, int n,
                  int classes, float temperature, float* out3, void* stream);
+
+/* Measurement support (bench.py's roofline denominator): the rate at which THIS device's tensor cores retire a stream of
+ * tcgen05.mma M128 x N256 x K32-byte instructions (kind::i8 for IEVM_DTYPE_I8, kind::f16 for IEVM_DTYPE_F16) issued
+ * from one CTA per SM, timed with CUDA events: `iters` x 16 instructions per SM; *tera_ops = 2 * MACs / s / 1e12.
+ * MEASURED_PEAKS.json holds a cuBLAS bf16 figure only; there is no library INT8 GEMM to measure against. */
+int ievm_probe_mma_peak(int device, int dtype, int iters, double* tera_ops);
+
+/* Every mbarrier wait inside the kernels is bounded: after `ms` milliseconds (default 2000) it records which pipeline
+ * role was stuck and traps, so that a protocol bug fails a test instead of hanging a GPU box.  0 = wait forever: for
+ * runs under ncu replay, compute-sanitizer or GPU time-slicing, where the limit can fire spuriously (also
+ * IEVM_WAIT_LIMIT_MS in the environment at ievm_create). */
+int ievm_set_wait_limit_ms(int device, int64_t ms);
 
 const char* ievm_last_error(void);
 /* "sm_100a" build tag and ABI version, for the loader to check. */

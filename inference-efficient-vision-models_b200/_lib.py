@@ -29,6 +29,8 @@ EXPORTS = [
     "ievm_count_correct", "ievm_set_resize", "ievm_forward_u8_resize", "ievm_forward_u8_resize_host", "ievm_debug_resize",
     "ievm_observer_points", "ievm_observe", "ievm_observer_read", "ievm_observer_capacity", "ievm_observer_set_groups",
     "ievm_observer_read_hist", "ievm_observer_clear",
+    "ievm_submit_i8_host", "ievm_submit_f16_host", "ievm_submit_u8_host", "ievm_submit_u8_resize_host", "ievm_wait",
+    "ievm_probe_mma_peak", "ievm_set_wait_limit_ms",
 ]
 
 
@@ -150,6 +152,15 @@ def load():
     lib.ievm_observer_read_hist.restype = C.c_int
     lib.ievm_observer_clear.argtypes = [H]
     lib.ievm_observer_clear.restype = C.c_int
+    for name in ("ievm_submit_i8_host", "ievm_submit_f16_host", "ievm_submit_u8_host", "ievm_submit_u8_resize_host"):
+        getattr(lib, name).argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
+        getattr(lib, name).restype = C.c_int
+    lib.ievm_wait.argtypes = [H, C.c_int64]
+    lib.ievm_wait.restype = C.c_int
+    lib.ievm_probe_mma_peak.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.ievm_probe_mma_peak.restype = C.c_int
+    lib.ievm_set_wait_limit_ms.argtypes = [C.c_int, C.c_int64]
+    lib.ievm_set_wait_limit_ms.restype = C.c_int
     for name in ("ievm_forward_i8", "ievm_forward_f16", "ievm_forward_i8_host", "ievm_forward_f16_host",
                  "ievm_set_option", "ievm_num_tensors", "ievm_tensor_shape", "ievm_launches_per_forward",
                  "ievm_debug_read_tensor", "ievm_debug_conv_acc", "ievm_kd_loss"):

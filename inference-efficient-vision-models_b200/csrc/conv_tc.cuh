@@ -114,6 +114,11 @@ struct ConvTcParams {
   float inv_add_scale; // 1 / scale of quantized::add_relu's output
   int add_zp;
   int relu;            // f16: apply ReLU at the end
+  // Input zero point != 0 (never the case for the post-ReLU tensors of a ResNet, but any qconfig the reference's
+  // quantization/main.py:187-222 style can produce with a non-ReLU conv input): TMA fills padding with the integer 0, so
+  // the tensor core computes sum_{in-bounds taps} x * w; the true accumulator is sum (x - zp) * w over the same taps.
+  // zcorr[cls][cout_pad] = zp * sum_{taps of class cls} sum_ci w, cls = (row-tap mask << ksize) | column-tap mask.
+  const int32_t* zcorr;
   int32_t* dump_acc;   // debug: raw accumulators [m_total][dump_pitch] (bit pattern for f16)
   int dump_pitch;
   unsigned int* stuck_flag;   // mapped host word; written before a bounded wait gives up
@@ -793,7 +798,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool sub_ok = kMode == kModeHalo && row < p.sub_pos && sub_x < p.w_in;
     constexpr bool kResI8 = kHasRes && kDtype == kDtypeI8;
     // One tile (accumulator buffer `acc`) of output rows starting at pixel index m (valid = this thread's row exists).
-    auto drain = [&](int acc, uint32_t acc_phase, int m, bool valid, int n0) {
+    // Border class of output pixel (oy, ox) for the zero-point correction: which filter taps read inside the image.
+    auto zcorr_row = [&](int oy, int ox) -> const int32_t* {
+      int my = 0, mx = 0;
+      for (int t = 0; t < p.ksize; ++t) {
+        const int iy = oy * p.stride - p.pad + t, ix = ox * p.stride - p.pad + t;
+        my |= (iy >= 0 && iy < p.h_in) ? (1 << t) : 0;
+        mx |= (ix >= 0 && ix < p.w_in) ? (1 << t) : 0;
+      }
+      return p.zcorr + static_cast<size_t>((my << p.ksize) | mx) * p.cout_pad;
+    };
+    auto drain = [&](int acc, uint32_t acc_phase, int m, bool valid, int n0, const int32_t* zc = nullptr) {
       uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
       int c = sub;
       if (kResI8 && c < nchunks) ra = load_res16_i8(p, m, valid, n0 + c * 16);   // does not depend on the MMA
@@ -810,6 +825,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (c < nchunks) tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), va);
       while (c < nchunks) {
         tmem_ld_wait();
+        if (kDtype == kDtypeI8 && zc != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) va[j] -= static_cast<uint32_t>(__ldg(zc + n0 + c * 16 + j));
+        }
         if (c + csub < nchunks) {
           tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + csub) * 16), vb);
           if (kResI8) rb = load_res16_i8(p, m, valid, n0 + (c + csub) * 16);
@@ -818,6 +837,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         c += csub;
         if (c >= nchunks) break;
         tmem_ld_wait();
+        if (kDtype == kDtypeI8 && zc != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vb[j] -= static_cast<uint32_t>(__ldg(zc + n0 + c * 16 + j));
+        }
         if (c + csub < nchunks) {
           tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + csub) * 16), va);
           if (kResI8) ra = load_res16_i8(p, m, valid, n0 + (c + csub) * 16);
@@ -856,22 +879,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           epilogue_chunk<kDtype, kHasRes>(p, vv[c & 1], rr[c & 1], m, valid, c * 16, p.epc0, p.epc1, k);
         }
-      } else {
-        // wide layers: the chunk loop stays a loop over chunk PAIRS (register pressure), the tables are still read from
-        // the constant bank, now through a uniform index
-#pragma unroll 1
-        for (int c = 0; c < kNch; c += 2) {
-          tmem_ld_wait();
-          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 1) * 16), vv[1]);
-          if (kResI8) rr[1] = load_res16_i8(p, m, valid, (c + 1) * 16);
-          epilogue_chunk<kDtype, kHasRes>(p, vv[0], rr[0], m, valid, c * 16, p.epc0, p.epc1, k);
-          tmem_ld_wait();
-          if (c + 2 < kNch) {
-            tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 2) * 16), vv[0]);
-            if (kResI8) rr[0] = load_res16_i8(p, m, valid, (c + 2) * 16);
-          }
-          epilogue_chunk<kDtype, kHasRes>(p, vv[1], rr[1], m, valid, (c + 1) * 16, p.epc0, p.epc1, k);
-        }
       }
 #endif
       tc_fence_before();
@@ -893,8 +900,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int oy = (t - img * p.subs_per_img) * p.sub_rows + sub_row;
         const bool valid = sub_ok && oy < p.h_in;
         const int m = (img * p.h_in + oy) * p.w_in + sub_x;
-        if (kShape != 0) drain_static(acc, acc_phase, m, valid);
-        else drain(acc, acc_phase, m, valid, 0);
+        // narrow layers (<= 4 chunks): unrolled, constant-bank tables; wide layers keep the chunk loop (register budget)
+        if (kShape != 0 && halo_shape_bn(kShape) <= 64) drain_static(acc, acc_phase, m, valid);
+        else drain(acc, acc_phase, m, valid, 0, (kDtype == kDtypeI8 && p.zcorr != nullptr) ? zcorr_row(oy, sub_x) : nullptr);
       }
     } else {
       int acc_next = 0, seq = 0;
@@ -914,7 +922,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int n_tile = tile - m_group * p.n_tiles;
         const int m_tile = kCluster > 1 ? m_group * kCluster + static_cast<int>(crank) : m_group;
         const int m = m_tile * kTileM + row;
-        drain(acc, acc_phase, m, m < p.m_total, n_tile * p.bn);
+        const int32_t* zc = nullptr;
+        if (kDtype == kDtypeI8 && p.zcorr != nullptr) {
+          const int rem = m - (m / hw) * hw;
+          zc = zcorr_row(rem / p.wo, rem - (rem / p.wo) * p.wo);
+        }
+        drain(acc, acc_phase, m, m < p.m_total, n_tile * p.bn, zc);
       }
     }
   }

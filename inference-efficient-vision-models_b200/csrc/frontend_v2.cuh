@@ -375,8 +375,17 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
       const F2Unit un = f2_unit(p, u);
       for (int i = 0; i <= un.nt; ++i, ++t) {
         const int qn = q0 + i + 2;               // newest chunk this tile reads (chunks complete in order)
-        wait_or_die(&line_full[qn % kF2ChunkSlots], (qn / kF2ChunkSlots) & 1u, 0x820u | (qn % kF2ChunkSlots), p.stuck_flag);
-        wait_or_die(&tmem_empty[ts], ph ^ 1u, 0x830u | ts, p.stuck_flag);
+        {
+          // both barrier tests in ONE round trip: every mbarrier test by the issuing thread is ~150 cycles of idle tensor
+          // pipe (conv_tc.cuh), and a tile is only ten instructions long
+          uint64_t* b0 = &line_full[qn % kF2ChunkSlots];
+          uint64_t* b1 = &tmem_empty[ts];
+          const uint32_t p0 = (qn / kF2ChunkSlots) & 1u, p1 = ph ^ 1u;
+          if (!mbar_try_wait5(b0, p0, b1, p1, b1, p1, b1, p1, b1, p1)) {
+            wait_or_die(b0, p0, 0x820u | (qn % kF2ChunkSlots), p.stuck_flag);
+            wait_or_die(b1, p1, 0x830u | ts, p.stuck_flag);
+          }
+        }
         tc_fence_after();
         fence_proxy_async_smem();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(ts * kF2TmemSlotCols);

@@ -23,6 +23,7 @@
 #include "stem_tc.cuh"
 #include "frontend_v2.cuh"
 #include "observe.cuh"
+#include "probe_mma.cuh"
 
 namespace {
 
@@ -47,6 +48,20 @@ int fail(int code, const char* fmt, ...) {
       return fail(e__ == cudaErrorMemoryAllocation ? IEVM_ERR_OOM : IEVM_ERR_CUDA, "%s failed: %s", \
                   #expr, cudaGetErrorString(e__));                                                  \
   } while (0)
+
+// Every entry point runs on the handle's device and leaves the calling thread's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 // ---- driver entry points for tensor-map encoding (resolved at run time: the library must load on a
 // machine without libcuda so that the CPU-only test tier can check its exports) ----
@@ -147,6 +162,7 @@ struct LayerPlan {
   void* w_front2 = nullptr;     // frontend_v2.cuh weight operand image (two stem rows stacked in M)
   int* wsum = nullptr;
   int* zwsum = nullptr;         // in_zp * wsum
+  int32_t* zcorr = nullptr;     // tensor-core convs with a non-zero input zero point: ConvTcParams::zcorr
   size_t stem_smem = 0;
   float* ep0 = nullptr;
   float* ep1 = nullptr;
@@ -164,6 +180,7 @@ struct ievm_handle {
   int num_sms = 0;
   int smem_optin = 0;
   int opt_halo = 1;        // IEVM_HALO=0 disables the halo-patch mode (all convs use per-tap im2col TMA)
+  int opt_halo_static = 1; // IEVM_HALO_STATIC=0: run-time-shaped halo kernel (class 0) even for the specialised shapes
   int opt_fused_front = 1; // IEVM_FUSED_FRONT=0: separate quantize / stem / maxpool kernels
   int front2_ok = 0;       // the network's front end fits frontend_v2.cuh (224-wide input, <= 64 stem channels)
   int front_tpu = 0;       // IEVM_FRONT_TPU: pooled rows per work unit (0 = heuristic)
@@ -216,7 +233,24 @@ struct ievm_handle {
   void* pin_in = nullptr;              // pinned host staging
   void* pin_out = nullptr;
   size_t pin_in_bytes = 0;
-  std::map<std::tuple<int, const void*, void*>, cudaGraphExec_t> graphs;
+  // CUDA graphs cached per (n, input mode, x, logits); bounded (kMaxGraphs, least recently used goes first)
+  std::map<std::tuple<int, const void*, void*>, std::pair<cudaGraphExec_t, unsigned long long>> graphs;
+  unsigned long long graph_clock = 0;
+  // All forwards of a handle share one activation workspace: work enqueued on a different stream than the previous
+  // forward's first waits for `order_event`, recorded at the end of every enqueue (y1 = model(x_cuda);
+  // y2 = model(x_cpu) raced on the workspace).
+  cudaEvent_t order_event = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool order_valid = false;
+  // pipelined host entry points (ievm_submit_*_host / ievm_wait): two staging slots, no per-call stream synchronisation
+  struct HostSlot {
+    void* dev_in = nullptr;
+    void* dev_out = nullptr;
+    size_t in_bytes = 0;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    long long ticket = -1;          // ticket in flight in this slot, -1 = free
+  } slots[2];
+  long long next_ticket = 0;
   // per-launch device timing (option "profile"): slot 0 = input quantize, slot 1 + i = layer i
   int profile = 0;
   std::vector<cudaEvent_t> prof_events;
@@ -330,8 +364,6 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
     }
     if (!((d.ksize == 3 && d.pad == 1) || (d.ksize == 1 && d.pad == 0)) || d.stride < 1 || d.stride > 2)
       return fail(IEVM_ERR_UNSUPPORTED, "layer %d: only 3x3/pad1 and 1x1/pad0 convs with stride 1|2", i);
-    if (h->dtype == IEVM_DTYPE_I8 && d.in_zp != 0)
-      return fail(IEVM_ERR_UNSUPPORTED, "layer %d: tensor-core conv input zero-point must be 0 (got %d)", i, d.in_zp);
     if (d.res_tensor >= 0) {
       const TensorInfo& tr = h->tensors[d.res_tensor];
       if (tr.h != L.ho || tr.w != L.wo || tr.c != d.cout || tr.pitch != L.cout_pad)
@@ -582,6 +614,26 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
     int8_t* dw = nullptr;
     if (int rc = dev_upload(h, wp, &dw)) return rc;
     L.w_packed = dw;
+    if (d.in_zp != 0) {
+      // border-aware zero-point correction (ConvTcParams::zcorr): class = (row-tap mask << k) | column-tap mask
+      const int k = d.ksize, ncls = 1 << (2 * k);
+      std::vector<int32_t> w2(static_cast<size_t>(d.cout) * taps, 0);           // sum over input channels per tap
+      for (int co = 0; co < d.cout; ++co)
+        for (int ci = 0; ci < d.cin; ++ci)
+          for (int t = 0; t < taps; ++t) w2[static_cast<size_t>(co) * taps + t] += w[(static_cast<size_t>(co) * d.cin + ci) * taps + t];
+      std::vector<int32_t> tab(static_cast<size_t>(ncls) * L.cout_pad, 0);
+      for (int cls = 0; cls < ncls; ++cls) {
+        const int my = cls >> k, mx = cls & ((1 << k) - 1);
+        for (int co = 0; co < d.cout; ++co) {
+          int32_t sum = 0;
+          for (int ty = 0; ty < k; ++ty)
+            for (int tx = 0; tx < k; ++tx)
+              if (((my >> ty) & 1) && ((mx >> tx) & 1)) sum += w2[static_cast<size_t>(co) * taps + ty * k + tx];
+          tab[static_cast<size_t>(cls) * L.cout_pad + co] = d.in_zp * sum;
+        }
+      }
+      if (int rc = dev_upload(h, tab, &L.zcorr)) return rc;
+    }
   } else {
     const uint16_t* w = static_cast<const uint16_t*>(d.weight);
     std::vector<uint16_t> wp(static_cast<size_t>(L.cout_pad) * k_total, 0);
@@ -681,7 +733,7 @@ int assign_buffers(ievm_handle* h) {
   for (void* b : h->buffers) cudaFree(b);
   h->buffers.clear();
   h->buffer_bytes.clear();
-  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
   h->graphs.clear();
   std::vector<size_t> need;          // planned size per buffer
   std::vector<int> free_list;
@@ -863,6 +915,7 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   p.inv_add_scale = d.res_tensor >= 0 ? 1.0f / d.add_scale : 0.f;
   p.add_zp = d.add_zp;
   p.relu = d.relu;
+  p.zcorr = L.zcorr;
   p.dump_acc = dump_acc;
   p.dump_pitch = L.cout_pad;
   p.stuck_flag = h->stuck_dev;
@@ -883,6 +936,7 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
     g.n = n; g.h = L.h; g.w = L.w; g.ho = L.ho; g.wo = L.wo;
     g.cin_pitch = L.cin_pitch; g.cin_w = L.cin_w; g.cin_real = L.d.cin; g.cout_pad = L.cout_pad;
     g.ksize = L.d.ksize; g.stride = L.d.stride; g.pad = L.d.pad;
+    g.in_zp = h->dtype == IEVM_DTYPE_I8 ? L.d.in_zp : 0;
     const long long total = static_cast<long long>(p.m_total) * L.cout_pad;
     const unsigned blocks = static_cast<unsigned>((total + 127) / 128);
     if (h->dtype == IEVM_DTYPE_I8)
@@ -914,7 +968,8 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
     } else if (cl == 2) IEVM_LAUNCH(DT, RES, kModeIm2col, 2, 0);           \
     else IEVM_LAUNCH(DT, RES, kModeIm2col, 1, 0);                          \
   } while (0)
-  const int shape = L.mode == kModeHalo ? halo_shape_class(L.wp, L.kc_bytes, L.bn) : 0;
+  // the shape-specialised kernels assume a zero input zero point (true for every post-ReLU tensor); others take class 0
+  const int shape = (L.mode == kModeHalo && h->opt_halo_static && L.zcorr == nullptr) ? halo_shape_class(L.wp, L.kc_bytes, L.bn) : 0;
   if (h->dtype == IEVM_DTYPE_I8) {
     if (has_res) IEVM_LAUNCH_MODE(kDtypeI8, true, 1, 2); else IEVM_LAUNCH_MODE(kDtypeI8, false, 1, 2);
   } else {
@@ -1222,34 +1277,70 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
   return IEVM_OK;
 }
 
+constexpr size_t kMaxGraphs = 16;
+
+// Stream ordering between consecutive uses of the handle's workspace (see ievm_handle::order_event).  Skipped while the
+// caller is capturing `s` into a graph of their own (an event recorded outside the capture cannot be waited on inside it).
+int order_begin(ievm_handle* h, cudaStream_t s, bool* capturing) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  *capturing = cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+  if (*capturing) return IEVM_OK;
+  if (h->order_valid && h->last_stream != s) CUDA_TRY(cudaStreamWaitEvent(s, h->order_event, 0));
+  return IEVM_OK;
+}
+int order_end(ievm_handle* h, cudaStream_t s, bool capturing) {
+  if (capturing) return IEVM_OK;
+  CUDA_TRY(cudaEventRecord(h->order_event, s));
+  h->last_stream = s;
+  h->order_valid = true;
+  return IEVM_OK;
+}
+
 int forward_common(ievm_handle* h, int want_dtype, const void* x, int n, void* logits, void* stream, int in_mode = kInNative) {
   if (!h || !x || !logits) return fail(IEVM_ERR_BAD_ARG, "null argument");
   if (h->dtype != want_dtype) return fail(IEVM_ERR_BAD_ARG, "engine dtype does not match this entry point");
   if (n < 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "batch %d outside [0, %d]", n, h->max_batch);
   if (n == 0) return IEVM_OK;
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!h->use_graph || h->profile) return enqueue_forward(h, x, n, logits, s, in_mode);
+  bool capturing = false;
+  if (int rc = order_begin(h, s, &capturing)) return rc;
+  if (!h->use_graph || h->profile || capturing) {
+    if (int rc = enqueue_forward(h, x, n, logits, s, in_mode)) return rc;
+    return order_end(h, s, capturing);
+  }
   const auto key = std::make_tuple(n * 4 + in_mode, x, logits);
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
+    if (h->graphs.size() >= kMaxGraphs) {          // evict the least recently used graph
+      auto victim = h->graphs.begin();
+      for (auto g = h->graphs.begin(); g != h->graphs.end(); ++g)
+        if (g->second.second < victim->second.second) victim = g;
+      cudaGraphExecDestroy(victim->second.first);
+      h->graphs.erase(victim);
+    }
     cudaStream_t cs = h->own_stream;
     cudaGraph_t graph = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     const int rc = enqueue_forward(h, x, n, logits, cs, in_mode);
     const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-    if (rc) return rc;
-    if (ce != cudaSuccess) return fail(IEVM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    if (rc || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      if (rc) return rc;
+      return fail(IEVM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    }
     cudaGraphExec_t exec = nullptr;
-    CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
-    it = h->graphs.emplace(key, exec).first;
+    if (ie != cudaSuccess) return fail(IEVM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+    it = h->graphs.emplace(key, std::make_pair(exec, 0ull)).first;
   }
-  CUDA_TRY(cudaGraphLaunch(it->second, s));
+  it->second.second = ++h->graph_clock;
+  CUDA_TRY(cudaGraphLaunch(it->second.first, s));
   h->last_n = n;
   h->last_x = x;
   h->last_logits = logits;
-  return IEVM_OK;
+  return order_end(h, s, capturing);
 }
 
 int check_stuck(ievm_handle* h, cudaError_t e, const char* what) {
@@ -1325,7 +1416,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(IEVM_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(IEVM_ERR_BAD_ARG, "device %d out of range", device);
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(IEVM_ERR_UNSUPPORTED, "device is sm_%d%d; this build is sm_100a only", prop.major, prop.minor);
@@ -1341,6 +1432,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   h->in_c = nd->in_c; h->in_h = nd->in_h; h->in_w = nd->in_w; h->classes = nd->num_classes;
   h->in_scale = nd->in_scale; h->in_zp = nd->in_zp;
   if (const char* e = getenv("IEVM_HALO")) h->opt_halo = atoi(e);
+  if (const char* e = getenv("IEVM_HALO_STATIC")) h->opt_halo_static = atoi(e);
   if (const char* e = getenv("IEVM_FIXED_BN")) h->opt_fixed_bn = atoi(e);
   if (const char* e = getenv("IEVM_PDL")) h->opt_pdl = atoi(e);
   if (const char* e = getenv("IEVM_CLUSTER")) h->opt_cluster = atoi(e);
@@ -1436,6 +1528,15 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
       e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->stuck_dev), h->stuck_host, 0);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming);
+    for (auto& sl : h->slots) {
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+    }
+    if (const char* w = getenv("IEVM_WAIT_LIMIT_MS")) {
+      const unsigned long long ns = static_cast<unsigned long long>(atoll(w)) * 1000000ull;
+      if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_wait_limit_ns, &ns, sizeof(ns));
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "runtime setup: %s", cudaGetErrorString(e));
   }
@@ -1451,8 +1552,8 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
 
 void ievm_destroy(ievm_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
-  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  DeviceGuard guard(h->device);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   for (void* p : h->buffers) cudaFree(p);
   for (void* p : h->owned) cudaFree(p);
@@ -1464,6 +1565,13 @@ void ievm_destroy(ievm_handle* h) {
   if (h->pin_in) cudaFreeHost(h->pin_in);
   if (h->pin_out) cudaFreeHost(h->pin_out);
   if (h->stuck_host) cudaFreeHost(h->stuck_host);
+  if (h->order_event) cudaEventDestroy(h->order_event);
+  for (auto& sl : h->slots) {
+    if (sl.dev_in) cudaFree(sl.dev_in);
+    if (sl.dev_out) cudaFree(sl.dev_out);
+    if (sl.copied) cudaEventDestroy(sl.copied);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
@@ -1481,7 +1589,7 @@ int ievm_forward_f16(ievm_handle* h, const void* x, int n, void* logits, void* s
 static int forward_host_common(ievm_handle* h, int dtype, const void* x_host, int n, void* logits_host, int in_mode = kInNative) {
   if (!h || !x_host || !logits_host) return fail(IEVM_ERR_BAD_ARG, "null argument");
   if (n <= 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "batch %d outside [1, %d]", n, h->max_batch);
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const size_t in_elem = in_mode != kInNative ? 1 : (dtype == IEVM_DTYPE_I8 ? 4 : 2);
   const size_t out_elem = dtype == IEVM_DTYPE_I8 ? 4 : 2;
   const size_t per_img = in_mode == kInU8Resize ? static_cast<size_t>(3) * h->rs_in_h * h->rs_in_w
@@ -1495,7 +1603,7 @@ static int forward_host_common(ievm_handle* h, int dtype, const void* x_host, in
       if (h->stage_in) cudaFree(h->stage_in);
       h->stage_in = nullptr;
       h->stage_in_bytes = 0;
-      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);      // graphs captured on the old staging buffer
+      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);      // graphs captured on the old staging buffer
       h->graphs.clear();
       CUDA_TRY(cudaMalloc(&h->stage_in, need));
       h->stage_in_bytes = need;
@@ -1536,10 +1644,127 @@ int ievm_forward_f16_host(ievm_handle* h, const void* x_host, int n, void* logit
   return forward_host_common(h, IEVM_DTYPE_F16, x_host, n, logits_host);
 }
 
+// ---- pipelined host entry points: enqueue and return; the H2D copy of call i+1 overlaps the forward of call i ----
+static int submit_host_common(ievm_handle* h, int dtype, const void* x_host, int n, void* logits_host, int in_mode,
+                              int64_t* ticket) {
+  if (!h || !x_host || !logits_host || !ticket) return fail(IEVM_ERR_BAD_ARG, "null argument");
+  if (h->dtype != dtype) return fail(IEVM_ERR_BAD_ARG, "engine dtype does not match this entry point");
+  if (n <= 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "batch %d outside [1, %d]", n, h->max_batch);
+  if (in_mode == kInU8Resize && !h->rs_out) return fail(IEVM_ERR_BAD_ARG, "call ievm_set_resize first");
+  DeviceGuard guard(h->device);
+  const size_t in_elem = in_mode != kInNative ? 1 : (dtype == IEVM_DTYPE_I8 ? 4 : 2);
+  const size_t out_elem = dtype == IEVM_DTYPE_I8 ? 4 : 2;
+  const size_t per_img = in_mode == kInU8Resize ? static_cast<size_t>(3) * h->rs_in_h * h->rs_in_w
+                                                : static_cast<size_t>(h->in_c) * h->in_h * h->in_w * in_elem;
+  ievm_handle::HostSlot& sl = h->slots[h->next_ticket & 1];
+  if (sl.ticket >= 0) {              // the slot's previous call must have left the device (normally long done)
+    if (int rc = check_stuck(h, cudaEventSynchronize(sl.done), "submit: previous call of this slot")) return rc;
+    sl.ticket = -1;
+  }
+  const size_t need = per_img * h->max_batch;
+  if (sl.in_bytes < need) {
+    if (sl.dev_in) {
+      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);    // graphs captured on the old staging buffer
+      h->graphs.clear();
+      CUDA_TRY(cudaFree(sl.dev_in));
+      sl.dev_in = nullptr;
+      sl.in_bytes = 0;
+    }
+    CUDA_TRY(cudaMalloc(&sl.dev_in, need + 256));
+    sl.in_bytes = need;
+  }
+  if (!sl.dev_out) CUDA_TRY(cudaMalloc(&sl.dev_out, out_elem * h->classes * h->max_batch));
+  cudaStream_t s = h->own_stream;
+  CUDA_TRY(cudaMemcpyAsync(sl.dev_in, x_host, per_img * n, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(cudaEventRecord(sl.copied, h->copy_stream));
+  CUDA_TRY(cudaStreamWaitEvent(s, sl.copied, 0));
+  if (int rc = forward_common(h, dtype, sl.dev_in, n, sl.dev_out, s, in_mode)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(logits_host, sl.dev_out, out_elem * h->classes * n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaEventRecord(sl.done, s));
+  sl.ticket = h->next_ticket;
+  *ticket = h->next_ticket++;
+  return IEVM_OK;
+}
+
+int ievm_submit_i8_host(ievm_handle* h, const float* x_host, int n, float* logits_host, int64_t* ticket) {
+  return submit_host_common(h, IEVM_DTYPE_I8, x_host, n, logits_host, kInNative, ticket);
+}
+int ievm_submit_f16_host(ievm_handle* h, const void* x_host, int n, void* logits_host, int64_t* ticket) {
+  return submit_host_common(h, IEVM_DTYPE_F16, x_host, n, logits_host, kInNative, ticket);
+}
+int ievm_submit_u8_host(ievm_handle* h, const uint8_t* x_nhwc_host, int n, float* logits_host, int64_t* ticket) {
+  return submit_host_common(h, IEVM_DTYPE_I8, x_nhwc_host, n, logits_host, kInU8, ticket);
+}
+int ievm_submit_u8_resize_host(ievm_handle* h, const uint8_t* x_nhwc_host, int n, float* logits_host, int64_t* ticket) {
+  return submit_host_common(h, IEVM_DTYPE_I8, x_nhwc_host, n, logits_host, kInU8Resize, ticket);
+}
+
+int ievm_wait(ievm_handle* h, int64_t ticket) {
+  if (!h) return fail(IEVM_ERR_BAD_ARG, "null argument");
+  if (ticket < 0 || ticket >= h->next_ticket) return fail(IEVM_ERR_BAD_ARG, "ievm_wait: unknown ticket %lld", (long long)ticket);
+  ievm_handle::HostSlot& sl = h->slots[ticket & 1];
+  if (sl.ticket != ticket) return IEVM_OK;          // already waited for (or overtaken by a later submit, which waited)
+  DeviceGuard guard(h->device);
+  const int rc = check_stuck(h, cudaEventSynchronize(sl.done), "ievm_wait");
+  sl.ticket = -1;
+  return rc;
+}
+
+int ievm_set_wait_limit_ms(int device, int64_t ms) {
+  if (ms < 0) return fail(IEVM_ERR_BAD_ARG, "ievm_set_wait_limit_ms: negative limit");
+  DeviceGuard guard(device);
+  const unsigned long long ns = static_cast<unsigned long long>(ms) * 1000000ull;
+  CUDA_TRY(cudaMemcpyToSymbol(g_wait_limit_ns, &ns, sizeof(ns)));
+  return IEVM_OK;
+}
+
+int ievm_probe_mma_peak(int device, int dtype, int iters, double* tera_ops) {
+  if (!tera_ops || iters <= 0 || (dtype != IEVM_DTYPE_I8 && dtype != IEVM_DTYPE_F16))
+    return fail(IEVM_ERR_BAD_ARG, "ievm_probe_mma_peak: bad arguments");
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(IEVM_ERR_UNSUPPORTED, "device is sm_%d%d; this build is sm_100a only", prop.major, prop.minor);
+  const int smem = 1024 + 256 * 128 + 64;
+  unsigned int* fail_flag = nullptr;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&fail_flag), sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(fail_flag, 0, sizeof(unsigned int)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  cudaError_t e = cudaSuccess;
+  for (int rep = 0; rep < 2 && e == cudaSuccess; ++rep) {       // the first launch warms up
+    if (rep == 1) cudaEventRecord(e0);
+    if (dtype == IEVM_DTYPE_I8) {
+      e = cudaFuncSetAttribute(probe_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) probe_mma_kernel<0><<<prop.multiProcessorCount, 128, smem>>>(iters, fail_flag);
+    } else {
+      e = cudaFuncSetAttribute(probe_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e == cudaSuccess) probe_mma_kernel<1><<<prop.multiProcessorCount, 128, smem>>>(iters, fail_flag);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  cudaEventRecord(e1);
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  unsigned int failed = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&failed, fail_flag, sizeof(failed), cudaMemcpyDeviceToHost);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(fail_flag);
+  if (e != cudaSuccess) return fail(IEVM_ERR_CUDA, "ievm_probe_mma_peak: %s", cudaGetErrorString(e));
+  if (failed || ms <= 0.f) return fail(IEVM_ERR_CUDA, "ievm_probe_mma_peak: the instruction stream did not complete");
+  const double k_per_mma = dtype == IEVM_DTYPE_I8 ? 32.0 : 16.0;
+  const double ops = 2.0 * 128.0 * 256.0 * k_per_mma * 16.0 * iters * prop.multiProcessorCount;
+  *tera_ops = ops / (ms * 1e-3) / 1e12;
+  return IEVM_OK;
+}
+
 int ievm_set_input_lut(ievm_handle* h, const uint8_t* lut768) {
   if (!h || !lut768) return fail(IEVM_ERR_BAD_ARG, "null argument");
   if (h->dtype != IEVM_DTYPE_I8) return fail(IEVM_ERR_BAD_ARG, "the 8-bit image input path belongs to the INT8 engine");
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   if (!h->lut_dev) {
     void* p = nullptr;
     CUDA_TRY(cudaMalloc(&p, 768));
@@ -1563,7 +1788,7 @@ int ievm_set_resize(ievm_handle* h, int src_h, int src_w, const int32_t* bounds_
   if (!h || src_h <= 0 || src_w <= 0 || !bounds_w || !kk_w || !bounds_h || !kk_h || ksize_w <= 0 || ksize_h <= 0)
     return fail(IEVM_ERR_BAD_ARG, "ievm_set_resize: bad arguments");
   if (h->dtype != IEVM_DTYPE_I8) return fail(IEVM_ERR_BAD_ARG, "the 8-bit image input path belongs to the INT8 engine");
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   CUDA_TRY(cudaDeviceSynchronize());
   for (void* q : {static_cast<void*>(h->rs_bounds_w), static_cast<void*>(h->rs_bounds_h), static_cast<void*>(h->rs_kk_w),
                   static_cast<void*>(h->rs_kk_h), static_cast<void*>(h->rs_tmp), static_cast<void*>(h->rs_out)})
@@ -1571,7 +1796,7 @@ int ievm_set_resize(ievm_handle* h, int src_h, int src_w, const int32_t* bounds_
   h->rs_bounds_w = h->rs_bounds_h = nullptr;
   h->rs_kk_w = h->rs_kk_h = nullptr;
   h->rs_tmp = h->rs_out = nullptr;
-  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
   h->graphs.clear();
   h->rs_in_h = src_h; h->rs_in_w = src_w; h->rs_ksize_w = ksize_w; h->rs_ksize_h = ksize_h;
   auto up = [&](const int32_t* src, size_t count, void** dst) -> cudaError_t {
@@ -1599,7 +1824,8 @@ int ievm_debug_resize(ievm_handle* h, const uint8_t* x_dev, int n, uint8_t* out_
   if (!h || !x_dev || !out_host || n <= 0 || n > h->max_batch) return fail(IEVM_ERR_BAD_ARG, "debug_resize: bad arguments");
   const size_t bytes = static_cast<size_t>(n) * h->in_h * h->in_w * 3;
   if (out_bytes < bytes) return fail(IEVM_ERR_BAD_ARG, "debug_resize: host buffer too small");
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());      // parity hook: whatever stream wrote the input is done
   if (int rc = launch_resize(h, x_dev, n, h->own_stream)) return rc;
   CUDA_TRY(cudaStreamSynchronize(h->own_stream));
   const uint8_t* src = (h->rs_in_h == h->in_h && h->rs_in_w == h->in_w) ? x_dev : h->rs_out;
@@ -1612,7 +1838,7 @@ int ievm_set_option(ievm_handle* h, const char* name, int value) {
   if (!strcmp(name, "conv_impl")) {
     if (value != 0 && value != 1) return fail(IEVM_ERR_BAD_ARG, "conv_impl must be 0 or 1");
     h->conv_impl = value;
-    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
     h->graphs.clear();
     return IEVM_OK;
   }
@@ -1629,7 +1855,7 @@ int ievm_set_option(ievm_handle* h, const char* name, int value) {
   if (!strcmp(name, "keep_tensors")) {
     if ((value ? 1 : 0) == h->keep_tensors) return IEVM_OK;
     h->keep_tensors = value ? 1 : 0;
-    CUDA_TRY(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     CUDA_TRY(cudaDeviceSynchronize());
     if (int rc = assign_buffers(h)) return rc;
     return encode_maps(h);
@@ -1641,9 +1867,9 @@ int ievm_set_option(ievm_handle* h, const char* name, int value) {
     if (value < 0 || value > 2) return fail(IEVM_ERR_BAD_ARG, "observe must be 0, 1 or 2");
     const int points = static_cast<int>(h->tensors.size()) + 2;
     if (points > kObsMaxPoints) return fail(IEVM_ERR_UNSUPPORTED, "more than %d observation points", kObsMaxPoints);
-    CUDA_TRY(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     CUDA_TRY(cudaDeviceSynchronize());
-    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);   // the pooled-output pointer is baked into captured launches
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);   // the pooled-output pointer is baked into captured launches
     h->graphs.clear();
     h->obs_records = 0;
     h->obs_mode = value;
@@ -1708,7 +1934,7 @@ int ievm_observe(ievm_handle* h, const float* x_f32, void* stream) {
   const void* x0 = x_f32 ? static_cast<const void*>(x_f32) : h->last_x;
   if (reinterpret_cast<uintptr_t>(x0) % 16 != 0 || reinterpret_cast<uintptr_t>(h->last_logits) % 16 != 0)
     return fail(IEVM_ERR_BAD_ARG, "ievm_observe: input / logits buffers must be 16-byte aligned");
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int T = static_cast<int>(h->tensors.size());
   const int points = T + 2;
@@ -1742,6 +1968,8 @@ int ievm_observe(ievm_handle* h, const float* x_f32, void* stream) {
   add(h->obs_pooled, static_cast<long long>(n) * head_cin, 1, 1, false);
   add(h->last_logits, static_cast<long long>(n) * h->classes, 1, 1, false);
   tab.total_blocks = nblocks;
+  bool capturing = false;
+  if (int rc = order_begin(h, s, &capturing)) return rc;
   uint32_t* rec = h->obs_log + static_cast<size_t>(h->obs_records) * points * 2;
   observe_init_kernel<<<(2 * points + 255) / 256, 256, 0, s>>>(rec, points);
   observe_minmax_multi_kernel<<<nblocks, 256, 0, s>>>(tab, rec, h->obs_run);
@@ -1749,14 +1977,14 @@ int ievm_observe(ievm_handle* h, const float* x_f32, void* stream) {
     observe_hist_multi_kernel<<<nblocks, 256, 0, s>>>(tab, h->obs_run, h->obs_hist + static_cast<size_t>(h->obs_records) * points * kObsBins);
   CUDA_TRY(cudaGetLastError());
   ++h->obs_records;
-  return IEVM_OK;
+  return order_end(h, s, capturing);
 }
 
 int ievm_observer_read(ievm_handle* h, float* minmax_host, int max_records) {
   if (!h || !minmax_host || max_records < 0) return fail(IEVM_ERR_BAD_ARG, "ievm_observer_read: bad arguments");
   const int nrec = std::min(h->obs_records, max_records);
   if (nrec == 0) return 0;
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   if (int rc = check_stuck(h, cudaDeviceSynchronize(), "observer_read sync")) return rc;
   const size_t words = static_cast<size_t>(nrec) * (h->tensors.size() + 2) * 2;
   std::vector<uint32_t> enc(words);
@@ -1769,7 +1997,7 @@ int ievm_observer_read_hist(ievm_handle* h, uint32_t* hist_host, float* range_ho
   if (!h || !hist_host || max_records < 0) return fail(IEVM_ERR_BAD_ARG, "ievm_observer_read_hist: bad arguments");
   if (h->obs_mode != 2 || !h->obs_hist) return fail(IEVM_ERR_BAD_ARG, "ievm_observer_read_hist: set option observe=2 first");
   const int nrec = std::min(h->obs_records, max_records);
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   if (int rc = check_stuck(h, cudaDeviceSynchronize(), "observer_read_hist sync")) return rc;
   if (range_host) {       // running (min, max) per observer group, as of the last record
     uint32_t enc[2 * kObsMaxPoints];
@@ -1785,7 +2013,7 @@ int ievm_observer_read_hist(ievm_handle* h, uint32_t* hist_host, float* range_ho
 int ievm_observer_clear(ievm_handle* h) {
   if (!h) return fail(IEVM_ERR_BAD_ARG, "null argument");
   if (!h->obs_mode) return fail(IEVM_ERR_BAD_ARG, "ievm_observer_clear: set option observe first");
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   CUDA_TRY(cudaDeviceSynchronize());
   if (h->obs_hist && h->obs_records > 0)
     CUDA_TRY(cudaMemset(h->obs_hist, 0, static_cast<size_t>(h->obs_records) * (h->tensors.size() + 2) * kObsBins * sizeof(uint32_t)));
@@ -1827,7 +2055,7 @@ int ievm_debug_read_tensor(ievm_handle* h, int id, void* host_out, uint64_t host
   const size_t row = static_cast<size_t>(t.w) * t.pitch * t.elem;
   const size_t bytes = row * t.h * h->last_n;
   if (host_bytes < bytes) return fail(IEVM_ERR_BAD_ARG, "host buffer too small: need %zu bytes", bytes);
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   if (int rc = check_stuck(h, cudaDeviceSynchronize(), "debug_read_tensor sync")) return rc;
   if (t.hp > 0) {   // strip the border: one 2-D copy per image
     const size_t src_row = static_cast<size_t>(t.wp) * t.pitch * t.elem;
@@ -1851,9 +2079,10 @@ int ievm_debug_conv_acc(ievm_handle* h, int layer, int n, int32_t* host_out, uin
   if (!h->keep_tensors) return fail(IEVM_ERR_BAD_ARG, "set keep_tensors=1 before the forward whose accumulators you want");
   const size_t bytes = static_cast<size_t>(n) * L.ho * L.wo * L.cout_pad * sizeof(int32_t);
   if (host_bytes < bytes) return fail(IEVM_ERR_BAD_ARG, "host buffer too small: need %zu bytes", bytes);
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   int32_t* dacc = nullptr;
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dacc), bytes));
+  cudaDeviceSynchronize();                  // parity hook: the forward that produced this layer's input is done
   int rc = L.is_stem ? launch_stem_tc(h, L, static_cast<const uint8_t*>(tensor_ptr(h, 0)),
                                       static_cast<uint8_t*>(tensor_ptr(h, L.d.out_tensor)), n, h->own_stream, dacc)
                      : launch_conv(h, L, n, h->own_stream, dacc);
@@ -1873,9 +2102,10 @@ int ievm_debug_frontend(ievm_handle* h, const void* x_dev, int n, void* pooled_h
   const size_t pooled = static_cast<size_t>(n) * Lp.ho * Lp.wo * Ls.cout_pad * h->elem;
   const size_t acc = static_cast<size_t>(n) * Ls.ho * Ls.wo * Ls.cout_pad * sizeof(int32_t);
   if (pooled_bytes < pooled || (acc_host && acc_bytes < acc)) return fail(IEVM_ERR_BAD_ARG, "debug_frontend: host buffer too small");
-  CUDA_TRY(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   int32_t* dacc = nullptr;
   if (acc_host) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dacc), acc));
+  cudaDeviceSynchronize();                  // parity hook: earlier work on other streams is done
   int rc = launch_frontend2(h, x_dev, n, h->own_stream, dacc);
   if (rc == IEVM_OK) rc = check_stuck(h, cudaStreamSynchronize(h->own_stream), "debug_frontend");
   if (rc == IEVM_OK && cudaMemcpy(pooled_host, tensor_ptr(h, Lp.d.out_tensor), pooled, cudaMemcpyDeviceToHost) != cudaSuccess)

@@ -122,9 +122,11 @@ __device__ __forceinline__ bool mbar_try_wait5(uint64_t* b0, uint32_t p0, uint64
   return ok != 0;
 }
 
-#ifndef IEVM_WAIT_LIMIT_NS
-#define IEVM_WAIT_LIMIT_NS 2000000000ull   // bounded mbarrier waits: a lost arrival must trap, never hang
-#endif
+// Bounded mbarrier waits: a lost arrival must trap, never hang a GPU box.  The limit is a __constant__ (default 2 s)
+// that the host can change (ievm_set_wait_limit_ms / IEVM_WAIT_LIMIT_MS; 0 = wait forever) for runs under ncu replay,
+// compute-sanitizer or GPU time-slicing, where two seconds of wall clock can pass legitimately.
+__constant__ unsigned long long g_wait_limit_ns = 2000000000ull;     // constant bank: a plain operand, no address registers
+#define IEVM_WAIT_LIMIT_NS (g_wait_limit_ns == 0ull ? ~0ull : g_wait_limit_ns)
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

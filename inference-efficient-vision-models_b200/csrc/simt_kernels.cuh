@@ -374,6 +374,7 @@ struct ConvDirectParams {
   int cin_real;
   int cout_pad;
   int ksize, stride, pad;
+  int in_zp;           // zero point of the input tensor (0 for every post-ReLU tensor)
 };
 
 __global__ void __launch_bounds__(128)
@@ -398,7 +399,7 @@ conv_direct_i8_kernel(const uint8_t* __restrict__ in, const int8_t* __restrict__
       if (ix < 0 || ix >= g.w) continue;
       const uint8_t* ip = in + ((static_cast<long long>(img) * g.h + iy) * g.w + ix) * g.cin_pitch;
       const int8_t* wr = wp + (static_cast<long long>(co) * taps + ky * g.ksize + kx) * g.cin_w;
-      for (int ci = 0; ci < g.cin_real; ++ci) acc += static_cast<int>(ip[ci]) * static_cast<int>(wr[ci]);
+      for (int ci = 0; ci < g.cin_real; ++ci) acc += (static_cast<int>(ip[ci]) - g.in_zp) * static_cast<int>(wr[ci]);
     }
   }
   if (p.dump_acc) p.dump_acc[m * p.dump_pitch + co] = acc;
@@ -528,15 +529,17 @@ __global__ void kd_loss_kernel(const float* __restrict__ s, const float* __restr
       ztt += expf(tr[c] / temp - mtt);
     }
     const float lzs = logf(zs), lzst = logf(zst), lztt = logf(ztt);
-    const int label = static_cast<int>(y[i]);
-    ce = -(sr[label] - ms - lzs);
+    const long long label64 = y[i];
+    const bool label_ok = label64 >= 0 && label64 < classes;       // an out-of-range label poisons the loss (NaN) instead
+    const int label = label_ok ? static_cast<int>(label64) : 0;    // of reading outside the row
+    ce = label_ok ? -(sr[label] - ms - lzs) : __int_as_float(0x7fc00000);
     for (int c = 0; c < classes; ++c) {
       const float logp_t = tr[c] / temp - mtt - lztt;
       const float logp_s = sr[c] / temp - mst - lzst;
       kl += expf(logp_t) * (logp_t - logp_s);
     }
     kl *= temp * temp;
-    correct = arg == label ? 1.f : 0.f;
+    correct = (label_ok && arg == label) ? 1.f : 0.f;
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -575,7 +578,7 @@ __global__ void count_correct_kernel(const T* __restrict__ logits, const long lo
         arg = c;
       }
     }
-    hit = arg == static_cast<int>(labels[i]) ? 1u : 0u;
+    hit = static_cast<long long>(arg) == labels[i] ? 1u : 0u;      // an out-of-range label never matches
   }
   const unsigned int warp_hits = __popc(__ballot_sync(0xffffffffu, hit != 0));
   if ((threadIdx.x & 31) == 0 && warp_hits) atomicAdd(counters, static_cast<unsigned long long>(warp_hits));

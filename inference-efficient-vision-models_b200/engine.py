@@ -135,6 +135,7 @@ class _B200Engine(nn.Module):
             return torch.cat([self.forward(images[i:i + self.max_batch]) for i in range(0, n, self.max_batch)])
         if not images.is_cuda:
             return self._forward_host(images)
+        self._check_device(images)
         x = images.contiguous()
         out = torch.empty((n, self.net.num_classes), dtype=self._torch_dtype, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
@@ -149,6 +150,43 @@ class _B200Engine(nn.Module):
         out = torch.empty((n, self.net.num_classes), dtype=self._torch_dtype)
         _lib.check(self._forward_host_fn(self._handle, x.data_ptr(), n, out.data_ptr()), "ievm_forward_host")
         return out
+
+    def _check_device(self, t: torch.Tensor) -> None:
+        if t.device.index != self.device_index:
+            raise ValueError(f"tensor is on cuda:{t.device.index} but this engine is bound to cuda:{self.device_index}")
+
+    # ---- pipelined host path: the reference's evaluation loops hand over one CPU batch per iteration --------------
+    def submit(self, images: torch.Tensor) -> "PendingLogits":
+        """Enqueue ``model(images)`` for a CPU batch and return at once (``ievm_submit_*_host``): the H2D copy of this
+        batch overlaps the forward of the previous one.  ``images`` is what ``forward`` accepts on the CPU (pinned
+        memory makes the copy asynchronous) or, for INT8 engines, decoded uint8 ``[N, h, w, 3]`` images.  At most two
+        batches are in flight; ``.result()`` of the returned object waits for this one's logits (a CPU tensor)."""
+        if images.is_cuda:
+            raise ValueError("submit() is the host-buffer path; call the engine directly with CUDA tensors")
+        n = int(images.shape[0])
+        if n == 0 or n > self.max_batch:
+            raise ValueError(f"submit() takes 1..{self.max_batch} images per call, got {n}")
+        x = images.contiguous()
+        if x.dtype == torch.uint8:
+            fn = self._submit_u8(x)
+        else:
+            if x.dim() != 4 or tuple(x.shape[1:]) != (self.net.in_c, self.net.in_h, self.net.in_w):
+                raise ValueError(f"expected [N,{self.net.in_c},{self.net.in_h},{self.net.in_w}], got {tuple(x.shape)}")
+            if x.dtype != self._torch_dtype:
+                raise TypeError(f"expected {self._torch_dtype} input, got {x.dtype}")
+            fn = self._submit_fn
+        if not hasattr(self, "_out_ring"):       # two pinned logits buffers, one per pipeline slot
+            self._out_ring = [torch.empty((self.max_batch, self.net.num_classes), dtype=self._torch_dtype).pin_memory()
+                              for _ in range(2)]
+            self._out_next = 0
+        out = self._out_ring[self._out_next]
+        self._out_next ^= 1
+        ticket = C.c_int64(-1)
+        _lib.check(fn(self._handle, x.data_ptr(), n, out.data_ptr(), C.byref(ticket)), "ievm_submit_host")
+        return PendingLogits(self, int(ticket.value), out, n, x)
+
+    def _submit_u8(self, x: torch.Tensor):
+        raise TypeError("uint8 image input belongs to the INT8 engine")
 
     def state_dict(self, *args, **kwargs):
         if self._source is not None and hasattr(self._source, "state_dict"):
@@ -249,6 +287,22 @@ class _B200Engine(nn.Module):
             pass
 
 
+class PendingLogits:
+    """Logits of a batch handed to ``submit()``; ``result()`` waits (``ievm_wait``) and returns them as a CPU tensor."""
+
+    def __init__(self, engine, ticket, out, n, keepalive):
+        self._engine, self._ticket, self._out, self._n, self._keepalive = engine, ticket, out, n, keepalive
+        self._value = None
+
+    def result(self) -> torch.Tensor:
+        if self._value is None:
+            eng = self._engine
+            _lib.check(eng._lib.ievm_wait(eng._handle, self._ticket), "ievm_wait")
+            self._value = self._out[:self._n].clone()       # the pinned slot is reused two submits later
+            self._keepalive = None
+        return self._value
+
+
 class B200QuantizedResNet(_B200Engine):
     """Drop-in for the converted static-INT8 module (fbgemm semantics, bit-exact target)."""
     _torch_dtype = torch.float32
@@ -259,6 +313,7 @@ class B200QuantizedResNet(_B200Engine):
         super().__init__(net, **kw)
         self._forward_fn = self._lib.ievm_forward_i8
         self._forward_host_fn = self._lib.ievm_forward_i8_host
+        self._submit_fn = self._lib.ievm_submit_i8_host
 
     @classmethod
     def from_converted(cls, gm, **kw) -> "B200QuantizedResNet":
@@ -272,6 +327,17 @@ class B200QuantizedResNet(_B200Engine):
         _lib.check(self._lib.ievm_set_input_lut(self._handle, lut.ctypes.data), "ievm_set_input_lut")
         self._lut = lut
         return lut
+
+    def _submit_u8(self, x: torch.Tensor):
+        if getattr(self, "_lut", None) is None:
+            self.set_input_transform()
+        if x.dim() != 4 or x.shape[3] != 3:
+            raise ValueError(f"expected uint8 [N,h,w,3], got {tuple(x.shape)}")
+        if tuple(x.shape[1:3]) == (self.net.in_h, self.net.in_w):
+            return self._lib.ievm_submit_u8_host
+        if getattr(self, "_resize_src", None) != tuple(x.shape[1:3]):
+            self.set_resize(x.shape[1], x.shape[2])
+        return self._lib.ievm_submit_u8_resize_host
 
     def set_resize(self, src_h: int, src_w: int) -> None:
         """Install ``T.Resize((in_h, in_w))`` (quantization/dataset.py:15: Pillow's bilinear resample) for decoded
@@ -311,6 +377,7 @@ class B200QuantizedResNet(_B200Engine):
             out = torch.empty((n, self.net.num_classes), dtype=torch.float32)
             _lib.check(self._lib.ievm_forward_u8_host(self._handle, x.data_ptr(), n, out.data_ptr()), "ievm_forward_u8_host")
             return out
+        self._check_device(x)
         out = torch.empty((n, self.net.num_classes), dtype=torch.float32, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _lib.check(self._lib.ievm_forward_u8(self._handle, x.data_ptr(), n, out.data_ptr(), stream), "ievm_forward_u8")
@@ -328,6 +395,7 @@ class B200QuantizedResNet(_B200Engine):
             _lib.check(self._lib.ievm_forward_u8_resize_host(self._handle, x.data_ptr(), n, out.data_ptr()),
                        "ievm_forward_u8_resize_host")
             return out
+        self._check_device(x)
         out = torch.empty((n, self.net.num_classes), dtype=torch.float32, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _lib.check(self._lib.ievm_forward_u8_resize(self._handle, x.data_ptr(), n, out.data_ptr(), stream), "ievm_forward_u8_resize")
@@ -348,6 +416,7 @@ class B200HalfResNet(_B200Engine):
         super().__init__(net, **kw)
         self._forward_fn = self._lib.ievm_forward_f16
         self._forward_host_fn = self._lib.ievm_forward_f16_host
+        self._submit_fn = self._lib.ievm_submit_f16_host
 
     @classmethod
     def from_half_module(cls, model, **kw) -> "B200HalfResNet":
@@ -359,12 +428,29 @@ def kd_eval_loss(student_logits: torch.Tensor, teacher_logits: torch.Tensor, lab
     """Soft-target KD loss of knowledge_distillation/train.py:47-57 on device logits.
     Returns (loss, ce, kd, n_correct) as a 4-element CUDA tensor without synchronising."""
     lib = _lib.load()
+    if student_logits.dim() != 2 or student_logits.shape != teacher_logits.shape:
+        raise ValueError(f"student / teacher logits must both be [N, classes]: {tuple(student_logits.shape)} vs "
+                         f"{tuple(teacher_logits.shape)}")
+    if labels.dim() != 1 or labels.shape[0] != student_logits.shape[0]:
+        raise ValueError(f"labels must be [N] = [{student_logits.shape[0]}], got {tuple(labels.shape)}")
+    if not student_logits.is_cuda or teacher_logits.device != student_logits.device or labels.device != student_logits.device:
+        raise ValueError("student logits, teacher logits and labels must live on the same CUDA device")
     s = student_logits.float().contiguous()
     t = teacher_logits.float().contiguous()
-    y = labels.to(torch.int64).contiguous()
+    y = labels.to(torch.int64).contiguous()       # a label outside [0, classes) makes the CE term NaN (no out-of-bounds read)
     out3 = torch.empty(3, dtype=torch.float32, device=s.device)
-    _lib.check(lib.ievm_kd_loss(s.data_ptr(), t.data_ptr(), y.data_ptr(), s.shape[0], s.shape[1],
-                                float(temperature), out3.data_ptr(),
-                                torch.cuda.current_stream(s.device).cuda_stream), "ievm_kd_loss")
+    with torch.cuda.device(s.device):
+        _lib.check(lib.ievm_kd_loss(s.data_ptr(), t.data_ptr(), y.data_ptr(), s.shape[0], s.shape[1],
+                                    float(temperature), out3.data_ptr(),
+                                    torch.cuda.current_stream(s.device).cuda_stream), "ievm_kd_loss")
     loss = (1.0 - alpha) * out3[0] + alpha * out3[1]
     return torch.stack([loss, out3[0], out3[1], out3[2]])
+
+
+def measure_mma_peak(dtype: str = "i8", device: int = 0, iters: int = 4000) -> float:
+    """Tera-ops/s this device's tensor cores sustain on a pure ``tcgen05.mma`` stream (``ievm_probe_mma_peak``):
+    the roofline denominator bench.py uses for the tensor-core kernels (no library INT8 GEMM exists to measure against)."""
+    lib = _lib.load()
+    out = C.c_double(0.0)
+    _lib.check(lib.ievm_probe_mma_peak(int(device), 0 if dtype == "i8" else 1, int(iters), C.byref(out)), "ievm_probe_mma_peak")
+    return float(out.value)

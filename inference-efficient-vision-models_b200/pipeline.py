@@ -95,8 +95,27 @@ def evaluate_accuracy(model, data_loader, device="cuda") -> float:
         param_dtype = torch.float32
     dev = torch.device("cuda", model.device_index) if isinstance(model, _B200Engine) else torch.device(device)
     counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    host_correct = host_total = 0
+    pending = []          # (PendingLogits, labels) of CPU batches in flight: at most two (ievm_submit_*_host)
+
+    def settle(item):
+        nonlocal host_correct, host_total
+        logits, lab = item[0].result(), item[1]
+        _, predicted = torch.max(logits.float(), 1)          # engines.py:61 (lowest index on ties)
+        host_total += int(lab.shape[0])
+        host_correct += int((predicted == lab).sum())
+
     with torch.no_grad():
         for images, labels in data_loader:
+            if isinstance(model, _B200Engine) and not images.is_cuda and 0 < images.shape[0] <= model.max_batch:
+                # the reference's loop hands over CPU batches (engines.py:52-60): pipelined host path -- the H2D copy of
+                # this batch overlaps the forward of the previous one, and nothing synchronises per batch
+                if images.dtype != torch.uint8 and param_dtype == torch.float16:
+                    images = images.half()
+                pending.append((model.submit(images), torch.as_tensor(labels).to(torch.int64)))
+                if len(pending) == 2:
+                    settle(pending.pop(0))
+                continue
             images = images.to(dev, non_blocking=True)
             labels = torch.as_tensor(labels).to(dev, dtype=torch.int64, non_blocking=True)
             if images.dtype == torch.uint8:
@@ -112,8 +131,10 @@ def evaluate_accuracy(model, data_loader, device="cuda") -> float:
             _lib.check(lib.ievm_count_correct(outputs.data_ptr(), dt, labels.data_ptr(), outputs.shape[0], outputs.shape[1],
                                               counters.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
                        "ievm_count_correct")
+        while pending:
+            settle(pending.pop(0))
     correct, total = (int(v) for v in counters.cpu())
-    return 100.0 * correct / max(total, 1)
+    return 100.0 * (correct + host_correct) / max(total + host_total, 1)
 
 
 def measure_latency(model, input_dummy, num_runs: int = 100) -> float:

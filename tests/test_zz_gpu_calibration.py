@@ -18,8 +18,8 @@ pytestmark = pytest.mark.gpu
 from oracle import int8_forward as O  # noqa: E402
 from oracle import model_factory as mf  # noqa: E402
 
-CALIB_REL_TOL = 2e-2     # |observer range ours - reference| / reference range (fp16 vs fp32 activations)
-TOP1_AGREE = 0.90        # top-1 agreement between the two INT8 networks (different qparams, same weights)
+CALIB_REL_TOL = 1.5e-2   # |observer range ours - reference| / reference range (fp16 vs fp32 activations; measured <= 1.06e-2)
+TOP1_AGREE = 0.99        # top-1 agreement between the two INT8 networks (different qparams, same weights; measured 100 %)
 
 
 def _prepared():
@@ -179,7 +179,7 @@ def test_gpu_histogram_calibration_matches_the_reference_fbgemm_calibration():
         worst = max(worst, abs(lb.out_scale / la.out_scale - 1), abs(lb.add_scale / la.add_scale - 1) if la.res_tensor >= 0 else 0)
         assert abs(lb.out_zp - la.out_zp) <= 3, la.name
     print(f"histogram flavour: worst relative scale deviation {worst:.2e}")
-    assert worst < 3e-2
+    assert worst < 1.5e-2
     e_ref = ievm_b200.B200QuantizedResNet(na, device=0, max_batch=128)
     e_ours = ievm_b200.B200QuantizedResNet(nb, device=0, max_batch=128)
     x = mf.synthetic_images(128, seed=21).cuda()
