@@ -389,8 +389,11 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
 // deep K (layers 3-4) are bound by how fast an SM can ingest operands (~40 B/clk), and the pair ingests
 // (128 + bn/2) instead of (128 + bn) rows per k-block for the same MMA work.  Only the leader (even) CTA issues
 // MMAs; full barriers live in the leader, empty / tmem-full barriers are signalled in both CTAs by the commit.
-template <int kDtype, bool kHasRes, int kMode, int kCluster, int kShape = 0>
-__global__ void __launch_bounds__(kConvThreads, 1)
+// kEpiW = 16 (576 threads, one CTA per SM) or 8 (320 threads, TWO CTAs per SM: layers whose operands fit in half of the
+// shared memory and half of TMEM run two independent producer -> MMA -> epilogue pipelines per SM, so that the stalls of
+// one -- the issuer's barrier tests, an epilogue group waiting for its accumulator -- are filled by the other).
+template <int kDtype, bool kHasRes, int kMode, int kCluster, int kShape = 0, int kEpiW = kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * kEpiW, kEpiW == 8 ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -417,7 +420,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5;       // warp-uniform
   const int lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < p.cout_pad; i += kConvThreads) {
+  constexpr int kThreads = 64 + 32 * kEpiW;
+  constexpr int kGroupsMax = kEpiW / 4;
+  for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) {
     s_ep0[i] = p.ep0[i];
     s_ep1[i] = p.ep1[i];
   }
@@ -433,7 +438,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int i = 0; i < p.nacc; ++i) {
       mbar_init(&tfull_bar[i], 1);
       // one arrival per warp of the owning group (of both CTAs of a pair); groups = min(4, nacc), see the epilogue
-      mbar_init(&tempty_bar[i], kCluster * kEpiWarps / (p.nacc < kEpiGroups ? p.nacc : kEpiGroups));
+      mbar_init(&tempty_bar[i], kCluster * kEpiW / (p.nacc < kGroupsMax ? p.nacc : kGroupsMax));
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -769,10 +774,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // groups = min(4, nacc) so that a TMEM buffer is always drained by the same group: a waiter can tell only
     // adjacent mbarrier phases apart, so it has to see every phase of the barriers it waits on.  With two
     // buffers (bn > 128) there are two groups of eight warps, two per quadrant, which interleave chunks.
-    const int groups = p.nacc < kEpiGroups ? p.nacc : kEpiGroups;      // 2 or 4
+    const int groups = p.nacc < kGroupsMax ? p.nacc : kGroupsMax;      // 2 or 4
     const int group = ((warp - 2) >> 2) & (groups - 1);
     const int sub = ((warp - 2) >> 2) / groups;                        // which of the group's warps of this quadrant
-    const int csub = kEpiGroups / groups;                              // warps per quadrant in a group
+    const int csub = kGroupsMax / groups;                              // warps per quadrant in a group
     const int row = quad * 32 + lane;
     const int nchunks = p.bn >> 4;
     griddep_wait();                     // before the first residual read / output store

@@ -154,6 +154,7 @@ struct LayerPlan {
   int wp = 0, patch_rows = 0, a_stage_bytes = 0, a_tx_bytes = 0;
   int sub_rows = 0, subs_per_img = 0, band_subs = 0;   // halo (band) mode, conv_tc.cuh
   int kb_group = 1;             // im2col mode: k-blocks per barrier pair
+  int two_cta = 0;              // halo mode, narrow INT8 layers: two 320-thread CTAs per SM (conv_tc.cuh, kEpiW = 8)
   size_t smem_bytes = 0;
   // device operands
   void* w_packed = nullptr;     // tensor-core layout [cout_pad][taps][cin_w]
@@ -180,6 +181,7 @@ struct ievm_handle {
   int num_sms = 0;
   int smem_optin = 0;
   int opt_halo = 1;        // IEVM_HALO=0 disables the halo-patch mode (all convs use per-tap im2col TMA)
+  int opt_two_cta = 1;     // IEVM_TWO_CTA=0: one CTA per SM for every layer
   int opt_halo_static = 1; // IEVM_HALO_STATIC=0: run-time-shaped halo kernel (class 0) even for the specialised shapes
   int opt_fused_front = 1; // IEVM_FUSED_FRONT=0: separate quantize / stem / maxpool kernels
   int front2_ok = 0;       // the network's front end fits frontend_v2.cuh (224-wide input, <= 64 stem channels)
@@ -385,6 +387,35 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
       while (acc_stride < L.bn) acc_stride *= 2;
       const int nacc = std::max(2, std::min(kMaxAcc, 512 / acc_stride));
       const int b_all = 9 * L.bn * rb;
+      // Two CTAs per SM (two independent pipelines that fill each other's stalls) when weights + >= 2 patch stages fit in
+      // half of the shared memory and the accumulators in half of TMEM: the 64-channel INT8 layers.
+      if (h->opt_two_cta && h->dtype == IEVM_DTYPE_I8 && halo_shape_class(wp, rb, L.bn) == 1 && h->opt_halo_static) {
+        const int half_smem = (h->smem_optin + 1024 /* per-CTA reservation */) / 2 - 1024 - 1024;
+        const int nacc2 = std::max(2, std::min(kMaxAcc, 256 / acc_stride));
+        const int S2 = std::max(1, std::min({kMaxBandSubs, nacc2 / 2, T}));
+        const int a_stage2 = round_up((S2 * R + 2) * wp * rb, 1024);
+        const int stages2 = std::min(8, (half_smem - fixed - b_all - 2048) / a_stage2);
+        if (stages2 >= 2) {
+          L.mode = kModeHalo;
+          L.two_cta = 1;
+          L.kc_bytes = rb;
+          L.kc_elems = rb / h->elem;
+          L.kchunks = 1;
+          L.cin_w = L.kc_elems;
+          L.wp = wp;
+          L.sub_rows = R;
+          L.subs_per_img = T;
+          L.band_subs = S2;
+          L.patch_rows = S2 * R + 2;
+          L.a_tx_bytes = L.patch_rows * wp * rb;
+          L.a_stage_bytes = a_stage2;
+          L.resident_b = 1;
+          L.stages = stages2;
+          L.kb_group = 1;
+          L.smem_bytes = static_cast<size_t>(L.stages) * a_stage2 + b_all + 2048 + fixed;
+          continue;
+        }
+      }
       // largest band (sub-tiles per patch) that leaves the epilogue half of the accumulator ring and >= 2 patch stages
       int best_s = 0, best_stages = 0, best_stage_bytes = 0;
       for (int S = std::min({kMaxBandSubs, nacc / 2 > 0 ? nacc / 2 : 1, T}); S >= 1; --S) {
@@ -896,7 +927,7 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   // accumulator ring: buffers a power-of-two number of columns apart, as many as TMEM's 512 columns hold (<= 8)
   p.acc_stride = 32;
   while (p.acc_stride < L.bn) p.acc_stride *= 2;
-  p.nacc = std::max(2, std::min(kMaxAcc, 512 / p.acc_stride));
+  p.nacc = std::max(2, std::min(kMaxAcc, (L.two_cta ? 256 : 512) / p.acc_stride));
   p.tmem_cols = p.nacc * p.acc_stride;
   p.fast_round = L.fast_round;
   const int mma_m = L.cluster > 1 ? 256 : 128;             // a CTA pair issues M = 256 instructions
@@ -970,6 +1001,17 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
   } while (0)
   // the shape-specialised kernels assume a zero input zero point (true for every post-ReLU tensor); others take class 0
   const int shape = (L.mode == kModeHalo && h->opt_halo_static && L.zcorr == nullptr) ? halo_shape_class(L.wp, L.kc_bytes, L.bn) : 0;
+  if (L.two_cta && shape == 1 && h->dtype == IEVM_DTYPE_I8) {
+    const int grid2 = std::min(p.m_tiles, 2 * h->num_sms);
+    if (has_res)
+      CUDA_TRY(launch_kernel_cluster(conv_tc_kernel<kDtypeI8, true, kModeHalo, 1, 1, 8>, grid2, 64 + 32 * 8, L.smem_bytes, s,
+                                     h->opt_pdl != 0, 1u, L.tmap_a, L.tmap_b, p));
+    else
+      CUDA_TRY(launch_kernel_cluster(conv_tc_kernel<kDtypeI8, false, kModeHalo, 1, 1, 8>, grid2, 64 + 32 * 8, L.smem_bytes, s,
+                                     h->opt_pdl != 0, 1u, L.tmap_a, L.tmap_b, p));
+    CUDA_TRY(cudaGetLastError());
+    return IEVM_OK;
+  }
   if (h->dtype == IEVM_DTYPE_I8) {
     if (has_res) IEVM_LAUNCH_MODE(kDtypeI8, true, 1, 2); else IEVM_LAUNCH_MODE(kDtypeI8, false, 1, 2);
   } else {
@@ -1433,6 +1475,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   h->in_scale = nd->in_scale; h->in_zp = nd->in_zp;
   if (const char* e = getenv("IEVM_HALO")) h->opt_halo = atoi(e);
   if (const char* e = getenv("IEVM_HALO_STATIC")) h->opt_halo_static = atoi(e);
+  if (const char* e = getenv("IEVM_TWO_CTA")) h->opt_two_cta = atoi(e);
   if (const char* e = getenv("IEVM_FIXED_BN")) h->opt_fixed_bn = atoi(e);
   if (const char* e = getenv("IEVM_PDL")) h->opt_pdl = atoi(e);
   if (const char* e = getenv("IEVM_CLUSTER")) h->opt_cluster = atoi(e);
@@ -1475,6 +1518,8 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
       IEVM_ATTR(kDtypeI8, false, kModeHalo, 1, 0);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1, 0);
       IEVM_ATTR(kDtypeI8, false, kModeHalo, 1, 1);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1, 1);
       IEVM_ATTR(kDtypeI8, false, kModeHalo, 1, 2);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1, 2);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<kDtypeI8, false, kModeHalo, 1, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<kDtypeI8, true, kModeHalo, 1, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
       IEVM_ATTR(kDtypeF16, false, kModeIm2col, 1, 0); IEVM_ATTR(kDtypeF16, true, kModeIm2col, 1, 0);
       IEVM_ATTR(kDtypeF16, false, kModeIm2col, 2, 0); IEVM_ATTR(kDtypeF16, true, kModeIm2col, 2, 0);
       IEVM_ATTR(kDtypeF16, false, kModeHalo, 1, 0);   IEVM_ATTR(kDtypeF16, true, kModeHalo, 1, 0);
