@@ -392,7 +392,9 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
 // kEpiW = 16 (576 threads, one CTA per SM) or 8 (320 threads, TWO CTAs per SM: layers whose operands fit in half of the
 // shared memory and half of TMEM run two independent producer -> MMA -> epilogue pipelines per SM, so that the stalls of
 // one -- the issuer's barrier tests, an epilogue group waiting for its accumulator -- are filled by the other).
-template <int kDtype, bool kHasRes, int kMode, int kCluster, int kShape = 0, int kEpiW = kEpiWarps>
+// kZc: the layer's input zero point is not 0 (ConvTcParams::zcorr); a separate instantiation so that the
+// register-starved default kernels carry none of it.
+template <int kDtype, bool kHasRes, int kMode, int kCluster, int kShape = 0, int kEpiW = kEpiWarps, bool kZc = false>
 __global__ void __launch_bounds__(64 + 32 * kEpiW, kEpiW == 8 ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ ConvTcParams p) {
@@ -830,7 +832,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (c < nchunks) tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), va);
       while (c < nchunks) {
         tmem_ld_wait();
-        if (kDtype == kDtypeI8 && zc != nullptr) {
+        if (kZc && zc != nullptr) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) va[j] -= static_cast<uint32_t>(__ldg(zc + n0 + c * 16 + j));
         }
@@ -842,7 +844,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         c += csub;
         if (c >= nchunks) break;
         tmem_ld_wait();
-        if (kDtype == kDtypeI8 && zc != nullptr) {
+        if (kZc && zc != nullptr) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) vb[j] -= static_cast<uint32_t>(__ldg(zc + n0 + c * 16 + j));
         }
@@ -884,6 +886,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           epilogue_chunk<kDtype, kHasRes>(p, vv[c & 1], rr[c & 1], m, valid, c * 16, p.epc0, p.epc1, k);
         }
+      } else {
+        // wide layers: the chunk loop stays a loop over chunk PAIRS (register budget); the tables are still read from
+        // the constant bank, through a uniform index
+#pragma unroll 1
+        for (int c = 0; c < kNch; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 1) * 16), vv[1]);
+          if (kResI8) rr[1] = load_res16_i8(p, m, valid, (c + 1) * 16);
+          epilogue_chunk<kDtype, kHasRes>(p, vv[0], rr[0], m, valid, c * 16, p.epc0, p.epc1, k);
+          tmem_ld_wait();
+          if (c + 2 < kNch) {
+            tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 2) * 16), vv[0]);
+            if (kResI8) rr[0] = load_res16_i8(p, m, valid, (c + 2) * 16);
+          }
+          epilogue_chunk<kDtype, kHasRes>(p, vv[1], rr[1], m, valid, (c + 1) * 16, p.epc0, p.epc1, k);
+        }
       }
 #endif
       tc_fence_before();
@@ -905,9 +923,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int oy = (t - img * p.subs_per_img) * p.sub_rows + sub_row;
         const bool valid = sub_ok && oy < p.h_in;
         const int m = (img * p.h_in + oy) * p.w_in + sub_x;
-        // narrow layers (<= 4 chunks): unrolled, constant-bank tables; wide layers keep the chunk loop (register budget)
-        if (kShape != 0 && halo_shape_bn(kShape) <= 64) drain_static(acc, acc_phase, m, valid);
-        else drain(acc, acc_phase, m, valid, 0, (kDtype == kDtypeI8 && p.zcorr != nullptr) ? zcorr_row(oy, sub_x) : nullptr);
+        if (kShape != 0) drain_static(acc, acc_phase, m, valid);
+        else drain(acc, acc_phase, m, valid, 0, kZc ? zcorr_row(oy, sub_x) : nullptr);
       }
     } else {
       int acc_next = 0, seq = 0;
@@ -928,7 +945,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int m_tile = kCluster > 1 ? m_group * kCluster + static_cast<int>(crank) : m_group;
         const int m = m_tile * kTileM + row;
         const int32_t* zc = nullptr;
-        if (kDtype == kDtypeI8 && p.zcorr != nullptr) {
+        if (kZc) {
           const int rem = m - (m / hw) * hw;
           zc = zcorr_row(rem / p.wo, rem - (rem / p.wo) * p.wo);
         }

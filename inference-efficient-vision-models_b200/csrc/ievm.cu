@@ -1001,6 +1001,22 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
   } while (0)
   // the shape-specialised kernels assume a zero input zero point (true for every post-ReLU tensor); others take class 0
   const int shape = (L.mode == kModeHalo && h->opt_halo_static && L.zcorr == nullptr) ? halo_shape_class(L.wp, L.kc_bytes, L.bn) : 0;
+  if (L.zcorr != nullptr && h->dtype == IEVM_DTYPE_I8) {
+    // non-zero input zero point: the run-time-shaped kernels with the border-aware correction compiled in
+#define IEVM_LAUNCH_ZC(RES, MODE, CL)                                                                                        \
+  CUDA_TRY(launch_kernel_cluster(conv_tc_kernel<kDtypeI8, RES, MODE, CL, 0, kEpiWarps, true>, grid, kConvThreads, L.smem_bytes, s, \
+                                 h->opt_pdl != 0, static_cast<unsigned>(CL), L.tmap_a, L.tmap_b, p))
+    if (L.mode == kModeHalo) {
+      if (has_res) IEVM_LAUNCH_ZC(true, kModeHalo, 1); else IEVM_LAUNCH_ZC(false, kModeHalo, 1);
+    } else if (cl == 2) {
+      if (has_res) IEVM_LAUNCH_ZC(true, kModeIm2col, 2); else IEVM_LAUNCH_ZC(false, kModeIm2col, 2);
+    } else {
+      if (has_res) IEVM_LAUNCH_ZC(true, kModeIm2col, 1); else IEVM_LAUNCH_ZC(false, kModeIm2col, 1);
+    }
+#undef IEVM_LAUNCH_ZC
+    CUDA_TRY(cudaGetLastError());
+    return IEVM_OK;
+  }
   if (L.two_cta && shape == 1 && h->dtype == IEVM_DTYPE_I8) {
     const int grid2 = std::min(p.m_tiles, 2 * h->num_sms);
     if (has_res)
@@ -1518,6 +1534,12 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
       IEVM_ATTR(kDtypeI8, false, kModeHalo, 1, 0);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1, 0);
       IEVM_ATTR(kDtypeI8, false, kModeHalo, 1, 1);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1, 1);
       IEVM_ATTR(kDtypeI8, false, kModeHalo, 1, 2);   IEVM_ATTR(kDtypeI8, true, kModeHalo, 1, 2);
+#define IEVM_ATTR_ZC(RES, MODE, CL) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<kDtypeI8, RES, MODE, CL, 0, kEpiWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms)
+      IEVM_ATTR_ZC(false, kModeIm2col, 1); IEVM_ATTR_ZC(true, kModeIm2col, 1);
+      IEVM_ATTR_ZC(false, kModeIm2col, 2); IEVM_ATTR_ZC(true, kModeIm2col, 2);
+      IEVM_ATTR_ZC(false, kModeHalo, 1);   IEVM_ATTR_ZC(true, kModeHalo, 1);
+#undef IEVM_ATTR_ZC
       if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<kDtypeI8, false, kModeHalo, 1, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<kDtypeI8, true, kModeHalo, 1, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
       IEVM_ATTR(kDtypeF16, false, kModeIm2col, 1, 0); IEVM_ATTR(kDtypeF16, true, kModeIm2col, 1, 0);

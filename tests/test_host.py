@@ -50,7 +50,7 @@ def test_hot_kernels_do_not_spill():
             # a handful of kernel-entry values (schedule bounds, ring pointers) may be parked on the stack of the shape-
             # specialised kernels -- reloaded once per warp role, never inside a tile loop; anything bigger is a real spill
             stack = int(re.search(r"STACK:(\d+)", usage).group(1))
-            assert stack <= 32 and "LOCAL:0 " in usage, f"{name}: {usage.strip()}"
+            assert stack <= 48 and "LOCAL:0 " in usage, f"{name}: {usage.strip()}"
             regs = int(re.search(r"REG:(\d+)", usage).group(1))
             assert regs <= (128 if "frontend2" in name else 96), f"{name}: {regs} registers"
     assert found >= 23          # 18 conv_tc instantiations, 3 front ends, 2 heads
