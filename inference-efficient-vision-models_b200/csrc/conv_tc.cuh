@@ -220,6 +220,12 @@ __device__ __forceinline__ int round_add(float x, int zp) {
   if (kFast) return __float_as_int(__fadd_rn(x, 12582912.0f)) + (zp - kRoundMagicBits);
   return __float2int_rn(x) + zp;
 }
+// max(rne(x) + zp, lo): with the magic add the integer add and the lower clamp are ONE instruction (VIADDMNMX).
+template <bool kFast>
+__device__ __forceinline__ int round_add_max(float x, int zp, int lo) {
+  if (kFast) return __viaddmax_s32(__float_as_int(__fadd_rn(x, 12582912.0f)), zp - kRoundMagicBits, lo);
+  return max(__float2int_rn(x) + zp, lo);
+}
 
 // 16 accumulators -> 16 requantised bytes (no residual).
 template <bool kFast>
@@ -235,10 +241,10 @@ __device__ __forceinline__ uint4 epilogue16_i8(const uint32_t (&v)[16], const fl
     const float4 b4 = *reinterpret_cast<const float4*>(s_bd + 4 * j);
     const float4 m4 = *reinterpret_cast<const float4*>(s_mu + 4 * j);
 #endif
-    q[4 * j + 0] = max(round_add<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 0])), b4.x), m4.x), zp), lo);
-    q[4 * j + 1] = max(round_add<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 1])), b4.y), m4.y), zp), lo);
-    q[4 * j + 2] = max(round_add<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 2])), b4.z), m4.z), zp), lo);
-    q[4 * j + 3] = max(round_add<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 3])), b4.w), m4.w), zp), lo);
+    q[4 * j + 0] = round_add_max<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 0])), b4.x), m4.x), zp, lo);
+    q[4 * j + 1] = round_add_max<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 1])), b4.y), m4.y), zp, lo);
+    q[4 * j + 2] = round_add_max<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 2])), b4.z), m4.z), zp, lo);
+    q[4 * j + 3] = round_add_max<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 3])), b4.w), m4.w), zp, lo);
   }
   return make_uint4(pack4_sat_u8(q[0], q[1], q[2], q[3]), pack4_sat_u8(q[4], q[5], q[6], q[7]),
                     pack4_sat_u8(q[8], q[9], q[10], q[11]), pack4_sat_u8(q[12], q[13], q[14], q[15]));
@@ -270,7 +276,9 @@ __device__ __forceinline__ uint4 epilogue16_i8_res(const uint32_t (&v)[16], cons
         // max(s, 0) before the final scaling equals clamping the rounded value at 0 (the scale is positive), so
         // each clamp pair is ONE add-min-relu instruction instead of two FMNMX (the ALU pipe issues at half rate).
         const int tq = __viaddmin_s32_relu(__float_as_int(__fadd_rn(t, kRoundMagic)), k.c1_add, k.c1_max);   // q2 - lo
-        const float a = __fmaf_rn(k.a_scale, __fadd_rn(__int2float_rn(tq), k.lo_q), k.pa);                  // fma(s2, q2, fl(s2 * -zp2))
+        // the fast form is only enabled for a conv without its own ReLU (lower clamp 0: every residual conv of a ResNet),
+        // so q2 == tq and the float(lo) addend is gone
+        const float a = __fmaf_rn(k.a_scale, __int2float_rn(tq), k.pa);                                      // fma(s2, q2, fl(s2 * -zp2))
         const float u = __fmul_rn(__fadd_rn(a, rb), k.inv_scale);
         q[i] = __viaddmin_s32_relu(__float_as_int(__fadd_rn(u, kRoundMagic)), k.c2_add, k.c2_max);          // q - add_zp
       } else {

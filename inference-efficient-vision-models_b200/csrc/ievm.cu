@@ -568,6 +568,7 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
     }
     if (d.res_tensor >= 0) vmax = std::max(vmax, 256.0 * (static_cast<double>(d.out_scale) + d.res_scale) / d.add_scale);
     L.fast_round = vmax < 2097152.0 ? 1 : 0;       // 2^21: a factor two of margin
+    if (d.res_tensor >= 0 && d.relu) L.fast_round = 0;   // the fast fused add_relu assumes the conv's own lower clamp is 0
     if (const char* e = getenv("IEVM_FAST_ROUND")) L.fast_round = L.fast_round && atoi(e);
   } else {
     for (int c = 0; c < d.cout; ++c) ep0[c] = d.bias[c];
