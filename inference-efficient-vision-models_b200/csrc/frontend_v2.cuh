@@ -106,6 +106,7 @@ struct Frontend2Params {
   const int* zwsum;          // i8: in_zp * sum(w[c])
   const uint8_t* lut;        // u8 input mode: [3][256] quantised value of every 8-bit level per channel
   int out_zp, out_lo;
+  int fast_round;            // i8: see ConvTcParams::fast_round
   int32_t* dump_acc;         // debug: corrected stem accumulators [n][ho][112][64] (f16: float bit patterns)
   unsigned int* stuck_flag;
 };
@@ -159,7 +160,7 @@ __device__ __forceinline__ uint32_t f2_max3(uint32_t a, uint32_t b, uint32_t c) 
 }
 
 // Epilogue of one warpgroup (kWg = 0: pooled columns 0..27, kWg = 1: 28..55).
-template <int kDtype, int kWg, int kSlots>
+template <int kDtype, int kWg, int kSlots, bool kFast>
 __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t tmem_base, uint64_t* tmem_full,
                                             uint64_t* tmem_empty, uint4* s_x, int units) {
   constexpr int kOff = kWg == 0 ? -1 : 7;        // register index of a pooled column's first stem column: 2k + kOff
@@ -176,6 +177,10 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
   const int out_elem = kDtype == kDtypeI8 ? 1 : 2;
   uint4* xs = s_x + kWg * 2 * kF2XRows * 64;
 
+#ifdef IEVM_EXP_TIMING
+  long long f2_tm_wait = 0;
+  const long long f2_tm_t0 = clock64();
+#endif
   uint32_t prev[kF2PxPerWg];                     // upper threads: horizontal maxima of the previous tile's row
 #pragma unroll
   for (int k = 0; k < kF2PxPerWg; ++k) prev[k] = kLow;
@@ -191,7 +196,13 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
         ts_next = 0;
         ph_next ^= 1u;
       }
+#ifdef IEVM_EXP_TIMING
+      const long long tw0 = clock64();
+#endif
       wait_or_die(&tmem_full[ts], ph, 0x840u | ts, p.stuck_flag);
+#ifdef IEVM_EXP_TIMING
+      f2_tm_wait += clock64() - tw0;
+#endif
       tc_fence_after();
       const uint32_t taddr = lane_addr + static_cast<uint32_t>(ts * kF2TmemSlotCols);
       const bool real = i > 0;
@@ -257,7 +268,14 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
                       (((static_cast<size_t>(un.img) * p.ph + T) * kF2Pw + kWg * kF2PxPerWg) * 64 + c) * out_elem;
       auto finish = [&](int k, uint32_t m) {
         if (kDtype == kDtypeI8) {
-          orow[k * 64] = static_cast<uint8_t>(requant_i8(static_cast<int>(m) - zw, bd, mu, p.out_zp, p.out_lo));
+          if (kFast) {
+            // magic-number rounding (|value| < 2^21 for every possible input, checked at engine creation): FADD instead
+            // of the 8-cycle F2I, and the zero-point add and lower clamp in one VIADDMNMX
+            const float v = __fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(m) - zw), bd), mu);
+            orow[k * 64] = static_cast<uint8_t>(min(round_add_max<true>(v, p.out_zp, p.out_lo), 255));
+          } else {
+            orow[k * 64] = static_cast<uint8_t>(requant_i8(static_cast<int>(m) - zw, bd, mu, p.out_zp, p.out_lo));
+          }
         } else {
           reinterpret_cast<__half*>(orow)[k * 64] = __float2half_rn(fmaxf(__uint_as_float(m) + bd, 0.f));
         }
@@ -283,9 +301,16 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
       }
     }
   }
+#ifdef IEVM_EXP_TIMING
+  if (threadIdx.x == 0 && blockIdx.x < kExpCtas) {
+    unsigned long long* o = g_exp_timing + (static_cast<size_t>(31) * kExpCtas + blockIdx.x) * kExpWords;
+    o[6] = clock64() - f2_tm_t0;
+    o[7] = f2_tm_wait;
+  }
+#endif
 }
 
-template <int kDtype, int kIn>
+template <int kDtype, int kIn, bool kFast = false>
 __global__ void __launch_bounds__(kF2Threads, 1)
 frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Params p) {
   using Cfg = F2Cfg<kDtype, kIn>;
@@ -362,8 +387,8 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
   const int units = p.n * p.upi;
 
   if (warp < kF2EpiWarps) {
-    if (warp < 4) f2_epilogue<kDtype, 0, Cfg::kSlots>(p, tmem_base, tmem_full, tmem_empty, sX, units);
-    else f2_epilogue<kDtype, 1, Cfg::kSlots>(p, tmem_base, tmem_full, tmem_empty, sX, units);
+    if (warp < 4) f2_epilogue<kDtype, 0, Cfg::kSlots, kFast>(p, tmem_base, tmem_full, tmem_empty, sX, units);
+    else f2_epilogue<kDtype, 1, Cfg::kSlots, kFast>(p, tmem_base, tmem_full, tmem_empty, sX, units);
   } else if (warp == kF2MmaWarp) {
     // ================================ MMA issuer ================================
     const uint32_t hi = (128u >> 4) | (1u << 14);                                  // SBO = 128 B, version 1, no swizzle
@@ -371,6 +396,10 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
     const uint32_t b_lo0 = ((smem_u32(sLines) & 0x3FFFFu) >> 4) | (1u << 16);          // LBO = 16 B (next record)
     int q0 = 0, t = 0, ts = 0;
     uint32_t ph = 0;
+#ifdef IEVM_EXP_TIMING
+    long long f2_wait = 0, f2_wait_line = 0;
+    const long long f2_t0 = clock64();
+#endif
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const F2Unit un = f2_unit(p, u);
       for (int i = 0; i <= un.nt; ++i, ++t) {
@@ -381,10 +410,22 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
           uint64_t* b0 = &line_full[qn % kF2ChunkSlots];
           uint64_t* b1 = &tmem_empty[ts];
           const uint32_t p0 = (qn / kF2ChunkSlots) & 1u, p1 = ph ^ 1u;
+#ifdef IEVM_EXP_TIMING
+          const long long tw0 = clock64();
+#endif
           if (!mbar_try_wait5(b0, p0, b1, p1, b1, p1, b1, p1, b1, p1)) {
+#ifdef IEVM_EXP_TIMING
+            const long long tw1 = clock64();
             wait_or_die(b0, p0, 0x820u | (qn % kF2ChunkSlots), p.stuck_flag);
+            f2_wait_line += clock64() - tw1;
+#else
+            wait_or_die(b0, p0, 0x820u | (qn % kF2ChunkSlots), p.stuck_flag);
+#endif
             wait_or_die(b1, p1, 0x830u | ts, p.stuck_flag);
           }
+#ifdef IEVM_EXP_TIMING
+          f2_wait += clock64() - tw0;
+#endif
         }
         tc_fence_after();
         fence_proxy_async_smem();
@@ -414,14 +455,35 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
       }
       q0 += un.nt + 3;
     }
+#ifdef IEVM_EXP_TIMING
+    if (lane == 0 && blockIdx.x < kExpCtas) {
+      unsigned long long* o = g_exp_timing + (static_cast<size_t>(31) * kExpCtas + blockIdx.x) * kExpWords;
+      o[0] = clock64() - f2_t0;
+      o[1] = f2_wait_line;
+      o[2] = f2_wait;
+      o[8] = t;
+      o[9] = clock64() - f2_t0;
+      o[10] = 1;
+    }
+#endif
   } else if (warp == kF2TmaWarp) {
     // ================================ TMA producer: raw input rows ================================
     int q = 0;
+#ifdef IEVM_EXP_TIMING
+    long long f2_wait = 0;
+    const long long f2_t0 = clock64();
+#endif
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const F2Unit un = f2_unit(p, u);
       for (int j = 0; j < un.nt + 3; ++j, ++q) {
         const int slot = q % kF2RawSlots;
+#ifdef IEVM_EXP_TIMING
+        const long long tw0 = clock64();
+#endif
         wait_or_die(&raw_empty[slot], ((q / kF2RawSlots) & 1u) ^ 1u, 0x800u | slot, p.stuck_flag);
+#ifdef IEVM_EXP_TIMING
+        f2_wait += clock64() - tw0;
+#endif
         if (elect_one()) {
           mbar_expect_tx(&raw_full[slot], static_cast<uint32_t>(Cfg::kRawTx));
           if (kIn == 1)     // (32-bit words of a row, row, image): 4 words = 16 bytes before the first pixel
@@ -434,16 +496,37 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
         __syncwarp();
       }
     }
+#ifdef IEVM_EXP_TIMING
+    if (lane == 0 && blockIdx.x < kExpCtas) {
+      unsigned long long* o = g_exp_timing + (static_cast<size_t>(31) * kExpCtas + blockIdx.x) * kExpWords;
+      o[4] = clock64() - f2_t0;
+      o[5] = f2_wait;
+    }
+#endif
   } else {
     // ================================ quantisers: raw rows -> records ================================
     const int qt = threadIdx.x - 32 * kF2FirstQuantWarp;
     int q = 0;
+#ifdef IEVM_EXP_TIMING
+    long long f2_wait_raw = 0, f2_wait_line = 0;
+    const long long f2_t0 = clock64();
+#endif
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const F2Unit un = f2_unit(p, u);
       for (int j = 0; j < un.nt + 3; ++j, ++q) {
         const int slot = q % kF2RawSlots, cs = q % kF2ChunkSlots;
+#ifdef IEVM_EXP_TIMING
+        const long long tw0 = clock64();
+#endif
         wait_or_die(&raw_full[slot], (q / kF2RawSlots) & 1u, 0x810u | slot, p.stuck_flag);
+#ifdef IEVM_EXP_TIMING
+        const long long tw1 = clock64();
+        f2_wait_raw += tw1 - tw0;
+#endif
         wait_or_die(&line_empty[cs], ((q / kF2ChunkSlots) & 1u) ^ 1u, 0x818u | cs, p.stuck_flag);
+#ifdef IEVM_EXP_TIMING
+        f2_wait_line += clock64() - tw1;
+#endif
         const uint8_t* raw = sRaw + slot * Cfg::kRawStride;
         uint8_t* lines = sLines + cs * Cfg::kLpc * kF2LinePitch;
         if (kIn == 1) {
@@ -534,6 +617,14 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
         mbar_arrive(&line_full[cs]);
       }
     }
+#ifdef IEVM_EXP_TIMING
+    if (qt == 0 && blockIdx.x < kExpCtas) {
+      unsigned long long* o = g_exp_timing + (static_cast<size_t>(31) * kExpCtas + blockIdx.x) * kExpWords;
+      o[11] = clock64() - f2_t0;
+      o[12] = f2_wait_raw;
+      o[13] = f2_wait_line;
+    }
+#endif
   }
 
   tc_fence_before();

@@ -1189,10 +1189,13 @@ int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32
   fp.lut = h->lut_dev;
   fp.out_zp = Ls.d.out_zp;
   fp.out_lo = Ls.d.relu ? Ls.d.out_zp : 0;
+  fp.fast_round = Ls.fast_round;
   fp.dump_acc = dump_acc;
   fp.stuck_flag = h->stuck_dev;
   const int grid = std::min(n * fp.upi, h->num_sms);
-  if (u8_input) frontend2_kernel<kDtypeI8, 1><<<grid, kF2Threads, F2Cfg<kDtypeI8, 1>::kSmemBytes, s>>>(tmap, fp);
+  if (u8_input && fp.fast_round) frontend2_kernel<kDtypeI8, 1, true><<<grid, kF2Threads, F2Cfg<kDtypeI8, 1>::kSmemBytes, s>>>(tmap, fp);
+  else if (u8_input) frontend2_kernel<kDtypeI8, 1><<<grid, kF2Threads, F2Cfg<kDtypeI8, 1>::kSmemBytes, s>>>(tmap, fp);
+  else if (i8 && fp.fast_round) frontend2_kernel<kDtypeI8, 0, true><<<grid, kF2Threads, F2Cfg<kDtypeI8>::kSmemBytes, s>>>(tmap, fp);
   else if (i8) frontend2_kernel<kDtypeI8, 0><<<grid, kF2Threads, F2Cfg<kDtypeI8>::kSmemBytes, s>>>(tmap, fp);
   else frontend2_kernel<kDtypeF16, 0><<<grid, kF2Threads, F2Cfg<kDtypeF16>::kSmemBytes, s>>>(tmap, fp);
   CUDA_TRY(cudaGetLastError());
@@ -1577,9 +1580,13 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
         : cudaFuncSetAttribute(frontend2_kernel<kDtypeF16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2Cfg<kDtypeF16>::kSmemBytes);
     if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend2_kernel): %s", cudaGetErrorString(e));
     if (rc == IEVM_OK && h->dtype == IEVM_DTYPE_I8 &&
-        cudaFuncSetAttribute(frontend2_kernel<kDtypeI8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)F2Cfg<kDtypeI8, 1>::kSmemBytes) != cudaSuccess)
-      rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend2_kernel, u8 input) failed");
+        (cudaFuncSetAttribute(frontend2_kernel<kDtypeI8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)F2Cfg<kDtypeI8, 1>::kSmemBytes) != cudaSuccess ||
+         cudaFuncSetAttribute(frontend2_kernel<kDtypeI8, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)F2Cfg<kDtypeI8, 1>::kSmemBytes) != cudaSuccess ||
+         cudaFuncSetAttribute(frontend2_kernel<kDtypeI8, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)F2Cfg<kDtypeI8>::kSmemBytes) != cudaSuccess))
+      rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend2_kernel, u8 input / fast rounding) failed");
   }
   if (rc == IEVM_OK) {
     for (const LayerPlan& L : h->layers)

@@ -35,3 +35,13 @@ for li, L in enumerate(eng.net.layers):
     mhz = 1e3 * a[live][:, 9].sum() / max(a[live][:, 10].sum(), 1)
     print(f"{L.name:22s} {int(live.sum()):4d} {4 * m[8]:8.1f}  | {m[9]:9.0f} {mhz:6.0f} | {m[0]:9.0f} {m[1]:9.0f} {m[2]:8.0f} | {m[4]:9.0f} {m[5]:8.0f} | "
           f"{m[6]:9.0f} {m[7]:8.0f}")
+
+a = t[31]
+live = a[:, 10] > 0
+if live.any():
+    m = a[live].mean(0)
+    print(f"front end (frontend2_kernel), {int(live.sum())} CTAs, {m[8]:.1f} tiles/CTA:")
+    print(f"  MMA warp   loop {m[0]:9.0f}  wait (both barriers) {m[2]:8.0f}  of which blocking wait for records {m[1]:8.0f}")
+    print(f"  TMA warp   loop {m[4]:9.0f}  wait raw slot free {m[5]:8.0f}")
+    print(f"  quantiser  loop {m[11]:9.0f}  wait raw rows {m[12]:8.0f}  wait line slot free {m[13]:8.0f}")
+    print(f"  epilogue   loop {m[6]:9.0f}  wait accumulator {m[7]:8.0f}")
