@@ -191,6 +191,10 @@ int ievm_num_tensors(const ievm_handle* h);
 int ievm_tensor_shape(const ievm_handle* h, int id, int32_t out6[6]);
 /* Number of kernel launches one forward() enqueues. */
 int ievm_launches_per_forward(const ievm_handle* h);
+/* Index of the layer whose kernel launch computes `layer`: the layer itself, except that a residual block's 1x1
+ * downsample conv runs as a second tile class of the block's first 3x3 conv (option "dual", default on) and the
+ * max-pool runs inside the fused front end (layer 0).  -1 for a bad index. */
+int ievm_layer_launch(const ievm_handle* h, int layer);
 
 /* Per-launch device timing.  With ievm_set_option(h, "profile", 1) every forward brackets each of its
  * launches with CUDA events on the caller's stream and synchronises at the end (not for timed

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 EXPORTS = [
     "ievm_create", "ievm_destroy", "ievm_forward_i8", "ievm_forward_f16", "ievm_forward_i8_host",
     "ievm_forward_f16_host", "ievm_set_option", "ievm_num_tensors", "ievm_tensor_shape",
-    "ievm_launches_per_forward", "ievm_debug_read_tensor", "ievm_debug_conv_acc", "ievm_kd_loss",
+    "ievm_launches_per_forward", "ievm_layer_launch", "ievm_debug_read_tensor", "ievm_debug_conv_acc", "ievm_kd_loss",
     "ievm_last_error", "ievm_build_info", "ievm_probe_im2col", "ievm_profile_read", "ievm_probe_patch",
     "ievm_debug_frontend", "ievm_set_input_lut", "ievm_forward_u8", "ievm_forward_u8_host",
     "ievm_count_correct", "ievm_set_resize", "ievm_forward_u8_resize", "ievm_forward_u8_resize_host", "ievm_debug_resize",
@@ -110,6 +110,8 @@ def load():
     lib.ievm_num_tensors.argtypes = [H]
     lib.ievm_tensor_shape.argtypes = [H, C.c_int, C.POINTER(C.c_int32 * 6)]
     lib.ievm_launches_per_forward.argtypes = [H]
+    lib.ievm_layer_launch.argtypes = [H, C.c_int]
+    lib.ievm_layer_launch.restype = C.c_int
     lib.ievm_debug_read_tensor.argtypes = [H, C.c_int, C.c_void_p, C.c_uint64]
     lib.ievm_debug_conv_acc.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
     lib.ievm_kd_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p,

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "conv_tc.cuh"
+#include "conv_dual.cuh"
 #include "simt_kernels.cuh"
 #include "stem_tc.cuh"
 #include "frontend_v2.cuh"
@@ -169,6 +170,12 @@ struct LayerPlan {
   float* ep1 = nullptr;
   std::vector<float> ep0_host, ep1_host;   // copies for the kernel-parameter block (ConvTcParams::epc0 / epc1)
   CUtensorMap tmap_a, tmap_b;
+  // conv_dual.cuh: a block's first 3x3 conv runs the block's 1x1 downsample (the next layer) as a second tile class
+  int dual_partner = -1;        // on the 3x3: index of the downsample layer
+  int dual_of = -1;             // on the downsample: index of the 3x3 whose launch computes it
+  int dual_stages = 0, dual_kb_group = 1, dual_max_clusters = 0;
+  size_t dual_smem_bytes = 0;
+  CUtensorMap tmap_b2;          // the downsample's weights with the 3x3's N-tile box
 };
 
 }  // namespace
@@ -199,6 +206,7 @@ struct ievm_handle {
   int opt_cluster = 1;     // IEVM_CLUSTER=0: no 2-CTA clusters / weight multicast
   int opt_pdl = 1;         // IEVM_PDL=0: no programmatic dependent launch
   int opt_fixed_bn = 0;    // IEVM_FIXED_BN=1: one N tile per <=256 channels (disables the tile-width heuristic)
+  int opt_dual = 1;        // IEVM_DUAL=0 / option "dual": the 1x1 downsample convs run as launches of their own
   int front_chunk = 0;     // IEVM_FRONT_CHUNK: images per front-end chunk (0 = whole batch at once, default)
   // IEVM_HALO_RB128=1: 64-byte pixels use 128-byte shared-memory rows in halo mode
   int in_c = 0, in_h = 0, in_w = 0, classes = 0;
@@ -538,6 +546,43 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
     L.smem_bytes = static_cast<size_t>(L.stages) * L.kb_group * a_bytes +
                    static_cast<size_t>(L.resident_b ? num_kb : L.stages * L.kb_group) * b_bytes + fixed;
   }
+  // ---- dual launches (conv_dual.cuh): a 3x3 conv next to a 1x1 conv of the same stride on the same tensor (either order:
+  // the FX graph of the INT8 module lists conv1 first, the FP16 flattening the downsample) ----
+  for (size_t j = 0; j + 1 < 2 * h->layers.size(); ++j) {
+    const size_t i = j / 2;
+    if (i + 1 >= h->layers.size()) break;
+    LayerPlan& P = h->layers[(j & 1) ? i + 1 : i];
+    LayerPlan& D = h->layers[(j & 1) ? i : i + 1];
+    const ievm_layer_desc& a = P.d;
+    const ievm_layer_desc& b = D.d;
+    if (P.dual_partner >= 0 || P.dual_of >= 0 || D.dual_partner >= 0 || D.dual_of >= 0) continue;
+    if (a.op != IEVM_OP_CONV || b.op != IEVM_OP_CONV || P.is_stem || D.is_stem) continue;
+    if (P.mode != kModeIm2col || D.mode != kModeIm2col || a.ksize != 3 || a.pad != 1 || b.ksize != 1 || b.pad != 0) continue;
+    if (a.stride != b.stride || a.in_tensor != b.in_tensor || a.cout != b.cout || a.res_tensor >= 0 || b.res_tensor >= 0) continue;
+    if (P.cout_pad != D.cout_pad || P.kc_bytes != D.kc_bytes || P.kchunks != D.kchunks) continue;
+    if (h->dtype == IEVM_DTYPE_I8 && (a.in_zp != 0 || b.in_zp != 0)) continue;      // zero-point correction: separate launches
+    constexpr int kMaxStages = 16;
+    const int fixed2 = 1024 + 4 * P.cout_pad * 4 + (2 * kMaxStages + 2 * kMaxAcc + 1) * 8 + 16;
+    const int avail2 = h->smem_optin - fixed2;
+    const int a_bytes = kTileM * P.kc_bytes;
+    const int b_bytes = (P.bn / P.cluster) * P.kc_bytes;
+    const int num_kb = 9 * P.kchunks;
+    const int slots = P.resident_b ? std::min(kMaxStages, (avail2 - (num_kb + P.kchunks) * b_bytes) / a_bytes)
+                                   : std::min(kMaxStages, avail2 / (a_bytes + b_bytes));
+    if (slots < 2) continue;
+    int G = 1;
+    for (int g = 4; g >= 2; --g)
+      if (num_kb % g == 0 && slots / g >= 3) {
+        G = g;
+        break;
+      }
+    P.dual_partner = static_cast<int>(&D - h->layers.data());
+    D.dual_of = static_cast<int>(&P - h->layers.data());
+    P.dual_kb_group = G;
+    P.dual_stages = slots / G;
+    P.dual_smem_bytes = static_cast<size_t>(P.dual_stages) * G * a_bytes +
+                        static_cast<size_t>(P.resident_b ? num_kb + P.kchunks : P.dual_stages * G) * b_bytes + fixed2;
+  }
   return IEVM_OK;
 }
 
@@ -798,7 +843,14 @@ int assign_buffers(ievm_handle* h) {
     const LayerPlan& L = h->layers[i];
     if (L.d.op != IEVM_OP_HEAD) {
       TensorInfo& t = h->tensors[L.d.out_tensor];
-      t.buffer = take(t.bytes_per_image() * ((chunked && i == 0) ? front_imgs : static_cast<size_t>(h->max_batch)));
+      if (t.buffer < 0)
+        t.buffer = take(t.bytes_per_image() * ((chunked && i == 0) ? front_imgs : static_cast<size_t>(h->max_batch)));
+      // a dual launch (conv_dual.cuh) writes both convs' outputs at the position of the first of the two
+      const int mate = L.dual_partner >= 0 ? L.dual_partner : L.dual_of;
+      if (mate > static_cast<int>(i)) {
+        TensorInfo& tm = h->tensors[h->layers[mate].d.out_tensor];
+        tm.buffer = take(tm.bytes_per_image() * static_cast<size_t>(h->max_batch));
+      }
     }
     if (!h->keep_tensors)
       for (size_t ti = (f16 ? 0 : 1); ti < h->tensors.size(); ++ti) {   // the INT8 input keeps its bordered buffer
@@ -879,6 +931,19 @@ int encode_maps(ievm_handle* h) {
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled failed for layer %zu: CUresult %d", i, (int)r);
+    }
+    if (L.dual_partner >= 0) {
+      // the downsample's packed weights (one tap) read with THIS layer's N-tile box
+      const LayerPlan& D = h->layers[L.dual_partner];
+      const size_t k_total = D.cin_w;
+      cuuint64_t dims[2] = {k_total, static_cast<cuuint64_t>(D.cout_pad)};
+      cuuint64_t strides[1] = {k_total * e};
+      cuuint32_t box[2] = {static_cast<cuuint32_t>(L.kc_elems), static_cast<cuuint32_t>(L.bn / L.cluster)};
+      cuuint32_t estr[2] = {1, 1};
+      const CUresult r = g_encode_tiled(&L.tmap_b2, dt, 2, D.w_packed, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled (dual weights) failed for layer %zu: CUresult %d", i, (int)r);
     }
   }
   return IEVM_OK;
@@ -1036,6 +1101,42 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
   }
 #undef IEVM_LAUNCH_MODE
 #undef IEVM_LAUNCH
+  CUDA_TRY(cudaGetLastError());
+  return IEVM_OK;
+}
+
+// Are the 1x1 downsample convs computed inside their block's first 3x3 launch (conv_dual.cuh)?
+bool dual_active(const ievm_handle* h) { return h->opt_dual && h->conv_impl == 0; }
+
+// Layer P (3x3) and its partner (the block's 1x1 downsample) in one launch; dump0 / dump1: debug accumulators per class.
+int launch_conv_dual(ievm_handle* h, const LayerPlan& P, int n, cudaStream_t s, int32_t* dump0, int32_t* dump1) {
+  const LayerPlan& D = h->layers[P.dual_partner];
+  ConvTcParams p = make_conv_params(h, P, n, dump0);
+  p.stages = P.dual_stages;
+  p.kb_group = P.dual_kb_group;
+  ConvDualParams x;
+  memset(&x, 0, sizeof(x));
+  x.out = tensor_ptr(h, D.d.out_tensor);
+  x.ep0 = D.ep0;
+  x.ep1 = D.ep1;
+  x.out_zp = D.d.out_zp;
+  x.out_lo = D.d.relu ? D.d.out_zp : 0;
+  x.fast_round = D.fast_round;
+  x.relu = D.d.relu;
+  x.dump_acc = dump1;
+  const int cl = P.cluster;
+  const int class_tiles = ((p.m_tiles + cl - 1) / cl) * p.n_tiles;
+  const int max_cl = cl > 1 ? (P.dual_max_clusters > 0 ? P.dual_max_clusters : h->num_sms / cl) : h->num_sms;
+  const int grid = std::min(2 * class_tiles, max_cl) * cl;
+#define IEVM_LAUNCH_DUAL(DT, CL)                                                                                        \
+  CUDA_TRY(launch_kernel_cluster(conv_dual_kernel<DT, CL>, grid, kConvThreads, P.dual_smem_bytes, s, h->opt_pdl != 0, \
+                                 static_cast<unsigned>(CL), P.tmap_a, P.tmap_b, P.tmap_b2, p, x))
+  if (h->dtype == IEVM_DTYPE_I8) {
+    if (cl == 2) IEVM_LAUNCH_DUAL(kDtypeI8, 2); else IEVM_LAUNCH_DUAL(kDtypeI8, 1);
+  } else {
+    if (cl == 2) IEVM_LAUNCH_DUAL(kDtypeF16, 2); else IEVM_LAUNCH_DUAL(kDtypeF16, 1);
+  }
+#undef IEVM_LAUNCH_DUAL
   CUDA_TRY(cudaGetLastError());
   return IEVM_OK;
 }
@@ -1292,7 +1393,12 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     if (d.op == IEVM_OP_CONV && L.is_stem) {
       if (int rc = launch_stem(h, L, i8 ? tensor_ptr(h, 0) : x, tensor_ptr(h, d.out_tensor), n, s)) return rc;
     } else if (d.op == IEVM_OP_CONV) {
-      if (int rc = launch_conv(h, L, n, s, nullptr)) return rc;
+      const int mate = L.dual_partner >= 0 ? L.dual_partner : L.dual_of;      // conv_dual.cuh: the 3x3 / 1x1 pair of a block
+      if (dual_active(h) && mate >= 0) {
+        // one launch for the pair, at the position of whichever comes first (both read only the block input)
+        if (mate > static_cast<int>(li))
+          if (int rc = launch_conv_dual(h, L.dual_partner >= 0 ? L : h->layers[mate], n, s, nullptr, nullptr)) return rc;
+      } else if (int rc = launch_conv(h, L, n, s, nullptr)) return rc;
     } else if (d.op == IEVM_OP_MAXPOOL) {
       if (int rc = launch_maxpool(h, L, tensor_ptr(h, d.in_tensor), tensor_ptr(h, d.out_tensor), n, s)) return rc;
     } else if (d.op == IEVM_OP_ADD_RELU) {
@@ -1498,6 +1604,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (const char* e = getenv("IEVM_TWO_CTA")) h->opt_two_cta = atoi(e);
   if (const char* e = getenv("IEVM_FIXED_BN")) h->opt_fixed_bn = atoi(e);
   if (const char* e = getenv("IEVM_PDL")) h->opt_pdl = atoi(e);
+  if (const char* e = getenv("IEVM_DUAL")) h->opt_dual = atoi(e);
   if (const char* e = getenv("IEVM_CLUSTER")) h->opt_cluster = atoi(e);
   if (const char* e = getenv("IEVM_HOST_CHUNK")) h->host_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
@@ -1524,7 +1631,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (rc == IEVM_OK) rc = encode_maps(h);
   if (rc == IEVM_OK) {
     size_t max_smem = 0;
-    for (const LayerPlan& L : h->layers) max_smem = std::max(max_smem, L.smem_bytes);
+    for (const LayerPlan& L : h->layers) max_smem = std::max(max_smem, std::max(L.smem_bytes, L.dual_smem_bytes));
     if (max_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) rc = fail(IEVM_ERR_UNSUPPORTED, "smem plan exceeds device limit");
     if (rc == IEVM_OK && max_smem > 0) {
       cudaError_t e = cudaSuccess;
@@ -1551,6 +1658,10 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
       IEVM_ATTR(kDtypeF16, false, kModeHalo, 1, 0);   IEVM_ATTR(kDtypeF16, true, kModeHalo, 1, 0);
       IEVM_ATTR(kDtypeF16, false, kModeHalo, 1, 3);   IEVM_ATTR(kDtypeF16, true, kModeHalo, 1, 3);
 #undef IEVM_ATTR
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_dual_kernel<kDtypeI8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_dual_kernel<kDtypeI8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_dual_kernel<kDtypeF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_dual_kernel<kDtypeF16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
       if (e != cudaSuccess) rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       // how many 2-CTA clusters of the heaviest configuration can be co-resident (GPC packing may strand SMs)
       for (LayerPlan& L : h->layers) {
@@ -1571,6 +1682,14 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
             : cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<kDtypeF16, false, kModeIm2col, 2, 0>, &cfg);
         L.max_clusters = (qe == cudaSuccess && nc > 0) ? std::min(nc, h->num_sms / L.cluster) : h->num_sms / L.cluster;
         if (qe != cudaSuccess) cudaGetLastError();
+        if (L.dual_partner >= 0) {
+          cfg.dynamicSmemBytes = L.dual_smem_bytes;
+          nc = 0;
+          const cudaError_t de = h->dtype == IEVM_DTYPE_I8 ? cudaOccupancyMaxActiveClusters(&nc, conv_dual_kernel<kDtypeI8, 2>, &cfg)
+                                                           : cudaOccupancyMaxActiveClusters(&nc, conv_dual_kernel<kDtypeF16, 2>, &cfg);
+          L.dual_max_clusters = (de == cudaSuccess && nc > 0) ? std::min(nc, h->num_sms / L.cluster) : h->num_sms / L.cluster;
+          if (de != cudaSuccess) cudaGetLastError();
+        }
       }
     }
   }
@@ -1927,6 +2046,12 @@ int ievm_set_option(ievm_handle* h, const char* name, int value) {
     h->use_graph = value ? 1 : 0;
     return IEVM_OK;
   }
+  if (!strcmp(name, "dual")) {        // 0: every 1x1 downsample conv is a launch of its own (conv_dual.cuh off)
+    h->opt_dual = value ? 1 : 0;
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
+    h->graphs.clear();
+    return IEVM_OK;
+  }
   if (!strcmp(name, "keep_tensors")) {
     if ((value ? 1 : 0) == h->keep_tensors) return IEVM_OK;
     h->keep_tensors = value ? 1 : 0;
@@ -2108,9 +2233,21 @@ int ievm_tensor_shape(const ievm_handle* h, int id, int32_t out6[6]) {
 int ievm_launches_per_forward(const ievm_handle* h) {
   if (!h) return 0;
   const int n = h->last_n > 0 ? h->last_n : h->max_batch;
-  if (front_end_is_v2(h)) return static_cast<int>(h->layers.size()) - 1;
-  if (front_end_is_chunked(h)) return 3 * ((n + h->front_chunk - 1) / h->front_chunk) + static_cast<int>(h->layers.size()) - 2;
-  return static_cast<int>(h->layers.size()) + (h->dtype == IEVM_DTYPE_I8 ? 1 : 0);
+  int duals = 0;
+  if (dual_active(h))
+    for (const LayerPlan& L : h->layers) duals += L.dual_of >= 0 ? 1 : 0;
+  if (front_end_is_v2(h)) return static_cast<int>(h->layers.size()) - 1 - duals;
+  if (front_end_is_chunked(h))
+    return 3 * ((n + h->front_chunk - 1) / h->front_chunk) + static_cast<int>(h->layers.size()) - 2 - duals;
+  return static_cast<int>(h->layers.size()) + (h->dtype == IEVM_DTYPE_I8 ? 1 : 0) - duals;
+}
+
+int ievm_layer_launch(const ievm_handle* h, int layer) {
+  if (!h || layer < 0 || layer >= static_cast<int>(h->layers.size())) return -1;
+  if (front_end_is_v2(h) && layer == 1) return 0;
+  const LayerPlan& L = h->layers[layer];
+  const int mate = L.dual_partner >= 0 ? L.dual_partner : L.dual_of;
+  return (dual_active(h) && mate >= 0) ? std::min(mate, layer) : layer;
 }
 
 int ievm_profile_read(const ievm_handle* h, int max_slots, float* ms_sum, int32_t* calls) {
@@ -2158,9 +2295,12 @@ int ievm_debug_conv_acc(ievm_handle* h, int layer, int n, int32_t* host_out, uin
   int32_t* dacc = nullptr;
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dacc), bytes));
   cudaDeviceSynchronize();                  // parity hook: the forward that produced this layer's input is done
+  // a layer that the forward runs as half of a dual launch is re-run the same way, so the accumulators are that kernel's
   int rc = L.is_stem ? launch_stem_tc(h, L, static_cast<const uint8_t*>(tensor_ptr(h, 0)),
                                       static_cast<uint8_t*>(tensor_ptr(h, L.d.out_tensor)), n, h->own_stream, dacc)
-                     : launch_conv(h, L, n, h->own_stream, dacc);
+           : (dual_active(h) && L.dual_partner >= 0) ? launch_conv_dual(h, L, n, h->own_stream, dacc, nullptr)
+           : (dual_active(h) && L.dual_of >= 0)      ? launch_conv_dual(h, h->layers[L.dual_of], n, h->own_stream, nullptr, dacc)
+                                                     : launch_conv(h, L, n, h->own_stream, dacc);
   if (rc == IEVM_OK) rc = check_stuck(h, cudaStreamSynchronize(h->own_stream), "debug_conv_acc");
   if (rc == IEVM_OK && cudaMemcpy(host_out, dacc, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
     rc = fail(IEVM_ERR_CUDA, "accumulator copy failed");

@@ -215,6 +215,11 @@ class _B200Engine(nn.Module):
     def launches_per_forward(self) -> int:
         return int(self._lib.ievm_launches_per_forward(self._handle))
 
+    def layer_launch(self, index: int) -> int:
+        """Index of the layer whose kernel launch computes layer `index` (a fused 1x1 downsample reports its block's
+        first conv, the max-pool of the fused front end reports the stem)."""
+        return int(self._lib.ievm_layer_launch(self._handle, index))
+
     def profile_read(self):
         """[(name, total_ms, calls)] per launch slot accumulated since set_option('profile', 1)."""
         slots = len(self.net.layers) + 1

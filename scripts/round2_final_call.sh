@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call for the round's evidence: GPU test tier, bench + reference arm, ncu launch list of the bench command,
-# ncu --set full of one forward (all 21 launches) for profiles/r02_ncu_full_int8_r18_pruned.json.
+# ncu --set full of one forward (all 18 launches) for profiles/r02_ncu_full_int8_r18_pruned.json.
 TAG=${1:-r02}
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/${TAG}_gpu_tests.log 2>&1
@@ -13,6 +13,6 @@ IEVM_WAIT_LIMIT_MS=0 timeout 300 ncu --metrics gpu__time_duration.sum --clock-co
   --log-file gpurun_out/${TAG}_ncu_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-extra --no-latency --no-cpu-baseline > gpurun_out/${TAG}_ncu.log 2>&1
 echo "ncu launches rc=$?"
 timeout 100 python scripts/forward_once.py 256 1 int8 > gpurun_out/plain.log 2>&1 &&
-IEVM_WAIT_LIMIT_MS=0 timeout 500 ncu --set full --clock-control none --import-source on -c 21 -o gpurun_out/${TAG}_ncu_full_int8 -f \
+IEVM_WAIT_LIMIT_MS=0 timeout 500 ncu --set full --clock-control none --import-source on -c 18 -o gpurun_out/${TAG}_ncu_full_int8 -f \
   python scripts/forward_once.py 256 1 int8 > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"; ls -la gpurun_out/${TAG}_ncu_full_int8.ncu-rep
