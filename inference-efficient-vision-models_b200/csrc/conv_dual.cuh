@@ -113,7 +113,7 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tma_load_2d(sB + (num_kb + ch) * b_bytes, &tmap_b2, bres_bar, ch * p.kc_elems, 0);
     }
     __syncwarp();
-    griddep_wait();
+    griddep_wait_conv();
     const uint32_t tx_bytes = static_cast<uint32_t>(p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
     int stage = 0;
     uint32_t phase = 0;
@@ -242,7 +242,7 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int csub = kGroupsMax / groups;
     const int row = quad * 32 + lane;
     const int nchunks = p.bn >> 4;
-    griddep_wait();
+    griddep_wait_conv();
     int acc_next = 0, seq = 0;
     uint32_t acc_phase_next = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++seq) {

@@ -504,7 +504,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sB + kb * b_bytes, &tmap_b, bres_bar, kb * p.kc_elems, 0);
     }
     __syncwarp();
-    griddep_wait();                     // weights were loadable early; activations need the previous kernel done
+    griddep_wait_conv();                     // weights were loadable early; activations need the previous kernel done
     const uint32_t tx_bytes = static_cast<uint32_t>(p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
     int stage = 0;
     uint32_t phase = 0;
@@ -790,7 +790,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int csub = kGroupsMax / groups;                              // warps per quadrant in a group
     const int row = quad * 32 + lane;
     const int nchunks = p.bn >> 4;
-    griddep_wait();                     // before the first residual read / output store
+    griddep_wait_conv();                     // before the first residual read / output store
     AddReluConst k;
     k.lo_f = static_cast<float>(p.out_lo - p.out_zp);
     k.hi_f = static_cast<float>(255 - p.out_zp);

@@ -1358,9 +1358,18 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     return fail(IEVM_ERR_UNSUPPORTED, "8-bit image input needs the fused front end (224-wide input, <= 64 stem channels, "
                                       "keep_tensors = 0, conv_impl = 0)");
   if (u8_input && h->lut_dev == nullptr) return fail(IEVM_ERR_BAD_ARG, "call ievm_set_input_lut before ievm_forward_u8");
+#ifdef IEVM_EXP_SKIP
+  // A/B build only (scripts/skip_costs.py): leave out the launches whose layer bit is set, to measure what each launch
+  // costs INSIDE the graph step (results are wrong, timing is data independent)
+  const unsigned long long skip_mask = getenv("IEVM_SKIP_MASK") ? strtoull(getenv("IEVM_SKIP_MASK"), nullptr, 0) : 0ull;
+#define IEVM_SKIPPED(li) ((skip_mask >> (li)) & 1ull)
+#else
+#define IEVM_SKIPPED(li) false
+#endif
   if (front_end_is_v2(h)) {
     // profile slots: the fused kernel is attributed to the stem's slot (quantize and maxpool read 0)
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
+    if (!IEVM_SKIPPED(0))
     if (int rc = launch_frontend2(h, x, n, s, nullptr, u8_input)) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[2], s));
     first_layer = 2;
@@ -1390,6 +1399,7 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     const LayerPlan& L = h->layers[li];
     const ievm_layer_desc& d = L.d;
     if (prof && li > 0) CUDA_TRY(cudaEventRecord(h->prof_events[li + 1], s));
+    if (IEVM_SKIPPED(li)) continue;
     if (d.op == IEVM_OP_CONV && L.is_stem) {
       if (int rc = launch_stem(h, L, i8 ? tensor_ptr(h, 0) : x, tensor_ptr(h, d.out_tensor), n, s)) return rc;
     } else if (d.op == IEVM_OP_CONV) {
@@ -1415,7 +1425,9 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
         hp.hw = tin.h * tin.w; hp.c = tin.c; hp.cpad = tin.pitch; hp.classes = d.cout; hp.in_zp = d.in_zp;
         hp.w = static_cast<const int8_t*>(L.w_packed); hp.bdiv = L.ep0; hp.mult = L.ep1;
         hp.fc_zp = d.out_zp; hp.fc_scale = d.out_scale;
-        CUDA_TRY(launch_kernel(head_i8_kernel, n, kHeadThreads, 0, s, h->opt_pdl != 0,
+        const int wbytes = hp.classes * hp.cpad;
+        hp.w_smem = wbytes <= kHeadWeightSmemMax ? 1 : 0;
+        CUDA_TRY(launch_kernel(head_i8_kernel, n, kHeadThreads, hp.w_smem ? wbytes : 0, s, h->opt_pdl != 0,
                                static_cast<const uint8_t*>(tensor_ptr(h, d.in_tensor)), static_cast<float*>(logits),
                                static_cast<uint8_t*>(nullptr), hp));
       } else {
@@ -1423,7 +1435,9 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
         hp.hw = tin.h * tin.w; hp.c = tin.c; hp.cpad = tin.pitch; hp.classes = d.cout;
         hp.w = static_cast<const __half*>(L.w_packed); hp.bias = L.ep0;
         hp.pooled = h->obs_pooled;           // non-null only while calibrating (ievm_observe)
-        CUDA_TRY(launch_kernel(head_f16_kernel, n, kHeadThreads, 0, s, h->opt_pdl != 0,
+        const int wbytes = 2 * hp.classes * hp.cpad;
+        hp.w_smem = wbytes <= kHeadWeightSmemMax ? 1 : 0;
+        CUDA_TRY(launch_kernel(head_f16_kernel, n, kHeadThreads, hp.w_smem ? wbytes : 0, s, h->opt_pdl != 0,
                                static_cast<const __half*>(tensor_ptr(h, d.in_tensor)), static_cast<__half*>(logits), hp));
       }
       CUDA_TRY(cudaGetLastError());

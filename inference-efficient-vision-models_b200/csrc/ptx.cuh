@@ -44,6 +44,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef IEVM_EXP_NOWAIT
+// timing experiment (A/B build): the conv kernels do not wait for their predecessor at all -- results are wrong, the step
+// time is the bound on what overlapping consecutive layers can buy
+__device__ __forceinline__ void griddep_wait_conv() {}
+#else
+__device__ __forceinline__ void griddep_wait_conv() { griddep_wait(); }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier

@@ -202,6 +202,11 @@ maxpool3x3s2_f16_kernel(const __half* __restrict__ in, __half* __restrict__ out,
 // Head: AdaptiveAvgPool2d(1) + flatten + quantized Linear + dequantize, one CTA per image.
 //   pooled = clamp(rne(float(sum) / count), 0, 255)  (same qparams as the input, zp == in_zp)
 //   acc[o] = sum_c (pooled[c] - in_zp) * w[o][c];  q = requant(acc);  logit = (q - fc_zp) * fc_scale
+// The kernel is a latency chain, not a bandwidth problem (23 KB per image): inside the graph step it cost 15 us at batch
+// 256 and 9 us at batch 1 when every thread walked its pixels one dependent load at a time and fetched the fc weights
+// from L2 inside the channel loop.  Now the fc weights are copied to shared memory BEFORE griddepcontrol.wait (they do
+// not depend on the previous kernel, so the copy hides behind its tail), every thread issues all of its pixel loads
+// before the first add, and the channel loop reads weights from shared memory.
 // --------------------------------------------------------------------------------------------
 struct HeadParams {
   int hw;            // pixels per image (7*7)
@@ -214,10 +219,13 @@ struct HeadParams {
   const float* mult;
   int fc_zp;
   float fc_scale;
+  int w_smem;        // 1: the launch carries classes * cpad bytes of dynamic shared memory for the weights
 };
 
-constexpr int kHeadThreads = 128;
+constexpr int kHeadThreads = 256;
 constexpr int kMaxClasses = 16;
+constexpr int kHeadLoadsInFlight = 8;         // 16-byte loads a thread issues before it starts adding
+constexpr int kHeadWeightSmemMax = 30 * 1024; // dynamic shared memory the heads may use for the fc weights
 
 constexpr int kHeadSumWords = 4096;          // shared partial channel sums: pixel phases x channel pitch
 
@@ -229,12 +237,25 @@ __device__ __forceinline__ void head_phases(int groups, int& g_stride, int& ph_c
   g_stride = groups >= kHeadThreads ? kHeadThreads : groups;
 }
 
+// fc weights -> shared memory (16-byte copies; `bytes` is a multiple of 16 because the channel pitch is)
+__device__ __forceinline__ void head_stage_weights(const void* w, void* smem, int bytes) {
+  const uint4* src = static_cast<const uint4*>(w);
+  uint4* dst = static_cast<uint4*>(smem);
+  for (int i = threadIdx.x; i < bytes / 16; i += kHeadThreads) dst[i] = __ldg(src + i);
+}
+
 __global__ void __launch_bounds__(kHeadThreads)
 head_i8_kernel(const uint8_t* __restrict__ in, float* __restrict__ logits, uint8_t* __restrict__ pooled_dbg,
                const HeadParams p) {
+  extern __shared__ __align__(16) uint8_t head_w_smem[];
   __shared__ int s_sum[kHeadSumWords];
   __shared__ int s_part[kHeadThreads / 32][kMaxClasses];
   griddep_launch_dependents();
+  const int8_t* w = p.w;
+  if (p.w_smem) {
+    head_stage_weights(p.w, head_w_smem, p.classes * p.cpad);
+    w = reinterpret_cast<const int8_t*>(head_w_smem);
+  }
   griddep_wait();
   const int img = blockIdx.x;
   const uint8_t* base = in + static_cast<long long>(img) * p.hw * p.cpad;
@@ -248,22 +269,30 @@ head_i8_kernel(const uint8_t* __restrict__ in, float* __restrict__ logits, uint8
       int sum[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) sum[j] = 0;
-      for (int px = ph; px < p.hw; px += ph_count) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + px * p.cpad + g * 16));
-        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+      for (int px0 = ph; px0 < p.hw; px0 += kHeadLoadsInFlight * ph_count) {
+        uint4 v[kHeadLoadsInFlight];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          sum[4 * k] += wv[k] & 0xff;
-          sum[4 * k + 1] += (wv[k] >> 8) & 0xff;
-          sum[4 * k + 2] += (wv[k] >> 16) & 0xff;
-          sum[4 * k + 3] += wv[k] >> 24;
+        for (int it = 0; it < kHeadLoadsInFlight; ++it) {
+          const int px = px0 + it * ph_count;
+          v[it] = px < p.hw ? __ldg(reinterpret_cast<const uint4*>(base + px * p.cpad + g * 16)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int it = 0; it < kHeadLoadsInFlight; ++it) {
+          const uint32_t wv[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            sum[4 * k] += wv[k] & 0xff;
+            sum[4 * k + 1] += (wv[k] >> 8) & 0xff;
+            sum[4 * k + 2] += (wv[k] >> 16) & 0xff;
+            sum[4 * k + 3] += wv[k] >> 24;
+          }
         }
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) s_sum[ph * p.cpad + g * 16 + j] = sum[j];
     }
   }
-  __syncthreads();
+  __syncthreads();                      // partial sums and the staged weights
   int acc[kMaxClasses];
 #pragma unroll
   for (int o = 0; o < kMaxClasses; ++o) acc[o] = 0;
@@ -275,14 +304,19 @@ head_i8_kernel(const uint8_t* __restrict__ in, float* __restrict__ logits, uint8
     q = min(max(q, 0), 255);
     if (pooled_dbg) pooled_dbg[static_cast<long long>(img) * p.c + c] = static_cast<uint8_t>(q);
     const int xv = q - p.in_zp;
-    for (int o = 0; o < p.classes; ++o) acc[o] += xv * static_cast<int>(p.w[o * p.cpad + c]);
+#pragma unroll
+    for (int o = 0; o < kMaxClasses; ++o)
+      if (o < p.classes) acc[o] += xv * static_cast<int>(w[o * p.cpad + c]);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int o = 0; o < p.classes; ++o) {
-    int v = acc[o];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    if (lane == 0) s_part[warp][o] = v;
+  for (int o = 0; o < kMaxClasses; ++o) {
+    if (o < p.classes) {
+      int v = acc[o];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) s_part[warp][o] = v;
+    }
   }
   __syncthreads();
   if (threadIdx.x < p.classes) {
@@ -300,13 +334,20 @@ struct HeadF16Params {
   const __half* w;   // [classes][cpad]
   const float* bias;
   __half* pooled = nullptr;   // calibration only (observe.cuh): the avgpool output, [n][c]
+  int w_smem = 0;             // as HeadParams::w_smem (2 * classes * cpad bytes)
 };
 
 __global__ void __launch_bounds__(kHeadThreads)
 head_f16_kernel(const __half* __restrict__ in, __half* __restrict__ logits, const HeadF16Params p) {
+  extern __shared__ __align__(16) uint8_t head_w_smem[];
   __shared__ float s_sum[kHeadSumWords];
   __shared__ float s_part[kHeadThreads / 32][kMaxClasses];
   griddep_launch_dependents();
+  const __half* w = p.w;
+  if (p.w_smem) {
+    head_stage_weights(p.w, head_w_smem, 2 * p.classes * p.cpad);
+    w = reinterpret_cast<const __half*>(head_w_smem);
+  }
   griddep_wait();
   const int img = blockIdx.x;
   const __half* base = in + static_cast<long long>(img) * p.hw * p.cpad;
@@ -320,14 +361,23 @@ head_f16_kernel(const __half* __restrict__ in, __half* __restrict__ logits, cons
       float sum[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum[j] = 0.f;
-      for (int px = ph; px < p.hw; px += ph_count) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + px * p.cpad + g * 8));
-        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+      // pixels are added in the fixed order ph, ph + PH, ...: the result does not depend on the batch or the schedule
+      for (int px0 = ph; px0 < p.hw; px0 += kHeadLoadsInFlight * ph_count) {
+        uint4 v[kHeadLoadsInFlight];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wv[k]));
-          sum[2 * k] += f.x;
-          sum[2 * k + 1] += f.y;
+        for (int it = 0; it < kHeadLoadsInFlight; ++it) {
+          const int px = px0 + it * ph_count;
+          v[it] = px < p.hw ? __ldg(reinterpret_cast<const uint4*>(base + px * p.cpad + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int it = 0; it < kHeadLoadsInFlight; ++it) {
+          const uint32_t wv[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wv[k]));
+            sum[2 * k] += f.x;           // a pixel past the image adds +0.0: the sum is unchanged
+            sum[2 * k + 1] += f.y;
+          }
         }
       }
 #pragma unroll
@@ -345,14 +395,19 @@ head_f16_kernel(const __half* __restrict__ in, __half* __restrict__ logits, cons
     const __half mh = __float2half_rn(sc * inv);
     if (p.pooled) p.pooled[static_cast<long long>(img) * p.c + c] = mh;
     const float m = __half2float(mh);
-    for (int o = 0; o < p.classes; ++o) acc[o] += m * __half2float(p.w[o * p.cpad + c]);
+#pragma unroll
+    for (int o = 0; o < kMaxClasses; ++o)
+      if (o < p.classes) acc[o] += m * __half2float(w[o * p.cpad + c]);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int o = 0; o < p.classes; ++o) {
-    float v = acc[o];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    if (lane == 0) s_part[warp][o] = v;
+  for (int o = 0; o < kMaxClasses; ++o) {
+    if (o < p.classes) {
+      float v = acc[o];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) s_part[warp][o] = v;
+    }
   }
   __syncthreads();
   if (threadIdx.x < p.classes) {
