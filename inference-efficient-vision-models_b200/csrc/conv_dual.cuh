@@ -6,9 +6,8 @@
 // two TILE CLASSES over the 3x3's own im2col tensor map:
 //   class 0: the 3x3 -- nine taps x channel chunks, weights `tmap_b`, epilogue / output of `p`
 //   class 1: the downsample -- the centre tap only, weights `tmap_b2`, epilogue tables / output tensor of `x`
-// Same tile shape (128 pixels x bn), same accumulator ring, same pipeline; a CTA runs the class-1 tile of an (m, n)
-// position right after its class-0 tile, so both outputs of a position are complete together (the next launch, which
-// reads one as its input and the other as its residual, can start on it: TileSync in conv_tc.cuh).  What it buys: the downsample kernels were 12-16 us
+// Same tile shape (128 pixels x bn), same accumulator ring, same pipeline; class-1 tiles follow the class-0 tiles in the
+// persistent schedule, so the light tiles fill the ragged last round.  What it buys: the downsample kernels were 12-16 us
 // each for 3-8 us of work (launch ramp, prologue, pipeline fill and drain on an almost idle GPU); as a tile class they
 // cost their steady-state share only, and the forward has three launches fewer.
 //
@@ -26,7 +25,6 @@ struct ConvDualParams {
   int fast_round;
   int relu;              // f16
   int32_t* dump_acc;     // debug: raw accumulators of class 1
-  uint32_t out_off;      // TileSync: counters of the downsample's output tensor
 };
 
 template <int kDtype, int kCluster>
@@ -97,11 +95,10 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   griddep_launch_dependents();
 
-  uint32_t* const sset = p.sync.flags != nullptr ? sync_set(p.sync) : nullptr;
-  const bool tiled = sset != nullptr && !p.sync.classic;
-  // Schedule: position ct of stride `tile_step` over the (m, n) grid; at every position the class-0 tile, then the
-  // class-1 tile.
+  // Schedule: work item t of stride `tile_step`; t < class_tiles is a class-0 tile, the rest are class-1 tiles of the
+  // same (m, n) grid.
   const int class_tiles = kCluster > 1 ? ((p.m_tiles + kCluster - 1) / kCluster) * p.n_tiles : p.m_tiles * p.n_tiles;
+  const int total_tiles = 2 * class_tiles;
   const int tile_first = kCluster > 1 ? static_cast<int>(blockIdx.x) / kCluster : static_cast<int>(blockIdx.x);
   const int tile_step = kCluster > 1 ? static_cast<int>(gridDim.x) / kCluster : static_cast<int>(gridDim.x);
   const int hw = p.ho * p.wo;
@@ -116,15 +113,13 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tma_load_2d(sB + (num_kb + ch) * b_bytes, &tmap_b2, bres_bar, ch * p.kc_elems, 0);
     }
     __syncwarp();
-    if (!tiled) griddep_wait_conv();
-    int ready_hi = -1;
-    bool in_done = !tiled;
+    griddep_wait_conv();
     const uint32_t tx_bytes = static_cast<uint32_t>(p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile2 = 2 * tile_first; tile2 < 2 * class_tiles; tile2 += (tile2 & 1) ? 2 * tile_step - 1 : 1) {
-      const bool cls1 = (tile2 & 1) != 0;
-      const int ct = tile2 >> 1;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const bool cls1 = tile >= class_tiles;
+      const int ct = cls1 ? tile - class_tiles : tile;
       const int m_group = ct / p.n_tiles;
       const int n_tile = ct - m_group * p.n_tiles;
       const int m_tile = kCluster > 1 ? m_group * kCluster + static_cast<int>(crank) : m_group;
@@ -135,20 +130,6 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int ox = rem - oy * p.wo;
       const int base_w = ox * p.stride - p.pad;
       const int base_h = oy * p.stride - p.pad;
-      if (!in_done && !cls1 && m0 < p.m_total) {          // class 1 reads a subset of what class 0 just waited for
-        const int m1 = min(m0 + kTileM, p.m_total) - 1;
-        const int img1 = fast_div(m1, hw, p.hw_magic);
-        const int oy1 = fast_div(m1 - img1 * hw, p.wo, p.wo_magic);
-        const int y_lo = max(base_h, 0), y_hi = min(oy1 * p.stride - p.pad + p.ksize - 1, p.h_in - 1);
-        const int u_hi = ((img1 * p.h_in + y_hi) * p.w_in + p.w_in - 1) / p.sync.in_unit_px;
-        const int u_lo = max(((img * p.h_in + y_lo) * p.w_in) / p.sync.in_unit_px, ready_hi + 1);
-        if (u_lo <= u_hi) {
-          in_done = sync_wait_units(sset, p.sync.in_off, u_lo, u_hi, p.sync.in_parts, p.sync.in_expected, p.sync.in_done_off,
-                                    p.sync.in_done_ctas, 0x600u, p.stuck_flag);
-          ready_hi = u_hi;
-          fence_proxy_async_all();
-        }
-      }
       const int t_lo = cls1 ? ctr : 0, t_hi = cls1 ? ctr + 1 : p.ksize;
       const int nkb = cls1 ? p.kchunks : num_kb;
       const CUtensorMap* wmap = cls1 ? &tmap_b2 : &tmap_b;
@@ -209,8 +190,8 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     };
     if (p.resident_b) wait_or_die(bres_bar, 0, 0x500u, p.stuck_flag);
-    for (int tile2 = 2 * tile_first; leader && tile2 < 2 * class_tiles; tile2 += (tile2 & 1) ? 2 * tile_step - 1 : 1) {
-      const bool cls1 = (tile2 & 1) != 0;
+    for (int tile = tile_first; leader && tile < total_tiles; tile += tile_step) {
+      const bool cls1 = tile >= class_tiles;
       const int nkb = cls1 ? p.kchunks : num_kb;
       const int b_first = cls1 ? num_kb : 0;             // resident weights: first block of this class
       wait_or_die(&tempty_bar[acc], acc_phase ^ 1u, 0x200u | acc, p.stuck_flag);
@@ -261,16 +242,10 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int csub = kGroupsMax / groups;
     const int row = quad * 32 + lane;
     const int nchunks = p.bn >> 4;
-    if (!tiled) griddep_wait_conv();
-    else if (p.sync.prev2_ctas != 0) {
-      if (lane == 0 && ld_acquire_gpu(sset + p.sync.prev2_done_off) < p.sync.prev2_ctas)
-        sync_spin(sset + p.sync.prev2_done_off, p.sync.prev2_ctas, 0x610u, p.stuck_flag);
-      __syncwarp();
-    }
-    SyncPending pend;
+    griddep_wait_conv();
     int acc_next = 0, seq = 0;
     uint32_t acc_phase_next = 0;
-    for (int tile2 = 2 * tile_first; tile2 < 2 * class_tiles; tile2 += (tile2 & 1) ? 2 * tile_step - 1 : 1, ++seq) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++seq) {
       const int acc = acc_next;
       const uint32_t acc_phase = acc_phase_next;
       if (++acc_next == p.nacc) {
@@ -278,8 +253,8 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         acc_phase_next ^= 1u;
       }
       if ((seq & (groups - 1)) != group) continue;
-      const bool cls1 = (tile2 & 1) != 0;
-      const int ct = tile2 >> 1;
+      const bool cls1 = tile >= class_tiles;
+      const int ct = cls1 ? tile - class_tiles : tile;
       const int m_group = ct / p.n_tiles;
       const int n_tile = ct - m_group * p.n_tiles;
       const int m_tile = kCluster > 1 ? m_group * kCluster + static_cast<int>(crank) : m_group;
@@ -338,18 +313,11 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (kCluster > 1 && !leader) mbar_arrive_remote(&tempty_bar[acc], 0u);
         else mbar_arrive(&tempty_bar[acc]);
       }
-      if (sset != nullptr)
-        sync_note(sset, pend, (cls1 ? x.out_off : p.sync.out_off) + static_cast<uint32_t>(m_tile * p.n_tiles + n_tile));
     }
-    if (sset != nullptr) sync_flush(sset, pend);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (sset != nullptr && threadIdx.x == 0) {
-    fence_acq_rel_gpu();
-    red_add_gpu(sset + p.sync.done_off, 1u);
-  }
   if (kCluster > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();

@@ -70,95 +70,6 @@ inline int halo_shape_class(int wp, int rb, int bn) {
   return 0;
 }
 
-// ---- Tile-level dependencies between consecutive launches (round 2) ----------------------------------------------
-// Stream order makes a layer wait for the LAST tile of its predecessor (griddepcontrol.wait), then fill its pipeline on an
-// idle GPU; with 18 launches per forward that drain + fill was ~10 % of the step at batch 256 and more than half of it at
-// batch 1 (profiles/r02_timing_experiments.md).  Instead every output tensor carries one counter per UNIT of `unit_px`
-// consecutive pixels (a 128-pixel tile or a halo sub-tile) and per N tile; an epilogue warp bumps it (gpu-scope release)
-// when its rows of the unit are stored, and a consumer waits (gpu-scope acquire, then the generic -> async proxy fence
-// its TMA reads need) only for the units its own tile touches.  A launch starts as soon as SMs free up (programmatic
-// dependent launch) and runs its first tiles while the predecessor's last ones are still in flight.
-//   * Two counter sets, selected by the parity of a per-engine forward generation; the head kernel (last launch)
-//     zeroes the set of the NEXT forward and bumps the generation, so nothing is reset on the critical path and ragged
-//     batches leave no stale counts.
-//   * Every launch also counts its finished CTAs.  Workspace buffers are reused two launches after a tensor's last
-//     reader (ievm.cu: assign_buffers), and a launch waits for the completion of the launch BEFORE its predecessor
-//     before its first store, so at most two consecutive launches ever run concurrently.
-//   * `classic`: an operand's producer does not signal (front end, CUDA-core kernels) -- the launch waits for its
-//     predecessor in stream order as before, but still signals its own tiles.
-struct TileSync {
-  uint32_t* flags;           // nullptr: no tile-level dependencies at all (debug relaunches, profiling, option "overlap" = 0)
-  const uint32_t* gen;       // forward generation
-  uint32_t set_stride;       // counters per parity set
-  int classic;
-  uint32_t out_off;          // counters [unit][n_tile] of the output tensor
-  uint32_t done_off;         // this launch's finished-CTA counter
-  uint32_t in_off;           // input operand: counters, pixels per unit, N tiles and arrivals per counter of its producer,
-  int in_unit_px, in_parts;  //   and the producer launch's finished-CTA counter (complete => no more polling)
-  uint32_t in_expected, in_done_off, in_done_ctas;
-  uint32_t res_off;          // residual operand, when its producer is the previous launch (res_unit_px == 0: it is at
-  int res_unit_px, res_parts;  // least two launches back and covered by `prev2`)
-  uint32_t res_expected, res_done_off, res_done_ctas;
-  uint32_t prev2_done_off, prev2_ctas;   // prev2_ctas == 0: nothing to wait for
-};
-
-__device__ __forceinline__ uint32_t* sync_set(const TileSync& s) {
-  return s.flags + (*reinterpret_cast<const volatile uint32_t*>(s.gen) & 1u) * s.set_stride;
-}
-__device__ __forceinline__ void sync_spin(const uint32_t* cnt, uint32_t expected, uint32_t code, unsigned int* flag) {
-  const uint64_t t0 = globaltimer_ns();
-  uint32_t spins = 0;
-  while (ld_acquire_gpu(cnt) < expected) {
-    __nanosleep(40);
-    if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > IEVM_WAIT_LIMIT_NS) {
-      if (flag) {
-        *reinterpret_cast<volatile unsigned int*>(flag) = code;
-        __threadfence_system();
-      }
-      __trap();
-    }
-  }
-}
-// Warp-collective.  Waits until the counters of units [u_lo, u_hi] x parts reached `expected`; lane 31 looks at the
-// producer launch's finished-CTA counter in the same round trip and returns true when that launch is complete (the
-// caller then stops polling for good).
-__device__ __forceinline__ bool sync_wait_units(const uint32_t* set, uint32_t off, int u_lo, int u_hi, int parts,
-                                                uint32_t expected, uint32_t done_off, uint32_t done_ctas, uint32_t code,
-                                                unsigned int* flag) {
-  const int total = (u_hi - u_lo + 1) * parts;
-  const uint32_t* first = set + off + static_cast<size_t>(u_lo) * parts;
-  const int lane = static_cast<int>(lane_id());
-  bool all = false;
-  if (lane == 31) all = ld_acquire_gpu(set + done_off) >= done_ctas;
-  all = __shfl_sync(0xffffffffu, all, 31);
-  if (!all) {
-    for (int i = lane; i < total; i += 32)
-      if (ld_acquire_gpu(first + i) < expected) sync_spin(first + i, expected, code, flag);
-  }
-  __syncwarp();
-  return all;
-}
-// Signalling finished tiles, warp-collective.  The gpu-scope fence that publishes a warp's stores waits for their
-// acknowledgement from L2 (~700 cycles of a stalled warp), which an epilogue-bound layer cannot afford per tile: a warp
-// notes up to kSyncBatch finished tiles (lane j keeps the counter of the j-th) and publishes them with ONE fence.
-// Consumers only ever run behind the producer's tail, so the coarser signal costs them nothing.
-constexpr int kSyncBatch = 4;
-struct SyncPending {
-  uint32_t mine = 0;     // counter offset this lane will bump
-  int n = 0;
-};
-__device__ __forceinline__ void sync_flush(uint32_t* set, SyncPending& q) {
-  if (q.n == 0) return;
-  fence_acq_rel_gpu();
-  __syncwarp();
-  if (static_cast<int>(lane_id()) < q.n) red_add_gpu(set + q.mine, 1u);
-  q.n = 0;
-}
-__device__ __forceinline__ void sync_note(uint32_t* set, SyncPending& q, uint32_t off) {
-  if (static_cast<int>(lane_id()) == q.n) q.mine = off;
-  if (++q.n == kSyncBatch) sync_flush(set, q);
-}
-
 struct ConvTcParams {
   // implicit-GEMM geometry
   int m_total;         // n * ho * wo
@@ -211,7 +122,6 @@ struct ConvTcParams {
   int32_t* dump_acc;   // debug: raw accumulators [m_total][dump_pitch] (bit pattern for f16)
   int dump_pitch;
   unsigned int* stuck_flag;   // mapped host word; written before a bounded wait gives up
-  TileSync sync;
   // The same per-channel tables as ep0 / ep1 inside the kernel-parameter block (filled when cout_pad <= kEpConst): the
   // statically shaped halo kernels unroll their chunk loop, so every table entry becomes a constant-bank operand of the
   // FADD / FMUL that uses it -- no shared-memory loads (and no short-scoreboard stalls behind them) in the epilogue.
@@ -404,8 +314,8 @@ __device__ __forceinline__ void epilogue16_f16(const uint32_t (&v)[16], const fl
     f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
   }
   if (kHasRes && valid) {
-    const uint4 r0 = __ldcg(reinterpret_cast<const uint4*>(rp));       // L2 only, as load_res16_i8
-    const uint4 r1 = __ldcg(reinterpret_cast<const uint4*>(rp + 8));
+    const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
+    const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
     const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -436,8 +346,7 @@ __device__ __forceinline__ void epilogue16_f16(const uint32_t (&v)[16], const fl
 // that the L2 latency is hidden behind the wait for the accumulator.
 __device__ __forceinline__ uint4 load_res16_i8(const ConvTcParams& p, int m, bool valid, int ch) {
   if (!valid) return make_uint4(0u, 0u, 0u, 0u);
-  // L2 only: with tile-level dependencies the residual may have been written while this kernel was already running
-  return __ldcg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch));
+  return __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch));
 }
 
 template <int kDtype, bool kHasRes>
@@ -559,9 +468,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   griddep_launch_dependents();          // the next kernel may begin its prologue as SMs free up
-  // tile-level dependencies (TileSync): `tiled` = operands are awaited per tile instead of per launch
-  uint32_t* const sset = p.sync.flags != nullptr ? sync_set(p.sync) : nullptr;
-  const bool tiled = sset != nullptr && !p.sync.classic;
 
   // Work schedule.
   //   im2col : work item `tile` of stride `tile_step` starting at `tile_first`:
@@ -598,30 +504,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sB + kb * b_bytes, &tmap_b, bres_bar, kb * p.kc_elems, 0);
     }
     __syncwarp();
-    if (!tiled) griddep_wait_conv();         // weights were loadable early; activations need the previous kernel done
-    int ready_hi = -1;                       // input units up to here are known complete (ranges only move forward)
-    bool in_done = !tiled;                   // the producing launch is complete: nothing left to poll
-    // wait for the input pixels [m_lo, m_hi] of the next TMA (tile-level dependencies)
-#ifdef IEVM_EXP_TIMING
-    long long tm_poll = 0;
-    int tm_polls = 0;
-#endif
-    auto await_input = [&](int m_lo, int m_hi) {
-      const int u_hi = m_hi / p.sync.in_unit_px;
-      const int u_lo = max(m_lo / p.sync.in_unit_px, ready_hi + 1);
-      if (u_lo > u_hi) return;
-#ifdef IEVM_EXP_TIMING
-      const long long tp0 = clock64();
-#endif
-      in_done = sync_wait_units(sset, p.sync.in_off, u_lo, u_hi, p.sync.in_parts, p.sync.in_expected, p.sync.in_done_off,
-                                p.sync.in_done_ctas, 0x600u, p.stuck_flag);
-      ready_hi = u_hi;
-      fence_proxy_async_all();               // flagged data was written through the generic proxy, TMA reads through the async one
-#ifdef IEVM_EXP_TIMING
-      tm_poll += clock64() - tp0;
-      ++tm_polls;
-#endif
-    };
+    griddep_wait_conv();                     // weights were loadable early; activations need the previous kernel done
     const uint32_t tx_bytes = static_cast<uint32_t>(p.resident_b ? p.a_tx_bytes : p.a_tx_bytes + b_bytes);
     int stage = 0;
     uint32_t phase = 0;
@@ -630,10 +513,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int s0 = t_begin - img * p.subs_per_img;
       for (int t = t_begin; t < t_end;) {
         const int ns = min(p.band_subs, min(p.subs_per_img - s0, t_end - t));
-        if (!in_done) {                      // the band's patch: input rows s0 R - 1 .. (s0 + ns) R of image `img`
-          const int y_lo = max(s0 * p.sub_rows - 1, 0), y_hi = min((s0 + ns) * p.sub_rows, p.h_in - 1);
-          await_input((img * p.h_in + y_lo) * p.w_in, (img * p.h_in + y_hi) * p.w_in + p.w_in - 1);
-        }
         IEVM_TIMED_WAIT(tm_wait_a, &empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
         if (elect_one()) {
 #ifdef IEVM_EXP_NOTMA
@@ -668,14 +547,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int ox = rem - oy * p.wo;
         const int base_w = ox * p.stride - p.pad;
         const int base_h = oy * p.stride - p.pad;
-        if (!in_done && m0 < p.m_total) {
-          // input rows of the tile's first .. last output pixel (a contiguous pixel range that covers every tap)
-          const int m1 = min(m0 + kTileM, p.m_total) - 1;
-          const int img1 = fast_div(m1, hw, p.hw_magic);
-          const int oy1 = fast_div(m1 - img1 * hw, p.wo, p.wo_magic);
-          const int y_lo = max(base_h, 0), y_hi = min(oy1 * p.stride - p.pad + p.ksize - 1, p.h_in - 1);
-          await_input((img * p.h_in + y_lo) * p.w_in, (img1 * p.h_in + y_hi) * p.w_in + p.w_in - 1);
-        }
         int kb = 0, g = 0;
         for (int ty = 0; ty < p.ksize; ++ty) {
           for (int tx = 0; tx < p.ksize; ++tx) {
@@ -716,9 +587,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0 && blockIdx.x < kExpCtas) {
       tm_out[4] = clock64() - tm_t0;
       tm_out[5] = tm_wait_a;
-      tm_out[11] = tm_poll;
-      tm_out[12] = tm_polls;
-      tm_out[13] = tm_t0;                    // kernel-entry clock of this CTA (SM clocks are not synchronised; rough)
     }
 #endif
   } else if (warp == 1) {
@@ -922,20 +790,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int csub = kGroupsMax / groups;                              // warps per quadrant in a group
     const int row = quad * 32 + lane;
     const int nchunks = p.bn >> 4;
-    if (!tiled) griddep_wait_conv();         // before the first residual read / output store
-    else if (p.sync.prev2_ctas != 0) {
-      // workspace reuse: the launch before the predecessor is complete before this one stores anything
-      if (lane == 0 && ld_acquire_gpu(sset + p.sync.prev2_done_off) < p.sync.prev2_ctas)
-        sync_spin(sset + p.sync.prev2_done_off, p.sync.prev2_ctas, 0x610u, p.stuck_flag);
-      __syncwarp();
-    }
-    SyncPending pend;
-    bool res_done = !(tiled && kHasRes && p.sync.res_unit_px != 0);   // true: no residual polling (any more)
-    // wait for the residual pixels [m_lo, m_hi] of this warp's next tile
-    auto await_res = [&](int m_lo, int m_hi) {
-      res_done = sync_wait_units(sset, p.sync.res_off, m_lo / p.sync.res_unit_px, m_hi / p.sync.res_unit_px, p.sync.res_parts,
-                                 p.sync.res_expected, p.sync.res_done_off, p.sync.res_done_ctas, 0x620u, p.stuck_flag);
-    };
+    griddep_wait_conv();                     // before the first residual read / output store
     AddReluConst k;
     k.lo_f = static_cast<float>(p.out_lo - p.out_zp);
     k.hi_f = static_cast<float>(255 - p.out_zp);
@@ -1076,15 +931,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int oy = (t - img * p.subs_per_img) * p.sub_rows + sub_row;
         const bool valid = sub_ok && oy < p.h_in;
         const int m = (img * p.h_in + oy) * p.w_in + sub_x;
-        if (kHasRes && !res_done) {          // the sub-tile's own pixels of the residual tensor
-          const int y0 = (t - img * p.subs_per_img) * p.sub_rows;
-          await_res((img * p.h_in + y0) * p.w_in, (img * p.h_in + min(y0 + p.sub_rows, p.h_in)) * p.w_in - 1);
-        }
         if (kShape != 0) drain_static(acc, acc_phase, m, valid);
         else drain(acc, acc_phase, m, valid, 0, kZc ? zcorr_row(oy, sub_x) : nullptr);
-        if (sset != nullptr) sync_note(sset, pend, p.sync.out_off + static_cast<uint32_t>(t));   // unit = sub-tile
       }
-      if (sset != nullptr) sync_flush(sset, pend);
     } else {
       int acc_next = 0, seq = 0;
       uint32_t acc_phase_next = 0;
@@ -1108,12 +957,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int rem = m - (m / hw) * hw;
           zc = zcorr_row(rem / p.wo, rem - (rem / p.wo) * p.wo);
         }
-        if (kHasRes && !res_done && m_tile * kTileM < p.m_total)
-          await_res(m_tile * kTileM, min(m_tile * kTileM + kTileM, p.m_total) - 1);
         drain(acc, acc_phase, m, m < p.m_total, n_tile * p.bn, zc);
-        if (sset != nullptr) sync_note(sset, pend, p.sync.out_off + static_cast<uint32_t>(m_tile * p.n_tiles + n_tile));
       }
-      if (sset != nullptr) sync_flush(sset, pend);
     }
   }
 
@@ -1132,10 +977,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tm_out[10] = globaltimer_ns() - tm_ns0;
   }
 #endif
-  if (sset != nullptr && threadIdx.x == 0) {  // every epilogue warp published its stores (sync_arrive) before the barrier
-    fence_acq_rel_gpu();
-    red_add_gpu(sset + p.sync.done_off, 1u);
-  }
   if (kCluster > 1) cluster_sync_all();     // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();

@@ -134,7 +134,6 @@ struct TensorInfo {
   int last_use = -1;
   int buffer = -1;
   int hp = 0, wp = 0, pad_t = 0, pad_l = 0;   // stored with a constant border when hp > 0 (INT8 network input)
-  uint32_t sync_off = 0, sync_words = 0;      // TileSync counters of this tensor inside one parity set (0 words: never signalled)
   size_t bytes_per_image() const {
     return hp > 0 ? static_cast<size_t>(hp) * wp * pitch * elem : static_cast<size_t>(h) * w * pitch * elem;
   }
@@ -208,10 +207,6 @@ struct ievm_handle {
   int opt_pdl = 1;         // IEVM_PDL=0: no programmatic dependent launch
   int opt_fixed_bn = 0;    // IEVM_FIXED_BN=1: one N tile per <=256 channels (disables the tile-width heuristic)
   int opt_dual = 1;        // IEVM_DUAL=0 / option "dual": the 1x1 downsample convs run as launches of their own
-  int opt_overlap = 1;     // IEVM_OVERLAP=0 / option "overlap": stream-order dependencies between launches only (no TileSync)
-  uint32_t* sync_flags = nullptr;   // TileSync (conv_tc.cuh): two parity sets of [tensor counters | per-launch CTA counters]
-  uint32_t* sync_gen = nullptr;     // forward generation (+ the head kernel's ticket counter behind it)
-  uint32_t sync_set_stride = 0, sync_done_base = 0;
   int front_chunk = 0;     // IEVM_FRONT_CHUNK: images per front-end chunk (0 = whole batch at once, default)
   // IEVM_HALO_RB128=1: 64-byte pixels use 128-byte shared-memory rows in halo mode
   int in_c = 0, in_h = 0, in_w = 0, classes = 0;
@@ -591,36 +586,6 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
   return IEVM_OK;
 }
 
-// TileSync counters (conv_tc.cuh): a slice per conv output tensor, sized for the finest unit and the most N tiles any of
-// its possible producers uses (its own launch, or the dual launch of its block), then one finished-CTA counter per launch.
-int plan_sync(ievm_handle* h) {
-  uint32_t off = 0;
-  for (size_t i = 0; i < h->layers.size(); ++i) {
-    const LayerPlan& L = h->layers[i];
-    if (L.d.op != IEVM_OP_CONV || L.is_stem) continue;
-    TensorInfo& t = h->tensors[L.d.out_tensor];
-    const long long px = static_cast<long long>(h->max_batch) * L.ho * L.wo;
-    const int unit = L.mode == kModeHalo ? std::min(kTileM, L.sub_rows * L.w) : kTileM;
-    int parts = L.mode == kModeHalo ? 1 : L.n_tiles;
-    if (L.dual_of >= 0) parts = std::max(parts, h->layers[L.dual_of].n_tiles);
-    t.sync_off = off;
-    t.sync_words = static_cast<uint32_t>((px + unit - 1) / unit + 4) * static_cast<uint32_t>(parts);
-    off += t.sync_words;
-  }
-  h->sync_done_base = off;
-  h->sync_set_stride = off + static_cast<uint32_t>(h->layers.size()) + 4;
-  void* p = nullptr;
-  CUDA_TRY(cudaMalloc(&p, 2ull * h->sync_set_stride * sizeof(uint32_t)));
-  h->owned.push_back(p);
-  CUDA_TRY(cudaMemset(p, 0, 2ull * h->sync_set_stride * sizeof(uint32_t)));
-  h->sync_flags = static_cast<uint32_t*>(p);
-  CUDA_TRY(cudaMalloc(&p, 16));
-  h->owned.push_back(p);
-  CUDA_TRY(cudaMemset(p, 0, 16));
-  h->sync_gen = static_cast<uint32_t*>(p);
-  return IEVM_OK;
-}
-
 // ----------------------------------------------------------------------------------------------
 // Weights and epilogue tables
 // ----------------------------------------------------------------------------------------------
@@ -887,15 +852,10 @@ int assign_buffers(ievm_handle* h) {
         tm.buffer = take(tm.bytes_per_image() * static_cast<size_t>(h->max_batch));
       }
     }
-    // A buffer becomes reusable kReuseDistance layers after its tensor's last reader: with tile-level dependencies
-    // (TileSync, conv_tc.cuh) two consecutive LAUNCHES may run concurrently, and a launch waits for the completion of the
-    // launch before its predecessor before it stores; three layer indices are at least two launches (a fused
-    // downsample or max-pool index is not a launch of its own).
-    constexpr int kReuseDistance = 3;
     if (!h->keep_tensors)
       for (size_t ti = (f16 ? 0 : 1); ti < h->tensors.size(); ++ti) {   // the INT8 input keeps its bordered buffer
         const TensorInfo& t = h->tensors[ti];
-        if (t.buffer >= 0 && t.last_use + kReuseDistance - 1 == static_cast<int>(i)) free_list.push_back(t.buffer);
+        if (t.buffer >= 0 && t.last_use == static_cast<int>(i)) free_list.push_back(t.buffer);
       }
   }
   for (size_t b = 0; b < need.size(); ++b) {
@@ -992,95 +952,6 @@ int encode_maps(ievm_handle* h) {
 // ----------------------------------------------------------------------------------------------
 // Launch helpers
 // ----------------------------------------------------------------------------------------------
-// ---- TileSync bookkeeping of one enqueue_forward (conv_tc.cuh): which launch produced a tensor, and how it signals ----
-struct TensorSignal {
-  int unit_px = 0, parts = 0;      // unit_px == 0: the producer does not signal tiles
-  uint32_t expected = 0;
-  int launch = -1;
-};
-struct LaunchRecord {
-  bool signals = false;            // counts its finished CTAs
-  bool classic = true;             // waited for its predecessor in stream order
-  uint32_t ctas = 0;
-};
-struct ForwardSync {
-  bool on = false;
-  std::vector<TensorSignal> tensors;
-  std::vector<LaunchRecord> launches;
-};
-
-// Arrivals per (unit, N tile) counter: one per epilogue warp that drains rows of the tile.
-uint32_t sync_arrivals(const ConvTcParams& p, bool two_cta) {
-  const int groups_max = two_cta ? 2 : kEpiWarps / 4;
-  const int groups = std::min(p.nacc, groups_max);
-  return static_cast<uint32_t>(4 * (groups_max / groups));
-}
-
-// Fills p.sync for a conv launch that reads `in_tensor` (and `res_tensor`) and appends the launch to the record.
-// `outs`: the tensors the launch writes (two for a dual launch); returns the launch's index.
-void sync_prepare(const ievm_handle* h, ForwardSync* fs, ConvTcParams& p, int in_tensor, int res_tensor, uint32_t ctas) {
-  memset(&p.sync, 0, sizeof(p.sync));
-  if (fs == nullptr || !fs->on) return;
-  const int cur = static_cast<int>(fs->launches.size());
-  TileSync& y = p.sync;
-  y.flags = h->sync_flags;
-  y.gen = h->sync_gen;
-  y.set_stride = h->sync_set_stride;
-  y.done_off = h->sync_done_base + static_cast<uint32_t>(cur);
-  const TensorSignal& ti = fs->tensors[in_tensor];
-  bool classic = ti.unit_px == 0;
-  if (!classic) {
-    y.in_off = h->tensors[in_tensor].sync_off;
-    y.in_unit_px = ti.unit_px;
-    y.in_parts = ti.parts;
-    y.in_expected = ti.expected;
-    y.in_done_off = h->sync_done_base + static_cast<uint32_t>(ti.launch);
-    y.in_done_ctas = fs->launches[ti.launch].ctas;
-  }
-  if (res_tensor >= 0) {
-    const TensorSignal& tr = fs->tensors[res_tensor];
-    if (tr.unit_px == 0) classic = true;
-    else if (tr.launch == cur - 1) {       // written by the previous launch: awaited tile by tile
-      y.res_off = h->tensors[res_tensor].sync_off;
-      y.res_unit_px = tr.unit_px;
-      y.res_parts = tr.parts;
-      y.res_expected = tr.expected;
-      y.res_done_off = h->sync_done_base + static_cast<uint32_t>(tr.launch);
-      y.res_done_ctas = fs->launches[tr.launch].ctas;
-    }                                      // else: at least two launches back, complete once `prev2` is
-  }
-  // the launch before the predecessor must be complete before this one stores (workspace reuse distance, assign_buffers)
-  if (cur >= 2) {
-    const LaunchRecord& p2 = fs->launches[cur - 2];
-    if (p2.signals) {
-      y.prev2_done_off = h->sync_done_base + static_cast<uint32_t>(cur - 2);
-      y.prev2_ctas = p2.ctas;
-    } else if (!fs->launches[cur - 1].classic) classic = true;    // cannot name its completion: fall back to stream order
-  }
-  if (cur >= 1 && !fs->launches[cur - 1].signals) classic = true;  // predecessor is not a tile-signalling kernel at all
-  y.classic = classic ? 1 : 0;
-  LaunchRecord r;
-  r.signals = true;
-  r.classic = classic;
-  r.ctas = ctas;
-  fs->launches.push_back(r);
-}
-
-void sync_record_output(ForwardSync* fs, int tensor, int unit_px, int parts, uint32_t expected) {
-  if (fs == nullptr || !fs->on) return;
-  TensorSignal& t = fs->tensors[tensor];
-  t.unit_px = unit_px;
-  t.parts = parts;
-  t.expected = expected;
-  t.launch = static_cast<int>(fs->launches.size()) - 1;
-}
-
-// A launch that neither awaits nor signals tiles (front end, CUDA-core kernels, head).
-void sync_record_plain_launch(ForwardSync* fs) {
-  if (fs == nullptr || !fs->on) return;
-  fs->launches.push_back(LaunchRecord());
-}
-
 ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, int32_t* dump_acc) {
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
@@ -1155,10 +1026,9 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
   return p;
 }
 
-int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32_t* dump_acc, ForwardSync* fs = nullptr) {
-  ConvTcParams p = make_conv_params(h, L, n, dump_acc);
+int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32_t* dump_acc) {
+  const ConvTcParams p = make_conv_params(h, L, n, dump_acc);
   if (h->conv_impl == 1) {
-    sync_record_plain_launch(fs);
     ConvDirectParams g;
     g.n = n; g.h = L.h; g.w = L.w; g.ho = L.ho; g.wo = L.wo;
     g.cin_pitch = L.cin_pitch; g.cin_w = L.cin_w; g.cin_real = L.d.cin; g.cout_pad = L.cout_pad;
@@ -1197,16 +1067,6 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
   } while (0)
   // the shape-specialised kernels assume a zero input zero point (true for every post-ReLU tensor); others take class 0
   const int shape = (L.mode == kModeHalo && h->opt_halo_static && L.zcorr == nullptr) ? halo_shape_class(L.wp, L.kc_bytes, L.bn) : 0;
-  const bool two_cta = L.two_cta && shape == 1 && h->dtype == IEVM_DTYPE_I8 && !(L.zcorr != nullptr);
-  {
-    // TileSync: what this launch waits for and how its output tensor is signalled (unit = 128-pixel tile, or the halo
-    // sub-tile when whole sub-tiles tile the image)
-    sync_prepare(h, fs, p, L.d.in_tensor, L.d.res_tensor, static_cast<uint32_t>(two_cta ? std::min(p.m_tiles, 2 * h->num_sms) : grid));
-    const bool halo = L.mode == kModeHalo;
-    const int unit_px = halo ? (L.h % L.sub_rows == 0 ? L.sub_rows * L.w : 0) : kTileM;
-    sync_record_output(fs, L.d.out_tensor, unit_px, halo ? 1 : p.n_tiles, sync_arrivals(p, two_cta));
-    p.sync.out_off = h->tensors[L.d.out_tensor].sync_off;
-  }
   if (L.zcorr != nullptr && h->dtype == IEVM_DTYPE_I8) {
     // non-zero input zero point: the run-time-shaped kernels with the border-aware correction compiled in
 #define IEVM_LAUNCH_ZC(RES, MODE, CL)                                                                                        \
@@ -1223,7 +1083,7 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
     CUDA_TRY(cudaGetLastError());
     return IEVM_OK;
   }
-  if (two_cta) {
+  if (L.two_cta && shape == 1 && h->dtype == IEVM_DTYPE_I8) {
     const int grid2 = std::min(p.m_tiles, 2 * h->num_sms);
     if (has_res)
       CUDA_TRY(launch_kernel_cluster(conv_tc_kernel<kDtypeI8, true, kModeHalo, 1, 1, 8>, grid2, 64 + 32 * 8, L.smem_bytes, s,
@@ -1249,8 +1109,7 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
 bool dual_active(const ievm_handle* h) { return h->opt_dual && h->conv_impl == 0; }
 
 // Layer P (3x3) and its partner (the block's 1x1 downsample) in one launch; dump0 / dump1: debug accumulators per class.
-int launch_conv_dual(ievm_handle* h, const LayerPlan& P, int n, cudaStream_t s, int32_t* dump0, int32_t* dump1,
-                     ForwardSync* fs = nullptr) {
+int launch_conv_dual(ievm_handle* h, const LayerPlan& P, int n, cudaStream_t s, int32_t* dump0, int32_t* dump1) {
   const LayerPlan& D = h->layers[P.dual_partner];
   ConvTcParams p = make_conv_params(h, P, n, dump0);
   p.stages = P.dual_stages;
@@ -1268,12 +1127,7 @@ int launch_conv_dual(ievm_handle* h, const LayerPlan& P, int n, cudaStream_t s, 
   const int cl = P.cluster;
   const int class_tiles = ((p.m_tiles + cl - 1) / cl) * p.n_tiles;
   const int max_cl = cl > 1 ? (P.dual_max_clusters > 0 ? P.dual_max_clusters : h->num_sms / cl) : h->num_sms;
-  const int grid = std::min(class_tiles, max_cl) * cl;       // a CTA runs both classes of its positions
-  sync_prepare(h, fs, p, P.d.in_tensor, -1, static_cast<uint32_t>(grid));
-  sync_record_output(fs, P.d.out_tensor, kTileM, p.n_tiles, sync_arrivals(p, false));
-  sync_record_output(fs, D.d.out_tensor, kTileM, p.n_tiles, sync_arrivals(p, false));
-  x.out_off = h->tensors[D.d.out_tensor].sync_off;
-  p.sync.out_off = h->tensors[P.d.out_tensor].sync_off;
+  const int grid = std::min(2 * class_tiles, max_cl) * cl;
 #define IEVM_LAUNCH_DUAL(DT, CL)                                                                                        \
   CUDA_TRY(launch_kernel_cluster(conv_dual_kernel<DT, CL>, grid, kConvThreads, P.dual_smem_bytes, s, h->opt_pdl != 0, \
                                  static_cast<unsigned>(CL), P.tmap_a, P.tmap_b, P.tmap_b2, p, x))
@@ -1499,10 +1353,6 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     h->prof_calls.resize(h->layers.size() + 1, 0);
     CUDA_TRY(cudaEventRecord(h->prof_events[0], s));
   }
-  // tile-level dependencies between the conv launches (TileSync, conv_tc.cuh); per-launch profiling wants them serialised
-  ForwardSync fs;
-  fs.on = h->opt_overlap && h->opt_pdl && h->conv_impl == 0 && !prof && h->sync_flags != nullptr;
-  fs.tensors.resize(h->tensors.size());
   size_t first_layer = 0;
   if (u8_input && !front_end_is_v2(h))
     return fail(IEVM_ERR_UNSUPPORTED, "8-bit image input needs the fused front end (224-wide input, <= 64 stem channels, "
@@ -1521,7 +1371,6 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
     if (!IEVM_SKIPPED(0))
     if (int rc = launch_frontend2(h, x, n, s, nullptr, u8_input)) return rc;
-    sync_record_plain_launch(&fs);
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[2], s));
     first_layer = 2;
   } else if (front_end_is_chunked(h)) {
@@ -1539,14 +1388,11 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
       if (int rc = launch_maxpool(h, Lp, tensor_ptr(h, Ls.d.out_tensor),
                                   static_cast<uint8_t*>(tensor_ptr(h, Lp.d.out_tensor)) + c0 * pooled_img, nc, s)) return rc;
     }
-    sync_record_plain_launch(&fs);
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[2], s));
     first_layer = 2;
   } else {
-    if (i8) {
+    if (i8)
       if (int rc = launch_quantize(h, static_cast<const float*>(x), n, static_cast<uint8_t*>(tensor_ptr(h, 0)), s)) return rc;
-      sync_record_plain_launch(&fs);
-    }
     if (prof) CUDA_TRY(cudaEventRecord(h->prof_events[1], s));
   }
   for (size_t li = first_layer; li < h->layers.size(); ++li) {
@@ -1556,19 +1402,16 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
     if (IEVM_SKIPPED(li)) continue;
     if (d.op == IEVM_OP_CONV && L.is_stem) {
       if (int rc = launch_stem(h, L, i8 ? tensor_ptr(h, 0) : x, tensor_ptr(h, d.out_tensor), n, s)) return rc;
-      sync_record_plain_launch(&fs);
     } else if (d.op == IEVM_OP_CONV) {
       const int mate = L.dual_partner >= 0 ? L.dual_partner : L.dual_of;      // conv_dual.cuh: the 3x3 / 1x1 pair of a block
       if (dual_active(h) && mate >= 0) {
         // one launch for the pair, at the position of whichever comes first (both read only the block input)
         if (mate > static_cast<int>(li))
-          if (int rc = launch_conv_dual(h, L.dual_partner >= 0 ? L : h->layers[mate], n, s, nullptr, nullptr, &fs)) return rc;
-      } else if (int rc = launch_conv(h, L, n, s, nullptr, &fs)) return rc;
+          if (int rc = launch_conv_dual(h, L.dual_partner >= 0 ? L : h->layers[mate], n, s, nullptr, nullptr)) return rc;
+      } else if (int rc = launch_conv(h, L, n, s, nullptr)) return rc;
     } else if (d.op == IEVM_OP_MAXPOOL) {
       if (int rc = launch_maxpool(h, L, tensor_ptr(h, d.in_tensor), tensor_ptr(h, d.out_tensor), n, s)) return rc;
-      sync_record_plain_launch(&fs);
     } else if (d.op == IEVM_OP_ADD_RELU) {
-      sync_record_plain_launch(&fs);
       const TensorInfo& tin = h->tensors[d.in_tensor];
       const long long nvec = static_cast<long long>(n) * tin.h * tin.w * tin.pitch / 8;
       add_relu_f16_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, 0, s>>>(
@@ -1584,7 +1427,6 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
         hp.fc_zp = d.out_zp; hp.fc_scale = d.out_scale;
         const int wbytes = hp.classes * hp.cpad;
         hp.w_smem = wbytes <= kHeadWeightSmemMax ? 1 : 0;
-        hp.sync_flags = h->sync_flags; hp.sync_gen = h->sync_gen; hp.sync_set_stride = h->sync_set_stride;
         CUDA_TRY(launch_kernel(head_i8_kernel, n, kHeadThreads, hp.w_smem ? wbytes : 0, s, h->opt_pdl != 0,
                                static_cast<const uint8_t*>(tensor_ptr(h, d.in_tensor)), static_cast<float*>(logits),
                                static_cast<uint8_t*>(nullptr), hp));
@@ -1595,7 +1437,6 @@ int enqueue_forward(ievm_handle* h, const void* x, int n, void* logits, cudaStre
         hp.pooled = h->obs_pooled;           // non-null only while calibrating (ievm_observe)
         const int wbytes = 2 * hp.classes * hp.cpad;
         hp.w_smem = wbytes <= kHeadWeightSmemMax ? 1 : 0;
-        hp.sync_flags = h->sync_flags; hp.sync_gen = h->sync_gen; hp.sync_set_stride = h->sync_set_stride;
         CUDA_TRY(launch_kernel(head_f16_kernel, n, kHeadThreads, hp.w_smem ? wbytes : 0, s, h->opt_pdl != 0,
                                static_cast<const __half*>(tensor_ptr(h, d.in_tensor)), static_cast<__half*>(logits), hp));
       }
@@ -1778,7 +1619,6 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (const char* e = getenv("IEVM_FIXED_BN")) h->opt_fixed_bn = atoi(e);
   if (const char* e = getenv("IEVM_PDL")) h->opt_pdl = atoi(e);
   if (const char* e = getenv("IEVM_DUAL")) h->opt_dual = atoi(e);
-  if (const char* e = getenv("IEVM_OVERLAP")) h->opt_overlap = atoi(e);
   if (const char* e = getenv("IEVM_CLUSTER")) h->opt_cluster = atoi(e);
   if (const char* e = getenv("IEVM_HOST_CHUNK")) h->host_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
@@ -1803,7 +1643,6 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   }
   if (rc == IEVM_OK) rc = assign_buffers(h);
   if (rc == IEVM_OK) rc = encode_maps(h);
-  if (rc == IEVM_OK) rc = plan_sync(h);
   if (rc == IEVM_OK) {
     size_t max_smem = 0;
     for (const LayerPlan& L : h->layers) max_smem = std::max(max_smem, std::max(L.smem_bytes, L.dual_smem_bytes));
@@ -2219,12 +2058,6 @@ int ievm_set_option(ievm_handle* h, const char* name, int value) {
   }
   if (!strcmp(name, "use_graph")) {
     h->use_graph = value ? 1 : 0;
-    return IEVM_OK;
-  }
-  if (!strcmp(name, "overlap")) {     // 0: stream-order dependencies between launches only (TileSync off)
-    h->opt_overlap = value ? 1 : 0;
-    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second.first);
-    h->graphs.clear();
     return IEVM_OK;
   }
   if (!strcmp(name, "dual")) {        // 0: every 1x1 downsample conv is a launch of its own (conv_dual.cuh off)

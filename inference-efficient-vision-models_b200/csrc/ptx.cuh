@@ -44,18 +44,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// Tile-level dependencies between consecutive layers (conv_tc.cuh, TileSync): global counters with gpu-scope
-// release / acquire, and the generic -> async proxy fence a TMA read of freshly flagged data needs.
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_add_gpu(uint32_t* p, uint32_t v) {
-  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 #ifdef IEVM_EXP_NOWAIT
 // timing experiment (A/B build): the conv kernels do not wait for their predecessor at all -- results are wrong, the step
 // time is the bound on what overlapping consecutive layers can buy

@@ -220,9 +220,6 @@ struct HeadParams {
   int fc_zp;
   float fc_scale;
   int w_smem;        // 1: the launch carries classes * cpad bytes of dynamic shared memory for the weights
-  uint32_t* sync_flags = nullptr;    // TileSync housekeeping (head_sync_turnover)
-  uint32_t* sync_gen = nullptr;
-  uint32_t sync_set_stride = 0;
 };
 
 constexpr int kHeadThreads = 256;
@@ -245,26 +242,6 @@ __device__ __forceinline__ void head_stage_weights(const void* w, void* smem, in
   const uint4* src = static_cast<const uint4*>(w);
   uint4* dst = static_cast<uint4*>(smem);
   for (int i = threadIdx.x; i < bytes / 16; i += kHeadThreads) dst[i] = __ldg(src + i);
-}
-
-// TileSync housekeeping (conv_tc.cuh), done by the head because it is the forward's last launch and has waited for the
-// last conv (hence, transitively, for every launch of the forward): zero the counter set of the NEXT forward and bump the
-// forward generation.  The generation is read by every CTA before it takes its ticket and written by the holder of the
-// last ticket, so all CTAs agree on which set to zero.
-__device__ __forceinline__ void head_sync_turnover(uint32_t* flags, uint32_t* gen, uint32_t set_stride) {
-  if (flags == nullptr) return;
-  const uint32_t g = *reinterpret_cast<volatile uint32_t*>(gen);
-  uint32_t* z = flags + ((g + 1u) & 1u) * set_stride;
-  for (uint32_t i = blockIdx.x * kHeadThreads + threadIdx.x; i < set_stride; i += gridDim.x * kHeadThreads) z[i] = 0u;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(gen + 1, 1u) == gridDim.x - 1) {
-      gen[1] = 0u;
-      __threadfence();
-      *reinterpret_cast<volatile uint32_t*>(gen) = g + 1u;
-    }
-  }
 }
 
 __global__ void __launch_bounds__(kHeadThreads)
@@ -349,7 +326,6 @@ head_i8_kernel(const uint8_t* __restrict__ in, float* __restrict__ logits, uint8
     const int q = requant_i8(a, p.bdiv[o], p.mult[o], p.fc_zp, 0);
     logits[static_cast<long long>(img) * p.classes + o] = __fmul_rn(__int2float_rn(q - p.fc_zp), p.fc_scale);
   }
-  head_sync_turnover(p.sync_flags, p.sync_gen, p.sync_set_stride);
 }
 
 // FP16 head: avgpool (fp32 accumulate, rounded to f16 like the reference's pooled tensor) + fc.
@@ -359,9 +335,6 @@ struct HeadF16Params {
   const float* bias;
   __half* pooled = nullptr;   // calibration only (observe.cuh): the avgpool output, [n][c]
   int w_smem = 0;             // as HeadParams::w_smem (2 * classes * cpad bytes)
-  uint32_t* sync_flags = nullptr;
-  uint32_t* sync_gen = nullptr;
-  uint32_t sync_set_stride = 0;
 };
 
 __global__ void __launch_bounds__(kHeadThreads)
@@ -443,7 +416,6 @@ head_f16_kernel(const __half* __restrict__ in, __half* __restrict__ logits, cons
     for (int wv = 0; wv < kHeadThreads / 32; ++wv) a += s_part[wv][o];
     logits[static_cast<long long>(img) * p.classes + o] = __float2half_rn(a);
   }
-  head_sync_turnover(p.sync_flags, p.sync_gen, p.sync_set_stride);
 }
 
 // --------------------------------------------------------------------------------------------

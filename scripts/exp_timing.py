@@ -34,7 +34,7 @@ for li, L in enumerate(eng.net.layers):
     m = a[live].mean(0)
     mhz = 1e3 * a[live][:, 9].sum() / max(a[live][:, 10].sum(), 1)
     print(f"{L.name:22s} {int(live.sum()):4d} {4 * m[8]:8.1f}  | {m[9]:9.0f} {mhz:6.0f} | {m[0]:9.0f} {m[1]:9.0f} {m[2]:8.0f} | {m[4]:9.0f} {m[5]:8.0f} | "
-          f"{m[6]:9.0f} {m[7]:8.0f} | polls {m[12]:5.1f} clk {m[11]:8.0f}")
+          f"{m[6]:9.0f} {m[7]:8.0f}")
 
 a = t[31]
 live = a[:, 10] > 0
