@@ -11,6 +11,14 @@
 // each for 3-8 us of work (launch ramp, prologue, pipeline fill and drain on an almost idle GPU); as a tile class they
 // cost their steady-state share only, and the forward has three launches fewer.
 //
+// Pixel-pair form (INT8 layer 2.0: 3x3 stride 2 over 64-byte pixels).  An im2col TMA delivers ROWS, ~3 cycles each
+// whatever their length, and nine 128-row x 64-byte loads per tile are 3 450 cycles for 1 150 cycles of
+// MMAs.  Two adjacent pixels are one 128-byte "wide pixel"; output column ox reads pixels 2ox-1, 2ox, 2ox+1 = the second
+// half of wide pixel ox-1 and both halves of wide pixel ox, so the conv is a 3 (rows, stride 2) x 2 (wide columns,
+// stride 1, left pad 1) conv over 128-byte pixels with zero weights on the unused half: six loads of 128 rows instead
+// of nine, and the 1x1 downsample is the first half of wide tap (1, 1).  ConvTcParams::kw / stride_w / pad_w carry the
+// W-side geometry; the weights are packed accordingly by the host (ievm.cu: upload_conv_operands).
+//
 // Warp roles as in conv_tc.cuh (im2col mode): warp 0 TMA producer, warp 1 MMA issuer, 16 epilogue warps in groups.
 #pragma once
 #include "conv_tc.cuh"
@@ -36,7 +44,10 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  const int num_kb = p.ksize * p.ksize * p.kchunks;       // class 0; class 1 has p.kchunks k-blocks
+  const int kw = p.kw != 0 ? p.kw : p.ksize;              // taps along W (pixel-pair form: 2 wide taps)
+  const int stride_w = p.kw != 0 ? p.stride_w : p.stride;
+  const int pad_w = p.kw != 0 ? p.pad_w : p.pad;
+  const int num_kb = p.ksize * kw * p.kchunks;            // class 0; class 1 has p.kchunks k-blocks
   const int a_bytes = p.a_stage_bytes;
   const int b_bytes = (p.bn / kCluster) * p.kc_bytes;
   const int G = p.kb_group;
@@ -102,7 +113,7 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int tile_first = kCluster > 1 ? static_cast<int>(blockIdx.x) / kCluster : static_cast<int>(blockIdx.x);
   const int tile_step = kCluster > 1 ? static_cast<int>(gridDim.x) / kCluster : static_cast<int>(gridDim.x);
   const int hw = p.ho * p.wo;
-  const int ctr = p.ksize >> 1;                          // the centre tap
+  const int ctr_y = p.ksize >> 1, ctr_x = kw >> 1;       // the tap whose tile is the downsample's operand
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -128,14 +139,15 @@ conv_dual_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int rem = m0 - img * hw;
       const int oy = fast_div(rem, p.wo, p.wo_magic);
       const int ox = rem - oy * p.wo;
-      const int base_w = ox * p.stride - p.pad;
+      const int base_w = ox * stride_w - pad_w;
       const int base_h = oy * p.stride - p.pad;
-      const int t_lo = cls1 ? ctr : 0, t_hi = cls1 ? ctr + 1 : p.ksize;
+      const int ty_lo = cls1 ? ctr_y : 0, ty_hi = cls1 ? ctr_y + 1 : p.ksize;
+      const int tx_lo = cls1 ? ctr_x : 0, tx_hi = cls1 ? ctr_x + 1 : kw;
       const int nkb = cls1 ? p.kchunks : num_kb;
       const CUtensorMap* wmap = cls1 ? &tmap_b2 : &tmap_b;
       int kb = 0, g = 0;
-      for (int ty = t_lo; ty < t_hi; ++ty) {
-        for (int tx = t_lo; tx < t_hi; ++tx) {
+      for (int ty = ty_lo; ty < ty_hi; ++ty) {
+        for (int tx = tx_lo; tx < tx_hi; ++tx) {
           for (int ch = 0; ch < p.kchunks; ++ch) {
             if (g == 0) wait_or_die(&empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
             const int slot = stage * G + g;

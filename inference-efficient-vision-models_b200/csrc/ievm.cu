@@ -176,6 +176,10 @@ struct LayerPlan {
   int dual_stages = 0, dual_kb_group = 1, dual_max_clusters = 0;
   size_t dual_smem_bytes = 0;
   CUtensorMap tmap_b2;          // the downsample's weights with the 3x3's N-tile box
+  // pixel-pair form of the dual launch (conv_dual.cuh): INT8 3x3 stride-2 convs over 64-byte pixels
+  int dual_wide = 0;
+  void* w_wide = nullptr;       // on the 3x3: [cout_pad][3 x 2 wide taps][128]; on the downsample: [cout_pad][1][128]
+  CUtensorMap tmap_a_wide, tmap_b_wide;
 };
 
 }  // namespace
@@ -207,6 +211,7 @@ struct ievm_handle {
   int opt_pdl = 1;         // IEVM_PDL=0: no programmatic dependent launch
   int opt_fixed_bn = 0;    // IEVM_FIXED_BN=1: one N tile per <=256 channels (disables the tile-width heuristic)
   int opt_dual = 1;        // IEVM_DUAL=0 / option "dual": the 1x1 downsample convs run as launches of their own
+  int opt_wide = 1;        // IEVM_WIDE=0: no pixel-pair form in dual launches (conv_dual.cuh)
   int front_chunk = 0;     // IEVM_FRONT_CHUNK: images per front-end chunk (0 = whole batch at once, default)
   // IEVM_HALO_RB128=1: 64-byte pixels use 128-byte shared-memory rows in halo mode
   int in_c = 0, in_h = 0, in_w = 0, classes = 0;
@@ -564,12 +569,18 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
     constexpr int kMaxStages = 16;
     const int fixed2 = 1024 + 4 * P.cout_pad * 4 + (2 * kMaxStages + 2 * kMaxAcc + 1) * 8 + 16;
     const int avail2 = h->smem_optin - fixed2;
-    const int a_bytes = kTileM * P.kc_bytes;
-    const int b_bytes = (P.bn / P.cluster) * P.kc_bytes;
-    const int num_kb = 9 * P.kchunks;
+    // pixel-pair form: 64-byte pixels, stride 2, even width, weights resident
+    const bool wide = h->dtype == IEVM_DTYPE_I8 && a.stride == 2 && P.kc_bytes == 64 && P.kchunks == 1 && P.cin_pitch == 64 &&
+                      P.w % 2 == 0 && P.resident_b && P.cluster == 1 && h->opt_wide &&
+                      (6 + 1) * P.bn * 128 + 4 * kTileM * 128 <= avail2;
+    const int kcb = wide ? 128 : P.kc_bytes;
+    const int a_bytes = kTileM * kcb;
+    const int b_bytes = (P.bn / P.cluster) * kcb;
+    const int num_kb = (wide ? 6 : 9) * P.kchunks;
     const int slots = P.resident_b ? std::min(kMaxStages, (avail2 - (num_kb + P.kchunks) * b_bytes) / a_bytes)
                                    : std::min(kMaxStages, avail2 / (a_bytes + b_bytes));
     if (slots < 2) continue;
+    P.dual_wide = wide ? 1 : 0;
     int G = 1;
     for (int g = 4; g >= 2; --g)
       if (num_kb % g == 0 && slots / g >= 3) {
@@ -691,6 +702,31 @@ int upload_conv_operands(ievm_handle* h, LayerPlan& L) {
     int8_t* dw = nullptr;
     if (int rc = dev_upload(h, wp, &dw)) return rc;
     L.w_packed = dw;
+    // pixel-pair form of the dual launch (conv_dual.cuh): a wide tap is 128 bytes = pixels (2j, 2j+1) x 64 channels
+    if (L.dual_partner >= 0 && L.dual_wide) {
+      // the 3x3: wide tap (ty, 0) = [unused pixel 2ox-2 | kx = 0], wide tap (ty, 1) = [kx = 1 | kx = 2]
+      std::vector<int8_t> ww(static_cast<size_t>(L.cout_pad) * 6 * 128, 0);
+      for (int co = 0; co < d.cout; ++co)
+        for (int ci = 0; ci < d.cin; ++ci)
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+              const int tx = kx == 0 ? 0 : 1, half = kx == 1 ? 0 : 1;
+              ww[(static_cast<size_t>(co) * 6 + ky * 2 + tx) * 128 + half * 64 + ci] =
+                  w[(static_cast<size_t>(co) * d.cin + ci) * 9 + ky * 3 + kx];
+            }
+      int8_t* dww = nullptr;
+      if (int rc = dev_upload(h, ww, &dww)) return rc;
+      L.w_wide = dww;
+    }
+    if (L.dual_of >= 0 && h->layers[L.dual_of].dual_wide) {
+      // the 1x1 downsample: pixel (2oy, 2ox) = first half of wide tap (1, 1)
+      std::vector<int8_t> ww(static_cast<size_t>(L.cout_pad) * 128, 0);
+      for (int co = 0; co < d.cout; ++co)
+        for (int ci = 0; ci < d.cin; ++ci) ww[static_cast<size_t>(co) * 128 + ci] = w[static_cast<size_t>(co) * d.cin + ci];
+      int8_t* dww = nullptr;
+      if (int rc = dev_upload(h, ww, &dww)) return rc;
+      L.w_wide = dww;
+    }
     if (d.in_zp != 0) {
       // border-aware zero-point correction (ConvTcParams::zcorr): class = (row-tap mask << k) | column-tap mask
       const int k = d.ksize, ncls = 1 << (2 * k);
@@ -932,7 +968,32 @@ int encode_maps(ievm_handle* h) {
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled failed for layer %zu: CUresult %d", i, (int)r);
     }
-    if (L.dual_partner >= 0) {
+    if (L.dual_partner >= 0 && L.dual_wide) {
+      // pixel-pair form: the input as (128 B wide pixels, W / 2, H, N); 3 x 2 taps, stride (1, 2), padding left / top 1
+      const LayerPlan& D = h->layers[L.dual_partner];
+      cuuint64_t dims[4] = {128, static_cast<cuuint64_t>(L.w / 2), static_cast<cuuint64_t>(L.h), static_cast<cuuint64_t>(h->max_batch)};
+      cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(L.w) * L.cin_pitch, static_cast<cuuint64_t>(L.h) * L.w * L.cin_pitch};
+      int lower[2] = {-1, -1};
+      int upper[2] = {-1, -1};              // W: no right padding, 2 taps; H: padding 1, 3 taps
+      cuuint32_t estr[4] = {1, 1, 2, 1};
+      CUresult r = g_encode_im2col(&L.tmap_a_wide, dt, 4, tensor_ptr(h, L.d.in_tensor), dims, strides, lower, upper, 128, kTileM,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeIm2col (pixel pairs) failed for layer %zu: CUresult %d", i, (int)r);
+      cuuint32_t westr[2] = {1, 1};
+      cuuint32_t wbox[2] = {128, static_cast<cuuint32_t>(L.bn)};
+      cuuint64_t wdims[2] = {6 * 128, static_cast<cuuint64_t>(L.cout_pad)};
+      cuuint64_t wstr[1] = {6 * 128};
+      r = g_encode_tiled(&L.tmap_b_wide, dt, 2, L.w_wide, wdims, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) {
+        cuuint64_t ddims[2] = {128, static_cast<cuuint64_t>(D.cout_pad)};
+        cuuint64_t dstr[1] = {128};
+        r = g_encode_tiled(&L.tmap_b2, dt, 2, D.w_wide, ddims, dstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled (pixel-pair weights) failed for layer %zu: CUresult %d", i, (int)r);
+    } else if (L.dual_partner >= 0) {
       // the downsample's packed weights (one tap) read with THIS layer's N-tile box
       const LayerPlan& D = h->layers[L.dual_partner];
       const size_t k_total = D.cin_w;
@@ -1114,6 +1175,15 @@ int launch_conv_dual(ievm_handle* h, const LayerPlan& P, int n, cudaStream_t s, 
   ConvTcParams p = make_conv_params(h, P, n, dump0);
   p.stages = P.dual_stages;
   p.kb_group = P.dual_kb_group;
+  if (P.dual_wide) {          // pixel-pair form: 128-byte wide pixels, 3 x 2 taps, stride (2, 1), left padding 1
+    p.kc_bytes = 128;
+    p.kc_elems = 128;
+    p.kchunks = 1;
+    p.a_stage_bytes = p.a_tx_bytes = kTileM * 128;
+    p.kw = 2;
+    p.stride_w = 1;
+    p.pad_w = 1;
+  }
   ConvDualParams x;
   memset(&x, 0, sizeof(x));
   x.out = tensor_ptr(h, D.d.out_tensor);
@@ -1130,7 +1200,8 @@ int launch_conv_dual(ievm_handle* h, const LayerPlan& P, int n, cudaStream_t s, 
   const int grid = std::min(2 * class_tiles, max_cl) * cl;
 #define IEVM_LAUNCH_DUAL(DT, CL)                                                                                        \
   CUDA_TRY(launch_kernel_cluster(conv_dual_kernel<DT, CL>, grid, kConvThreads, P.dual_smem_bytes, s, h->opt_pdl != 0, \
-                                 static_cast<unsigned>(CL), P.tmap_a, P.tmap_b, P.tmap_b2, p, x))
+                                 static_cast<unsigned>(CL), P.dual_wide ? P.tmap_a_wide : P.tmap_a,                  \
+                                 P.dual_wide ? P.tmap_b_wide : P.tmap_b, P.tmap_b2, p, x))
   if (h->dtype == IEVM_DTYPE_I8) {
     if (cl == 2) IEVM_LAUNCH_DUAL(kDtypeI8, 2); else IEVM_LAUNCH_DUAL(kDtypeI8, 1);
   } else {
@@ -1619,6 +1690,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (const char* e = getenv("IEVM_FIXED_BN")) h->opt_fixed_bn = atoi(e);
   if (const char* e = getenv("IEVM_PDL")) h->opt_pdl = atoi(e);
   if (const char* e = getenv("IEVM_DUAL")) h->opt_dual = atoi(e);
+  if (const char* e = getenv("IEVM_WIDE")) h->opt_wide = atoi(e);
   if (const char* e = getenv("IEVM_CLUSTER")) h->opt_cluster = atoi(e);
   if (const char* e = getenv("IEVM_HOST_CHUNK")) h->host_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
