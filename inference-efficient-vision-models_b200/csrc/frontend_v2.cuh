@@ -95,7 +95,7 @@ struct F2Cfg {
 struct Frontend2Params {
   int n, h;                  // images, input height (multiple of 4); the width is kF2W
   int ho, ph;                // stem rows (h / 2), pooled rows (h / 4)
-  int tpu, upi;              // pooled rows per work unit, units per image
+  int tpu;                   // cap on the pooled rows of one work unit (0 = none; diagnostics: IEVM_FRONT_TPU)
   int in_zp;
   float inv_scale;
   uint32_t idesc;
@@ -111,15 +111,32 @@ struct Frontend2Params {
   unsigned int* stuck_flag;
 };
 
+// Work distribution: the n * ph pooled rows of the batch are cut into gridDim.x CONTIGUOUS ranges whose sizes differ by at
+// most one row; a CTA walks its range as units = runs of rows inside one image (a unit starts with one warm-up tile for
+// the stem row above it).  Round 1 cut every image into equal units and dealt them round-robin: 103.8 tiles per CTA at
+// batch 256 for 96.9 rows of work; contiguous ranges need 96.9 + one warm-up per image touched (~ 2.7).
 struct F2Unit {
   int img, t0, nt;
 };
-__device__ __forceinline__ F2Unit f2_unit(const Frontend2Params& p, int u) {
-  F2Unit r;
-  r.img = u / p.upi;
-  r.t0 = (u - r.img * p.upi) * p.tpu;
-  r.nt = min(p.tpu, p.ph - r.t0);
-  return r;
+struct F2Walk {
+  int row, row_end;
+};
+__device__ __forceinline__ F2Walk f2_walk_begin(const Frontend2Params& p) {
+  const int total = p.n * p.ph, g = static_cast<int>(gridDim.x), b = static_cast<int>(blockIdx.x);
+  const int q = total / g, r = total - q * g;
+  F2Walk w;
+  w.row = b * q + min(b, r);
+  w.row_end = w.row + q + (b < r ? 1 : 0);
+  return w;
+}
+__device__ __forceinline__ bool f2_next_unit(const Frontend2Params& p, F2Walk& w, F2Unit& un) {
+  if (w.row >= w.row_end) return false;
+  un.img = w.row / p.ph;
+  un.t0 = w.row - un.img * p.ph;
+  un.nt = min(p.ph - un.t0, w.row_end - w.row);
+  if (p.tpu > 0) un.nt = min(un.nt, p.tpu);
+  w.row += un.nt;
+  return true;
 }
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -162,7 +179,7 @@ __device__ __forceinline__ uint32_t f2_max3(uint32_t a, uint32_t b, uint32_t c) 
 // Epilogue of one warpgroup (kWg = 0: pooled columns 0..27, kWg = 1: 28..55).
 template <int kDtype, int kWg, int kSlots, bool kFast>
 __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t tmem_base, uint64_t* tmem_full,
-                                            uint64_t* tmem_empty, uint4* s_x, int units) {
+                                            uint64_t* tmem_empty, uint4* s_x) {
   constexpr int kOff = kWg == 0 ? -1 : 7;        // register index of a pooled column's first stem column: 2k + kOff
   constexpr int kCol0 = kWg == 0 ? 0 : 48;       // first TMEM column this warpgroup loads
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,8 +203,9 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
   for (int k = 0; k < kF2PxPerWg; ++k) prev[k] = kLow;
   int t = 0, ts_next = 0;
   uint32_t ph_next = 0;
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const F2Unit un = f2_unit(p, u);
+  F2Walk walk = f2_walk_begin(p);
+  F2Unit un;
+  while (f2_next_unit(p, walk, un)) {
     for (int i = 0; i <= un.nt; ++i, ++t) {
       const int T = un.t0 - 1 + i;               // pooled row of this tile (the warm-up tile i == 0 only feeds `prev`)
       const int ts = ts_next;
@@ -384,11 +402,10 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
   __syncthreads();
   tc_fence_after();
 
-  const int units = p.n * p.upi;
 
   if (warp < kF2EpiWarps) {
-    if (warp < 4) f2_epilogue<kDtype, 0, Cfg::kSlots, kFast>(p, tmem_base, tmem_full, tmem_empty, sX, units);
-    else f2_epilogue<kDtype, 1, Cfg::kSlots, kFast>(p, tmem_base, tmem_full, tmem_empty, sX, units);
+    if (warp < 4) f2_epilogue<kDtype, 0, Cfg::kSlots, kFast>(p, tmem_base, tmem_full, tmem_empty, sX);
+    else f2_epilogue<kDtype, 1, Cfg::kSlots, kFast>(p, tmem_base, tmem_full, tmem_empty, sX);
   } else if (warp == kF2MmaWarp) {
     // ================================ MMA issuer ================================
     const uint32_t hi = (128u >> 4) | (1u << 14);                                  // SBO = 128 B, version 1, no swizzle
@@ -400,8 +417,9 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
     long long f2_wait = 0, f2_wait_line = 0;
     const long long f2_t0 = clock64();
 #endif
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const F2Unit un = f2_unit(p, u);
+    F2Walk walk = f2_walk_begin(p);
+    F2Unit un;
+    while (f2_next_unit(p, walk, un)) {
       for (int i = 0; i <= un.nt; ++i, ++t) {
         const int qn = q0 + i + 2;               // newest chunk this tile reads (chunks complete in order)
         {
@@ -473,8 +491,9 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
     long long f2_wait = 0;
     const long long f2_t0 = clock64();
 #endif
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const F2Unit un = f2_unit(p, u);
+    F2Walk walk = f2_walk_begin(p);
+    F2Unit un;
+    while (f2_next_unit(p, walk, un)) {
       for (int j = 0; j < un.nt + 3; ++j, ++q) {
         const int slot = q % kF2RawSlots;
 #ifdef IEVM_EXP_TIMING
@@ -511,8 +530,9 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
     long long f2_wait_raw = 0, f2_wait_line = 0;
     const long long f2_t0 = clock64();
 #endif
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const F2Unit un = f2_unit(p, u);
+    F2Walk walk = f2_walk_begin(p);
+    F2Unit un;
+    while (f2_next_unit(p, walk, un)) {
       for (int j = 0; j < un.nt + 3; ++j, ++q) {
         const int slot = q % kF2RawSlots, cs = q % kF2ChunkSlots;
 #ifdef IEVM_EXP_TIMING

@@ -1296,23 +1296,6 @@ bool front_end_is_v2(const ievm_handle* h) {
          h->tensors[h->layers[0].d.out_tensor].last_use == 1;
 }
 
-// Pooled rows per work unit: the persistent grid runs ceil(units / #SMs) rounds of (tpu + 1 warm-up) tiles.
-int front2_tiles_per_unit(const ievm_handle* h, int n, int ph) {
-  if (h->front_tpu > 0) return std::min(h->front_tpu, ph);
-  int best = ph;
-  double best_cost = 1e30;
-  for (int tpu = 1; tpu <= ph; ++tpu) {
-    const long long units = static_cast<long long>(n) * ((ph + tpu - 1) / tpu);
-    const long long rounds = (units + h->num_sms - 1) / h->num_sms;
-    const double cost = static_cast<double>(rounds) * (tpu + 2.5);
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = tpu;
-    }
-  }
-  return best;
-}
-
 int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32_t* dump_acc, bool u8_input = false) {
   const LayerPlan& Ls = h->layers[0];
   const LayerPlan& Lp = h->layers[1];
@@ -1348,8 +1331,7 @@ int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32
   fp.h = h->in_h;
   fp.ho = Ls.ho;
   fp.ph = Lp.ho;
-  fp.tpu = front2_tiles_per_unit(h, n, fp.ph);
-  fp.upi = (fp.ph + fp.tpu - 1) / fp.tpu;
+  fp.tpu = h->front_tpu > 0 ? std::min(h->front_tpu, fp.ph) : 0;
   fp.in_zp = h->in_zp;
   fp.inv_scale = i8 ? 1.0f / h->in_scale : 1.0f;
   fp.idesc = i8 ? make_idesc_i8_s8u8(kF2Wo) : make_idesc_f16(kF2Wo);
@@ -1364,7 +1346,7 @@ int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32
   fp.fast_round = Ls.fast_round;
   fp.dump_acc = dump_acc;
   fp.stuck_flag = h->stuck_dev;
-  const int grid = std::min(n * fp.upi, h->num_sms);
+  const int grid = std::min(n * fp.ph, h->num_sms);       // contiguous ranges of pooled rows (frontend_v2.cuh: F2Walk)
   if (u8_input && fp.fast_round) frontend2_kernel<kDtypeI8, 1, true><<<grid, kF2Threads, F2Cfg<kDtypeI8, 1>::kSmemBytes, s>>>(tmap, fp);
   else if (u8_input) frontend2_kernel<kDtypeI8, 1><<<grid, kF2Threads, F2Cfg<kDtypeI8, 1>::kSmemBytes, s>>>(tmap, fp);
   else if (i8 && fp.fast_round) frontend2_kernel<kDtypeI8, 0, true><<<grid, kF2Threads, F2Cfg<kDtypeI8>::kSmemBytes, s>>>(tmap, fp);
