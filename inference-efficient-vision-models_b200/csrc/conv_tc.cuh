@@ -254,7 +254,7 @@ __device__ __forceinline__ uint4 epilogue16_i8(const uint32_t (&v)[16], const fl
 // 16 accumulators + 16 residual bytes -> 16 bytes of quantized::add_relu(requant(acc), residual).
 // All float steps reproduce the scalar definition exactly: clamping before rounding commutes with
 // RNE because the clamp bounds are integers, and (x + M) - M is RNE for |x| <= 256.
-template <bool kFast>
+template <bool kFast, bool kResI2F = false>
 __device__ __forceinline__ uint4 epilogue16_i8_res(const uint32_t (&v)[16], const uint4 r4, const float* s_bd,
                                                    const float* s_mu, const AddReluConst& k) {
   const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
@@ -270,8 +270,13 @@ __device__ __forceinline__ uint4 epilogue16_i8_res(const uint32_t (&v)[16], cons
       const int i = 4 * j + b;
       float t = __fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[i])), bd[b]), mu[b]);
       // dequantised residual: (magic | byte) - magic == float(byte), then fma(s_r, byte, fl(s_r * -zp_r)) as ATen does
-      const float rb = __fmaf_rn(k.r_scale, __fadd_rn(__uint_as_float(__byte_perm(rw[j], 0x4B400000u, 0x7650 + b)), -kRoundMagic),
-                                 k.pb);
+      // float(byte): (magic | byte) - magic is PRMT + FADD, two issue slots on the ALU and FMA pipes; I2F.U8 with a byte
+      // selector is one slot on the 4-cycle conversion pipe, which the two I2Fs of the requantisation already load.
+      // Measured: the unrolled 64-channel kernels are faster with the first form (58 vs 60 us), the 128-channel loop
+      // kernels with the second (39 vs 41 us) -- kResI2F picks per instantiation.  Both are exact.
+      const float rbyte = kResI2F ? static_cast<float>((rw[j] >> (8 * b)) & 0xffu)
+                                  : __fadd_rn(__uint_as_float(__byte_perm(rw[j], 0x4B400000u, 0x7650 + b)), -kRoundMagic);
+      const float rb = __fmaf_rn(k.r_scale, rbyte, k.pb);
       if (kFast) {
         // Integer clamps after the magic-number rounding: rne commutes with clamping to integer bounds, and
         // max(s, 0) before the final scaling equals clamping the rounded value at 0 (the scale is positive), so
@@ -350,7 +355,7 @@ __device__ __forceinline__ uint4 load_res16_i8(const ConvTcParams& p, int m, boo
   return __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch));
 }
 
-template <int kDtype, bool kHasRes>
+template <int kDtype, bool kHasRes, bool kResI2F = false>
 __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint32_t (&v)[16], const uint4 r4, int m,
                                                bool valid, int ch, const float* s_ep0, const float* s_ep1,
                                                const AddReluConst& k) {
@@ -373,8 +378,8 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
     uint8_t* op = static_cast<uint8_t*>(p.out) + static_cast<size_t>(m) * p.out_pitch + ch;
     uint4 o;
     if (kHasRes) {
-      o = p.fast_round ? epilogue16_i8_res<true>(v, r4, s_ep0 + ch, s_ep1 + ch, k)
-                       : epilogue16_i8_res<false>(v, r4, s_ep0 + ch, s_ep1 + ch, k);
+      o = p.fast_round ? epilogue16_i8_res<true, kResI2F>(v, r4, s_ep0 + ch, s_ep1 + ch, k)
+                       : epilogue16_i8_res<false, kResI2F>(v, r4, s_ep0 + ch, s_ep1 + ch, k);
     } else {
       o = p.fast_round ? epilogue16_i8<true>(v, s_ep0 + ch, s_ep1 + ch, p.out_zp, p.out_lo)
                        : epilogue16_i8<false>(v, s_ep0 + ch, s_ep1 + ch, p.out_zp, p.out_lo);
@@ -903,13 +908,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tmem_ld_wait();
           tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 1) * 16), vv[1]);
           if (kResI8) rr[1] = load_res16_i8(p, m, valid, (c + 1) * 16);
-          epilogue_chunk<kDtype, kHasRes>(p, vv[0], rr[0], m, valid, c * 16, p.epc0, p.epc1, k);
+          epilogue_chunk<kDtype, kHasRes, true>(p, vv[0], rr[0], m, valid, c * 16, p.epc0, p.epc1, k);
           tmem_ld_wait();
           if (c + 2 < kNch) {
             tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 2) * 16), vv[0]);
             if (kResI8) rr[0] = load_res16_i8(p, m, valid, (c + 2) * 16);
           }
-          epilogue_chunk<kDtype, kHasRes>(p, vv[1], rr[1], m, valid, (c + 1) * 16, p.epc0, p.epc1, k);
+          epilogue_chunk<kDtype, kHasRes, true>(p, vv[1], rr[1], m, valid, (c + 1) * 16, p.epc0, p.epc1, k);
         }
       }
 #endif
