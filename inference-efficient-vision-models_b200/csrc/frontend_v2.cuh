@@ -288,9 +288,11 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
         if (kDtype == kDtypeI8) {
           if (kFast) {
             // magic-number rounding (|value| < 2^21 for every possible input, checked at engine creation): FADD instead
-            // of the 8-cycle F2I, and the zero-point add and lower clamp in one VIADDMNMX
+            // of the 8-cycle F2I; the zero-point add and BOTH clamps are one VIADDMNMX.RELU -- the host enables this
+            // instantiation only when the lower clamp is 0 (a ReLU stem whose output zero point is 0: every fbgemm qconfig)
             const float v = __fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(m) - zw), bd), mu);
-            orow[k * 64] = static_cast<uint8_t>(min(round_add_max<true>(v, p.out_zp, p.out_lo), 255));
+            orow[k * 64] = static_cast<uint8_t>(
+                __viaddmin_s32_relu(__float_as_int(__fadd_rn(v, kRoundMagic)), p.out_zp - kRoundMagicBits, 255));
           } else {
             orow[k * 64] = static_cast<uint8_t>(requant_i8(static_cast<int>(m) - zw, bd, mu, p.out_zp, p.out_lo));
           }

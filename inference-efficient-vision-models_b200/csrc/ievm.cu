@@ -1343,7 +1343,7 @@ int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32
   fp.lut = h->lut_dev;
   fp.out_zp = Ls.d.out_zp;
   fp.out_lo = Ls.d.relu ? Ls.d.out_zp : 0;
-  fp.fast_round = Ls.fast_round;
+  fp.fast_round = Ls.fast_round && fp.out_lo == 0;    // the fast instantiation folds both clamps into one instruction (lower = 0)
   fp.dump_acc = dump_acc;
   fp.stuck_flag = h->stuck_dev;
   const int grid = std::min(n * fp.ph, h->num_sms);       // contiguous ranges of pooled rows (frontend_v2.cuh: F2Walk)

@@ -62,6 +62,27 @@ def test_requant_fast_form_equals_the_oracle(relu):
     assert np.array_equal(got, want)
 
 
+def test_front_end_fast_form_with_both_clamps_in_one_instruction():
+    """frontend_v2.cuh, kFast: the stem's ReLU output has zero point 0, so the lower clamp is 0 and
+    clamp(rne(v) + zp, 0, 255) == max(min(bits(v + M) + (zp - M_bits), 255), 0) -- ONE VIADDMNMX.RELU (the host enables
+    the instantiation only when out_lo == 0; also checked here for a non-zero zero point of a non-ReLU output)."""
+    rng = np.random.default_rng(3)
+    n, c = 400_000, 64
+    acc = rng.integers(-200_000, 200_000, (n, c)).astype(np.int32)
+    acc[:100] = rng.integers(-2 ** 20, 2 ** 20, (100, c))
+    x_s, out_s = 0.0187, 0.0311
+    w_s = (rng.random(c, dtype=np.float32) * np.float32(0.004) + np.float32(0.0005)).astype(np.float32)
+    bias = (rng.standard_normal(c) * 0.5).astype(np.float32)
+    atw = (np.float32(x_s) * w_s).astype(np.float32)
+    bdiv, mult = (bias / atw).astype(np.float32), (atw / np.float32(out_s)).astype(np.float32)
+    v = ((acc.astype(np.float32) + bdiv).astype(np.float32) * mult).astype(np.float32)
+    assert np.abs(v).max() < 2 ** 21
+    for zp, relu in ((0, True), (37, False)):                # lower clamp 0 in both cases
+        want = O.requant(acc, x_s, w_s, bias, out_s, zp, relu, ch_axis=1)
+        got = viaddmin_relu(bits(v + MAGIC), zp - MAGIC_BITS, 255).astype(np.uint8)
+        assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("flavour", ["fbgemm_reduce_range", "main_py_full_range"])
 def test_fused_add_relu_fast_form_equals_the_oracle(flavour):
     """epilogue16_i8_res<kFast>: requantise the conv, dequantise it and the residual with ATen's fma form, add, ReLU,
