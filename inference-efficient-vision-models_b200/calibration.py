@@ -91,6 +91,20 @@ def _replay_histogram(obs, x_min: torch.Tensor, x_max: torch.Tensor, counts: np.
     """``HistogramObserver.forward`` (torch/ao/quantization/observer.py) with ``torch.aminmax(x)`` and
     ``torch.histc(x, bins, min, max)`` replaced by the values the device computed; everything else -- the running range,
     ``_combine_histograms`` with its up-scaling -- is the observer's own code on its own state."""
+    import inspect
+    # The replay calls the observer's private _combine_histograms; its signature changed between torch releases
+    # (older ones: orig_hist, new_hist, upsample_rate, downsample_rate, start_idx, Nbins).  Refuse clearly rather than
+    # fail with a TypeError in the middle of a calibration run (the reference only asks for torch >= 2.0).
+    want = ["orig_hist", "orig_min", "orig_max", "update_hist", "update_min", "update_max"]
+    have = list(inspect.signature(obs._combine_histograms).parameters)
+    if have != want:
+        raise NotImplementedError(
+            f"HistogramObserver._combine_histograms{tuple(have)} of this torch release is not the one the device-histogram "
+            f"replay was written against {tuple(want)}: calibrate this qconfig on the CPU (the reference's _calibrate), or "
+            "use a min/max observer qconfig")
+    if not (np.isfinite(float(x_min)) and np.isfinite(float(x_max))):
+        raise RuntimeError(f"{where}: non-finite activation range ({float(x_min)}, {float(x_max)}) -- the reference's "
+                           "HistogramObserver ignores infinities, the one-pass device histogram cannot")
     hist = torch.from_numpy(counts.astype(np.float32))
     cur_min, cur_max = obs.min_val, obs.max_val
     if cur_min == float("inf") or cur_max == float("-inf"):
