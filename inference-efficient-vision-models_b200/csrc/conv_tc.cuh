@@ -235,13 +235,8 @@ __device__ __forceinline__ uint4 epilogue16_i8(const uint32_t (&v)[16], const fl
   int q[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-#ifdef IEVM_EXP_NOTABLE
-    const float4 b4 = make_float4(s_bd[0], s_bd[0], s_bd[0], s_bd[0]);   // timing experiment: one broadcast load
-    const float4 m4 = make_float4(s_mu[0], s_mu[0], s_mu[0], s_mu[0]);
-#else
     const float4 b4 = *reinterpret_cast<const float4*>(s_bd + 4 * j);
     const float4 m4 = *reinterpret_cast<const float4*>(s_mu + 4 * j);
-#endif
     q[4 * j + 0] = round_add_max<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 0])), b4.x), m4.x), zp, lo);
     q[4 * j + 1] = round_add_max<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 1])), b4.y), m4.y), zp, lo);
     q[4 * j + 2] = round_add_max<kFast>(__fmul_rn(__fadd_rn(__int2float_rn(static_cast<int>(v[4 * j + 2])), b4.z), m4.z), zp, lo);
@@ -359,14 +354,6 @@ template <int kDtype, bool kHasRes, bool kResI2F = false>
 __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint32_t (&v)[16], const uint4 r4, int m,
                                                bool valid, int ch, const float* s_ep0, const float* s_ep1,
                                                const AddReluConst& k) {
-#ifdef IEVM_EXP_EPI_LDTM
-  // timing experiment: TMEM loads only -- fold the words so that the loads stay, store never happens
-  uint32_t x = v[0];
-#pragma unroll
-  for (int j = 1; j < 16; ++j) x ^= v[j];
-  if (x == 0x12345679u && m < 0) *(static_cast<uint32_t*>(p.out) + ch) = x;
-  return;
-#endif
   if (valid && p.dump_acc != nullptr) {
     int4* d = reinterpret_cast<int4*>(p.dump_acc + static_cast<size_t>(m) * p.dump_pitch + ch);
 #pragma unroll
@@ -384,11 +371,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
       o = p.fast_round ? epilogue16_i8<true>(v, s_ep0 + ch, s_ep1 + ch, p.out_zp, p.out_lo)
                        : epilogue16_i8<false>(v, s_ep0 + ch, s_ep1 + ch, p.out_zp, p.out_lo);
     }
-#ifdef IEVM_EXP_NOSTORE
-    if (valid && m < 0) *reinterpret_cast<uint4*>(op) = o;      // timing experiment: keep the math, drop the store
-#else
     if (valid) *reinterpret_cast<uint4*>(op) = o;
-#endif
   } else {
     __half* op = static_cast<__half*>(p.out) + static_cast<size_t>(m) * p.out_pitch + ch;
     const __half* rp = static_cast<const __half*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch;
@@ -521,12 +504,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int ns = min(p.band_subs, min(p.subs_per_img - s0, t_end - t));
         IEVM_TIMED_WAIT(tm_wait_a, &empty_bar[stage], phase ^ 1u, 0x100u | stage, p.stuck_flag);
         if (elect_one()) {
-#ifdef IEVM_EXP_NOTMA
-          mbar_arrive(&full_bar[stage]);                         // timing experiment: no activation loads
-#else
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_4d(sA + stage * a_bytes, &tmap_a, &full_bar[stage], 0, -1, s0 * p.sub_rows - 1, img);
-#endif
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -700,7 +679,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // instead of loop-invariant values parked in vector registers and moved back with R2UR before every use
             uint32_t b_base = b_lo0;
             asm volatile("" : "+r"(b_base));
-#ifndef IEVM_EXP_NOMMA
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const uint32_t ao = a_lo + static_cast<uint32_t>(tap / 3) * wp16 + static_cast<uint32_t>(tap % 3) * row16v;
@@ -712,7 +690,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 mma(d_tmem, ao + 6, bo + 6, 1u);
               }
             }
-#endif
             umma_commit(&tfull_bar[a2]);
             if (++a2 == p.nacc) a2 = 0;
           }
@@ -840,9 +817,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // two register buffers: the TMEM load (and residual fetch) of the next chunk is in flight while this
       // one is processed
       uint32_t va[16], vb[16];
-#ifdef IEVM_EXP_EPI_NONE
-      c = nchunks;                                               // timing experiment: epilogue does nothing
-#endif
       if (c < nchunks) tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>(c * 16), va);
       while (c < nchunks) {
         tmem_ld_wait();
@@ -888,7 +862,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(acc * p.acc_stride);
       uint32_t vv[2][16];
-#ifndef IEVM_EXP_EPI_NONE
       tmem_ld_32x32b_x16(t_row, vv[0]);
       if (kNch <= 4) {
 #pragma unroll
@@ -917,7 +890,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           epilogue_chunk<kDtype, kHasRes, true>(p, vv[1], rr[1], m, valid, (c + 1) * 16, p.epc0, p.epc1, k);
         }
       }
-#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
