@@ -75,6 +75,7 @@ struct ConvTcParams {
   int m_total;         // n * ho * wo
   int ho, wo;
   int stride, pad, ksize;
+  int phase_bytes;           // conv_s2.cuh: bytes of one phase buffer of a patch stage
   int kw, stride_w, pad_w;   // conv_dual.cuh, pixel-pair form: taps / stride / padding along W when they differ from H (kw == 0: same)
   int kchunks;         // channel chunks per filter tap
   int kc_bytes;        // bytes per smem row == bytes per channel chunk (64 or 128)

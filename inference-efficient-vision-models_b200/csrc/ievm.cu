@@ -20,6 +20,7 @@
 
 #include "conv_tc.cuh"
 #include "conv_dual.cuh"
+#include "conv_s2.cuh"
 #include "simt_kernels.cuh"
 #include "stem_tc.cuh"
 #include "frontend_v2.cuh"
@@ -178,6 +179,10 @@ struct LayerPlan {
   CUtensorMap tmap_b2;          // the downsample's weights with the 3x3's N-tile box
   // pixel-pair form of the dual launch (conv_dual.cuh): INT8 3x3 stride-2 convs over 64-byte pixels
   int dual_wide = 0;
+  // phase-patch form (conv_s2.cuh): the same layers as four stride-1 phase patches; preferred over the pixel-pair form
+  int dual_s2 = 0, s2_stages = 0, s2_rows = 0, s2_phase_bytes = 0;
+  size_t s2_smem_bytes = 0;
+  CUtensorMap tmap_a_s2, tmap_b2_s2;
   void* w_wide = nullptr;       // on the 3x3: [cout_pad][3 x 2 wide taps][128]; on the downsample: [cout_pad][1][128]
   CUtensorMap tmap_a_wide, tmap_b_wide;
 };
@@ -212,6 +217,7 @@ struct ievm_handle {
   int opt_fixed_bn = 0;    // IEVM_FIXED_BN=1: one N tile per <=256 channels (disables the tile-width heuristic)
   int opt_dual = 1;        // IEVM_DUAL=0 / option "dual": the 1x1 downsample convs run as launches of their own
   int opt_wide = 1;        // IEVM_WIDE=0: no pixel-pair form in dual launches (conv_dual.cuh)
+  int opt_s2 = 1;          // IEVM_S2=0: no phase-patch form of the stride-2 dual launch (conv_s2.cuh)
   int front_chunk = 0;     // IEVM_FRONT_CHUNK: images per front-end chunk (0 = whole batch at once, default)
   // IEVM_HALO_RB128=1: 64-byte pixels use 128-byte shared-memory rows in halo mode
   int in_c = 0, in_h = 0, in_w = 0, classes = 0;
@@ -581,6 +587,22 @@ int plan_shapes(ievm_handle* h, const ievm_net_desc* nd) {
                                    : std::min(kMaxStages, avail2 / (a_bytes + b_bytes));
     if (slots < 2) continue;
     P.dual_wide = wide ? 1 : 0;
+    // phase-patch form (conv_s2.cuh): 64-byte pixels, stride 2, one N tile of <= 128 channels, even input size
+    if (h->opt_s2 && h->dtype == IEVM_DTYPE_I8 && a.stride == 2 && P.kc_bytes == 64 && P.kchunks == 1 && P.cin_pitch == 64 &&
+        P.w % 2 == 0 && P.h % 2 == 0 && P.n_tiles == 1 && P.bn <= 128 && P.cluster == 1 && P.wo + 1 <= kTileM) {
+      const int wp = P.wo + 1;
+      const int R = kTileM / wp;
+      const int pbytes = round_up((R + 1) * wp * 64, 1024);
+      const int fixed_s2 = 1024 + 4 * P.cout_pad * 4 + (2 * kMaxStages + 2 * kMaxAcc + 1) * 8 + 16;
+      const int stages = std::min(4, (h->smem_optin - fixed_s2 - 10 * P.bn * 64 - 1024) / (4 * pbytes));
+      if (stages >= 2) {
+        P.dual_s2 = 1;
+        P.s2_rows = R;
+        P.s2_phase_bytes = pbytes;
+        P.s2_stages = stages;
+        P.s2_smem_bytes = static_cast<size_t>(stages) * 4 * pbytes + 1024 + 10 * P.bn * 64 + fixed_s2;
+      }
+    }
     int G = 1;
     for (int g = 4; g >= 2; --g)
       if (num_kb % g == 0 && slots / g >= 3) {
@@ -968,6 +990,29 @@ int encode_maps(ievm_handle* h) {
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled failed for layer %zu: CUresult %d", i, (int)r);
     }
+    if (L.dual_partner >= 0 && L.dual_s2) {
+      // phase patches (conv_s2.cuh): a tiled box that walks W and H with traversal stride 2 -- (R + 1) x (W_out + 1) pixels of
+      // one phase of the input, landing densely in shared memory
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(L.cin_pitch), static_cast<cuuint64_t>(L.w), static_cast<cuuint64_t>(L.h),
+                            static_cast<cuuint64_t>(h->max_batch)};
+      cuuint64_t strides[3] = {L.cin_pitch * e, static_cast<cuuint64_t>(L.w) * L.cin_pitch * e,
+                               static_cast<cuuint64_t>(L.h) * L.w * L.cin_pitch * e};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(2 * (L.wo + 1)), static_cast<cuuint32_t>(2 * (L.s2_rows + 1)), 1};
+      cuuint32_t estr[4] = {1, 2, 2, 1};
+      const CUresult r = g_encode_tiled(&L.tmap_a_s2, dt, 4, tensor_ptr(h, L.d.in_tensor), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled (phase patches) failed for layer %zu: CUresult %d", i, (int)r);
+      const LayerPlan& D = h->layers[L.dual_partner];       // the downsample's weights, 64-byte rows, this layer's N tile
+      cuuint64_t ddims[2] = {static_cast<cuuint64_t>(D.cin_w), static_cast<cuuint64_t>(D.cout_pad)};
+      cuuint64_t dstr[1] = {D.cin_w * e};
+      cuuint32_t dbox[2] = {64, static_cast<cuuint32_t>(L.bn)};
+      cuuint32_t destr[2] = {1, 1};
+      const CUresult r2 = g_encode_tiled(&L.tmap_b2_s2, dt, 2, D.w_packed, ddims, dstr, dbox, destr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r2 != CUDA_SUCCESS) return fail(IEVM_ERR_CUDA, "cuTensorMapEncodeTiled (phase-patch downsample weights) failed for layer %zu: CUresult %d", i, (int)r2);
+    }
     if (L.dual_partner >= 0 && L.dual_wide) {
       // pixel-pair form: the input as (128 B wide pixels, W / 2, H, N); 3 x 2 taps, stride (1, 2), padding left / top 1
       const LayerPlan& D = h->layers[L.dual_partner];
@@ -1175,7 +1220,7 @@ int launch_conv_dual(ievm_handle* h, const LayerPlan& P, int n, cudaStream_t s, 
   ConvTcParams p = make_conv_params(h, P, n, dump0);
   p.stages = P.dual_stages;
   p.kb_group = P.dual_kb_group;
-  if (P.dual_wide) {          // pixel-pair form: 128-byte wide pixels, 3 x 2 taps, stride (2, 1), left padding 1
+  if (P.dual_wide && !P.dual_s2) {          // pixel-pair form: 128-byte wide pixels, 3 x 2 taps, stride (2, 1), left padding 1
     p.kc_bytes = 128;
     p.kc_elems = 128;
     p.kchunks = 1;
@@ -1194,6 +1239,30 @@ int launch_conv_dual(ievm_handle* h, const LayerPlan& P, int n, cudaStream_t s, 
   x.fast_round = D.fast_round;
   x.relu = D.d.relu;
   x.dump_acc = dump1;
+  if (P.dual_s2) {
+    // phase-patch form (conv_s2.cuh): sub-tiles of R output rows, four stride-1 phase patches per sub-tile
+    const int wp = P.wo + 1, R = P.s2_rows, T = (P.ho + R - 1) / R;
+    p.stages = P.s2_stages;
+    p.kb_group = 1;
+    p.wp = wp;
+    p.sub_rows = R;
+    p.sub_pos = R * wp;
+    p.subs_per_img = T;
+    p.total_subs = n * T;
+    p.spi_magic = (T > 1 && static_cast<long long>(n) * T * T < 0x100000000ll) ? static_cast<uint32_t>((0x100000000ull + T - 1) / T) : 0u;
+    p.wp_magic = static_cast<uint32_t>((0x100000000ull + wp - 1) / wp);
+    p.phase_bytes = P.s2_phase_bytes;
+    p.a_stage_bytes = 4 * P.s2_phase_bytes;
+    p.a_tx_bytes = 4 * (R + 1) * wp * 64;
+    p.acc_stride = 128;
+    p.nacc = 4;
+    p.tmem_cols = 512;
+    const int grid = std::min(p.total_subs, h->num_sms);
+    CUDA_TRY(launch_kernel_cluster(conv_s2_kernel, grid, kConvThreads, P.s2_smem_bytes, s, h->opt_pdl != 0, 1u, P.tmap_a_s2,
+                                   P.tmap_b, P.tmap_b2_s2, p, x));
+    CUDA_TRY(cudaGetLastError());
+    return IEVM_OK;
+  }
   const int cl = P.cluster;
   const int class_tiles = ((p.m_tiles + cl - 1) / cl) * p.n_tiles;
   const int max_cl = cl > 1 ? (P.dual_max_clusters > 0 ? P.dual_max_clusters : h->num_sms / cl) : h->num_sms;
@@ -1673,6 +1742,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (const char* e = getenv("IEVM_PDL")) h->opt_pdl = atoi(e);
   if (const char* e = getenv("IEVM_DUAL")) h->opt_dual = atoi(e);
   if (const char* e = getenv("IEVM_WIDE")) h->opt_wide = atoi(e);
+  if (const char* e = getenv("IEVM_S2")) h->opt_s2 = atoi(e);
   if (const char* e = getenv("IEVM_CLUSTER")) h->opt_cluster = atoi(e);
   if (const char* e = getenv("IEVM_HOST_CHUNK")) h->host_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);
@@ -1699,7 +1769,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (rc == IEVM_OK) rc = encode_maps(h);
   if (rc == IEVM_OK) {
     size_t max_smem = 0;
-    for (const LayerPlan& L : h->layers) max_smem = std::max(max_smem, std::max(L.smem_bytes, L.dual_smem_bytes));
+    for (const LayerPlan& L : h->layers) max_smem = std::max(max_smem, std::max(L.smem_bytes, std::max(L.dual_smem_bytes, L.s2_smem_bytes)));
     if (max_smem > static_cast<size_t>(prop.sharedMemPerBlockOptin)) rc = fail(IEVM_ERR_UNSUPPORTED, "smem plan exceeds device limit");
     if (rc == IEVM_OK && max_smem > 0) {
       cudaError_t e = cudaSuccess;
@@ -1726,6 +1796,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
       IEVM_ATTR(kDtypeF16, false, kModeHalo, 1, 0);   IEVM_ATTR(kDtypeF16, true, kModeHalo, 1, 0);
       IEVM_ATTR(kDtypeF16, false, kModeHalo, 1, 3);   IEVM_ATTR(kDtypeF16, true, kModeHalo, 1, 3);
 #undef IEVM_ATTR
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_dual_kernel<kDtypeI8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_dual_kernel<kDtypeI8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_dual_kernel<kDtypeF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms);
