@@ -33,6 +33,10 @@ struct ConvDualParams {
   int fast_round;
   int relu;              // f16
   int32_t* dump_acc;     // debug: raw accumulators of class 1
+  // the same tables inside the kernel-parameter block (filled when cout_pad <= kEpConst; conv_s2.cuh reads its tables as
+  // constant-bank operands through a uniform index, as the wide halo kernels do: no shared-memory loads in the epilogue)
+  float epc0[kEpConst];
+  float epc1[kEpConst];
 };
 
 template <int kDtype, int kCluster>

@@ -35,8 +35,7 @@ conv_s2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int b_bytes = p.bn * kRowBytes;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * p.a_stage_bytes + 1024;   // tap views of the last rows run < 1 KB past a stage
-  float* s_ep = reinterpret_cast<float*>(sB + kBlocks * b_bytes);     // [class][table][cout_pad]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ep + 4 * p.cout_pad);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kBlocks * b_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + kMaxAcc;
@@ -46,12 +45,6 @@ conv_s2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < p.cout_pad; i += kConvThreads) {
-    s_ep[i] = p.ep0[i];
-    s_ep[p.cout_pad + i] = p.ep1[i];
-    s_ep[2 * p.cout_pad + i] = x.ep0[i];
-    s_ep[3 * p.cout_pad + i] = x.ep1[i];
-  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -185,50 +178,54 @@ conv_s2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int nchunks = p.bn >> 4;
     griddep_wait_conv();
     uint8_t* out_base = static_cast<uint8_t*>(cls1 ? x.out : p.out);
-    const float* e0 = s_ep + (cls1 ? 2 * p.cout_pad : 0);
-    const float* e1 = e0 + p.cout_pad;
     const int zp = cls1 ? x.out_zp : p.out_zp;
     const int lo = cls1 ? x.out_lo : p.out_lo;
     const bool fast = (cls1 ? x.fast_round : p.fast_round) != 0;
     int32_t* dump = cls1 ? x.dump_acc : p.dump_acc;
-    for (int i = group >> 1; t_begin + i < t_end; i += 2) {
-      const int t = t_begin + i;
-      const int acc = 2 * (i & 1) + (cls1 ? 1 : 0);
-      const uint32_t acc_phase = static_cast<uint32_t>(i >> 1) & 1u;
-      const int img = fast_div(t, p.subs_per_img, p.spi_magic);
-      const int oy = (t - img * p.subs_per_img) * p.sub_rows + r;
-      const bool valid = pos_ok && oy < p.ho;
-      const int m = (img * p.ho + oy) * p.wo + c;
-      uint8_t* out_row = out_base + static_cast<size_t>(m) * p.out_pitch;
-      wait_or_die(&tfull_bar[acc], acc_phase, 0x400u | acc, p.stuck_flag);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * p.acc_stride);
-      uint32_t va[16], vb[16];
-      auto chunk = [&](const uint32_t (&v)[16], int ch) {
-        if (valid && dump != nullptr) {
-          int4* d = reinterpret_cast<int4*>(dump + static_cast<size_t>(m) * p.dump_pitch + ch);
+    // e0 / e1: this class's per-channel tables in the kernel-parameter block (constant bank, uniform index)
+    auto run = [&](const float* e0, const float* e1) {
+      for (int i = group >> 1; t_begin + i < t_end; i += 2) {
+        const int t = t_begin + i;
+        const int acc = 2 * (i & 1) + (cls1 ? 1 : 0);
+        const uint32_t acc_phase = static_cast<uint32_t>(i >> 1) & 1u;
+        const int img = fast_div(t, p.subs_per_img, p.spi_magic);
+        const int oy = (t - img * p.subs_per_img) * p.sub_rows + r;
+        const bool valid = pos_ok && oy < p.ho;
+        const int m = (img * p.ho + oy) * p.wo + c;
+        uint8_t* out_row = out_base + static_cast<size_t>(m) * p.out_pitch;
+        wait_or_die(&tfull_bar[acc], acc_phase, 0x400u | acc, p.stuck_flag);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * p.acc_stride);
+        uint32_t va[16], vb[16];
+        auto chunk = [&](const uint32_t (&v)[16], int ch) {
+          if (valid && dump != nullptr) {
+            int4* d = reinterpret_cast<int4*>(dump + static_cast<size_t>(m) * p.dump_pitch + ch);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            d[j] = make_int4(static_cast<int>(v[4 * j]), static_cast<int>(v[4 * j + 1]), static_cast<int>(v[4 * j + 2]),
-                             static_cast<int>(v[4 * j + 3]));
+            for (int j = 0; j < 4; ++j)
+              d[j] = make_int4(static_cast<int>(v[4 * j]), static_cast<int>(v[4 * j + 1]), static_cast<int>(v[4 * j + 2]),
+                               static_cast<int>(v[4 * j + 3]));
+          }
+          const uint4 o = fast ? epilogue16_i8<true>(v, e0 + ch, e1 + ch, zp, lo) : epilogue16_i8<false>(v, e0 + ch, e1 + ch, zp, lo);
+          if (valid) *reinterpret_cast<uint4*>(out_row + ch) = o;
+        };
+        tmem_ld_32x32b_x16(t_row, va);
+#pragma unroll 1
+        for (int cc = 0; cc < nchunks; cc += 2) {
+          tmem_ld_wait();
+          if (cc + 1 < nchunks) tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((cc + 1) * 16), vb);
+          chunk(va, cc * 16);
+          if (cc + 1 >= nchunks) break;
+          tmem_ld_wait();
+          if (cc + 2 < nchunks) tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((cc + 2) * 16), va);
+          chunk(vb, (cc + 1) * 16);
         }
-        const uint4 o = fast ? epilogue16_i8<true>(v, e0 + ch, e1 + ch, zp, lo) : epilogue16_i8<false>(v, e0 + ch, e1 + ch, zp, lo);
-        if (valid) *reinterpret_cast<uint4*>(out_row + ch) = o;
-      };
-      tmem_ld_32x32b_x16(t_row, va);
-      for (int cc = 0; cc < nchunks; cc += 2) {
-        tmem_ld_wait();
-        if (cc + 1 < nchunks) tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((cc + 1) * 16), vb);
-        chunk(va, cc * 16);
-        if (cc + 1 >= nchunks) break;
-        tmem_ld_wait();
-        if (cc + 2 < nchunks) tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((cc + 2) * 16), va);
-        chunk(vb, (cc + 1) * 16);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-    }
+    };
+    if (cls1) run(x.epc0, x.epc1);
+    else run(p.epc0, p.epc1);
   }
 
   tc_fence_before();

@@ -1239,6 +1239,10 @@ int launch_conv_dual(ievm_handle* h, const LayerPlan& P, int n, cudaStream_t s, 
   x.fast_round = D.fast_round;
   x.relu = D.d.relu;
   x.dump_acc = dump1;
+  if (D.cout_pad <= kEpConst && !D.ep0_host.empty()) {
+    memcpy(x.epc0, D.ep0_host.data(), D.cout_pad * sizeof(float));
+    memcpy(x.epc1, D.ep1_host.data(), D.cout_pad * sizeof(float));
+  }
   if (P.dual_s2) {
     // phase-patch form (conv_s2.cuh): sub-tiles of R output rows, four stride-1 phase patches per sub-tile
     const int wp = P.wo + 1, R = P.s2_rows, T = (P.ho + R - 1) / R;
