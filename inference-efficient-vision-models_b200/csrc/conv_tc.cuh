@@ -24,6 +24,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace ievm {
@@ -351,7 +353,10 @@ __device__ __forceinline__ uint4 load_res16_i8(const ConvTcParams& p, int m, boo
   return __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch));
 }
 
-template <int kDtype, bool kHasRes, bool kResI2F = false>
+// kFastSel: -1 = ConvTcParams::fast_round decides per call (both forms compiled into the caller's loop), 0 / 1 = the caller
+// has already branched, once per tile, so the hot loop is straight-line code (40 % of the stall samples of the residual
+// kernels were `no_instructions`: instruction fetch behind taken branches and a footprint twice the size it needs to be).
+template <int kDtype, bool kHasRes, bool kResI2F = false, int kFastSel = -1>
 __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint32_t (&v)[16], const uint4 r4, int m,
                                                bool valid, int ch, const float* s_ep0, const float* s_ep1,
                                                const AddReluConst& k) {
@@ -365,7 +370,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
   if (kDtype == kDtypeI8) {
     uint8_t* op = static_cast<uint8_t*>(p.out) + static_cast<size_t>(m) * p.out_pitch + ch;
     uint4 o;
-    if (kHasRes) {
+    if (kFastSel >= 0) {
+      if (kHasRes) o = epilogue16_i8_res<kFastSel == 1, kResI2F>(v, r4, s_ep0 + ch, s_ep1 + ch, k);
+      else o = epilogue16_i8<kFastSel == 1>(v, s_ep0 + ch, s_ep1 + ch, p.out_zp, p.out_lo);
+    } else if (kHasRes) {
       o = p.fast_round ? epilogue16_i8_res<true, kResI2F>(v, r4, s_ep0 + ch, s_ep1 + ch, k)
                        : epilogue16_i8_res<false, kResI2F>(v, r4, s_ep0 + ch, s_ep1 + ch, k);
     } else {
@@ -853,7 +861,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     };
     // The same for a statically shaped halo layer: one warp per quadrant owns the tile (four groups), the chunk loop is
     // unrolled and the per-channel tables are constant-bank operands (ConvTcParams::epc0 / epc1).
-    auto drain_static = [&](int acc, uint32_t acc_phase, int m, bool valid) {
+    auto drain_static = [&](auto fast_sel, int acc, uint32_t acc_phase, int m, bool valid) {
+      constexpr int kFs = kDtype == kDtypeI8 ? decltype(fast_sel)::value : -1;
       constexpr int kNch = kShape != 0 ? halo_shape_bn(kShape) / 16 : 1;
       uint4 rr[2];
       rr[0] = rr[1] = make_uint4(0u, 0u, 0u, 0u);
@@ -872,7 +881,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 1) * 16), vv[(c + 1) & 1]);
             if (kResI8) rr[(c + 1) & 1] = load_res16_i8(p, m, valid, (c + 1) * 16);
           }
-          epilogue_chunk<kDtype, kHasRes>(p, vv[c & 1], rr[c & 1], m, valid, c * 16, p.epc0, p.epc1, k);
+          epilogue_chunk<kDtype, kHasRes, false, kFs>(p, vv[c & 1], rr[c & 1], m, valid, c * 16, p.epc0, p.epc1, k);
         }
       } else {
         // wide layers: the chunk loop stays a loop over chunk PAIRS (register budget); the tables are still read from
@@ -882,13 +891,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tmem_ld_wait();
           tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 1) * 16), vv[1]);
           if (kResI8) rr[1] = load_res16_i8(p, m, valid, (c + 1) * 16);
-          epilogue_chunk<kDtype, kHasRes, true>(p, vv[0], rr[0], m, valid, c * 16, p.epc0, p.epc1, k);
+          epilogue_chunk<kDtype, kHasRes, true, kFs>(p, vv[0], rr[0], m, valid, c * 16, p.epc0, p.epc1, k);
           tmem_ld_wait();
           if (c + 2 < kNch) {
             tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 2) * 16), vv[0]);
             if (kResI8) rr[0] = load_res16_i8(p, m, valid, (c + 2) * 16);
           }
-          epilogue_chunk<kDtype, kHasRes, true>(p, vv[1], rr[1], m, valid, (c + 1) * 16, p.epc0, p.epc1, k);
+          epilogue_chunk<kDtype, kHasRes, true, kFs>(p, vv[1], rr[1], m, valid, (c + 1) * 16, p.epc0, p.epc1, k);
         }
       }
       tc_fence_before();
@@ -910,8 +919,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int oy = (t - img * p.subs_per_img) * p.sub_rows + sub_row;
         const bool valid = sub_ok && oy < p.h_in;
         const int m = (img * p.h_in + oy) * p.w_in + sub_x;
-        if (kShape != 0) drain_static(acc, acc_phase, m, valid);
-        else drain(acc, acc_phase, m, valid, 0, kZc ? zcorr_row(oy, sub_x) : nullptr);
+        if (kShape != 0) {
+          if (p.fast_round) drain_static(std::integral_constant<int, 1>{}, acc, acc_phase, m, valid);
+          else drain_static(std::integral_constant<int, 0>{}, acc, acc_phase, m, valid);
+        } else drain(acc, acc_phase, m, valid, 0, kZc ? zcorr_row(oy, sub_x) : nullptr);
       }
     } else {
       int acc_next = 0, seq = 0;
