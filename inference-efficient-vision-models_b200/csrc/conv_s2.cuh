@@ -183,7 +183,10 @@ conv_s2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool fast = (cls1 ? x.fast_round : p.fast_round) != 0;
     int32_t* dump = cls1 ? x.dump_acc : p.dump_acc;
     // e0 / e1: this class's per-channel tables in the kernel-parameter block (constant bank, uniform index)
-    auto run = [&](const float* e0, const float* e1) {
+    // fast_sel: -1 = rounding form chosen per chunk and the debug dump compiled in, 0 / 1 = straight-line code (see
+    // epilogue_chunk in conv_tc.cuh)
+    auto run = [&](auto fast_sel, const float* e0, const float* e1) __attribute__((always_inline)) {
+      constexpr int kFs = decltype(fast_sel)::value;
       for (int i = group >> 1; t_begin + i < t_end; i += 2) {
         const int t = t_begin + i;
         const int acc = 2 * (i & 1) + (cls1 ? 1 : 0);
@@ -198,14 +201,16 @@ conv_s2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * p.acc_stride);
         uint32_t va[16], vb[16];
         auto chunk = [&](const uint32_t (&v)[16], int ch) {
-          if (valid && dump != nullptr) {
+          if (kFs < 0 && valid && dump != nullptr) {
             int4* d = reinterpret_cast<int4*>(dump + static_cast<size_t>(m) * p.dump_pitch + ch);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               d[j] = make_int4(static_cast<int>(v[4 * j]), static_cast<int>(v[4 * j + 1]), static_cast<int>(v[4 * j + 2]),
                                static_cast<int>(v[4 * j + 3]));
           }
-          const uint4 o = fast ? epilogue16_i8<true>(v, e0 + ch, e1 + ch, zp, lo) : epilogue16_i8<false>(v, e0 + ch, e1 + ch, zp, lo);
+          uint4 o;
+          if (kFs >= 0) o = epilogue16_i8<kFs == 1>(v, e0 + ch, e1 + ch, zp, lo);
+          else o = fast ? epilogue16_i8<true>(v, e0 + ch, e1 + ch, zp, lo) : epilogue16_i8<false>(v, e0 + ch, e1 + ch, zp, lo);
           if (valid) *reinterpret_cast<uint4*>(out_row + ch) = o;
         };
         tmem_ld_32x32b_x16(t_row, va);
@@ -224,8 +229,12 @@ conv_s2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
     };
-    if (cls1) run(x.epc0, x.epc1);
-    else run(p.epc0, p.epc1);
+    auto dispatch = [&](const float* e0, const float* e1) {
+      if (fast && dump == nullptr) run(std::integral_constant<int, 1>{}, e0, e1);      // the product's form
+      else run(std::integral_constant<int, -1>{}, e0, e1);
+    };
+    if (cls1) dispatch(x.epc0, x.epc1);
+    else dispatch(p.epc0, p.epc1);
   }
 
   tc_fence_before();
