@@ -177,7 +177,10 @@ __device__ __forceinline__ uint32_t f2_max3(uint32_t a, uint32_t b, uint32_t c) 
 }
 
 // Epilogue of one warpgroup (kWg = 0: pooled columns 0..27, kWg = 1: 28..55).
-template <int kDtype, int kWg, int kSlots, bool kFast>
+// kDump: the debug instantiation that also writes the raw stem accumulators (ievm_debug_frontend); the product's epilogue
+// loop carries none of that code (64 byte-stride stores and their addressing per tile, skipped by a branch, were a quarter
+// of the loop's instruction footprint).
+template <int kDtype, int kWg, int kSlots, bool kFast, bool kDump>
 __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t tmem_base, uint64_t* tmem_full,
                                             uint64_t* tmem_empty, uint4* s_x) {
   constexpr int kOff = kWg == 0 ? -1 : 7;        // register index of a pooled column's first stem column: 2k + kOff
@@ -229,7 +232,7 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
-        if (p.dump_acc != nullptr && T >= 0) {
+        if (kDump && p.dump_acc != nullptr && T >= 0) {
           const int oy = 2 * T + (upper ? 1 : 0);
           int32_t* d = p.dump_acc + ((static_cast<size_t>(un.img) * p.ho + oy) * kF2Wo + kCol0) * 64 + c;
 #pragma unroll
@@ -243,7 +246,7 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
         const uint32_t c30 = v[30], c31 = v[31];
         tmem_ld_32x32b_x32(taddr + 32, v);
         tmem_ld_wait();
-        if (p.dump_acc != nullptr && T >= 0) {
+        if (kDump && p.dump_acc != nullptr && T >= 0) {
           const int oy = 2 * T + (upper ? 1 : 0);
           int32_t* d = p.dump_acc + ((static_cast<size_t>(un.img) * p.ho + oy) * kF2Wo + kCol0 + 32) * 64 + c;
 #pragma unroll
@@ -330,7 +333,7 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
 #endif
 }
 
-template <int kDtype, int kIn, bool kFast = false>
+template <int kDtype, int kIn, bool kFast = false, bool kDump = false>
 __global__ void __launch_bounds__(kF2Threads, 1)
 frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Params p) {
   using Cfg = F2Cfg<kDtype, kIn>;
@@ -406,8 +409,8 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
 
 
   if (warp < kF2EpiWarps) {
-    if (warp < 4) f2_epilogue<kDtype, 0, Cfg::kSlots, kFast>(p, tmem_base, tmem_full, tmem_empty, sX);
-    else f2_epilogue<kDtype, 1, Cfg::kSlots, kFast>(p, tmem_base, tmem_full, tmem_empty, sX);
+    if (warp < 4) f2_epilogue<kDtype, 0, Cfg::kSlots, kFast, kDump>(p, tmem_base, tmem_full, tmem_empty, sX);
+    else f2_epilogue<kDtype, 1, Cfg::kSlots, kFast, kDump>(p, tmem_base, tmem_full, tmem_empty, sX);
   } else if (warp == kF2MmaWarp) {
     // ================================ MMA issuer ================================
     const uint32_t hi = (128u >> 4) | (1u << 14);                                  // SBO = 128 B, version 1, no swizzle

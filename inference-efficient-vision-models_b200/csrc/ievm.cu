@@ -1420,7 +1420,11 @@ int launch_frontend2(ievm_handle* h, const void* x, int n, cudaStream_t s, int32
   fp.dump_acc = dump_acc;
   fp.stuck_flag = h->stuck_dev;
   const int grid = std::min(n * fp.ph, h->num_sms);       // contiguous ranges of pooled rows (frontend_v2.cuh: F2Walk)
-  if (u8_input && fp.fast_round) frontend2_kernel<kDtypeI8, 1, true><<<grid, kF2Threads, F2Cfg<kDtypeI8, 1>::kSmemBytes, s>>>(tmap, fp);
+  if (dump_acc != nullptr) {
+    // debug instantiations (ievm_debug_frontend): the general rounding form, accumulators written out
+    if (i8) frontend2_kernel<kDtypeI8, 0, false, true><<<grid, kF2Threads, F2Cfg<kDtypeI8>::kSmemBytes, s>>>(tmap, fp);
+    else frontend2_kernel<kDtypeF16, 0, false, true><<<grid, kF2Threads, F2Cfg<kDtypeF16>::kSmemBytes, s>>>(tmap, fp);
+  } else if (u8_input && fp.fast_round) frontend2_kernel<kDtypeI8, 1, true><<<grid, kF2Threads, F2Cfg<kDtypeI8, 1>::kSmemBytes, s>>>(tmap, fp);
   else if (u8_input) frontend2_kernel<kDtypeI8, 1><<<grid, kF2Threads, F2Cfg<kDtypeI8, 1>::kSmemBytes, s>>>(tmap, fp);
   else if (i8 && fp.fast_round) frontend2_kernel<kDtypeI8, 0, true><<<grid, kF2Threads, F2Cfg<kDtypeI8>::kSmemBytes, s>>>(tmap, fp);
   else if (i8) frontend2_kernel<kDtypeI8, 0><<<grid, kF2Threads, F2Cfg<kDtypeI8>::kSmemBytes, s>>>(tmap, fp);
@@ -1835,6 +1839,12 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
         }
       }
     }
+  }
+  if (rc == IEVM_OK && h->front2_ok) {
+    if ((h->dtype == IEVM_DTYPE_I8
+             ? cudaFuncSetAttribute(frontend2_kernel<kDtypeI8, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2Cfg<kDtypeI8>::kSmemBytes)
+             : cudaFuncSetAttribute(frontend2_kernel<kDtypeF16, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2Cfg<kDtypeF16>::kSmemBytes)) != cudaSuccess)
+      rc = fail(IEVM_ERR_CUDA, "cudaFuncSetAttribute(frontend2_kernel, debug instantiation) failed");
   }
   if (rc == IEVM_OK && h->front2_ok) {
     const cudaError_t e = h->dtype == IEVM_DTYPE_I8

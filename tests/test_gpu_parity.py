@@ -156,6 +156,9 @@ def test_int8_fused_front_end_accumulators_and_pooled_tensor(n, tpu, monkeypatch
         f"stem accumulators: {(acc != net.trace['conv1:acc']).mean():.3%} differ"
     assert np.array_equal(pooled, net.trace["maxpool"]), \
         f"pooled tensor: {(pooled != net.trace['maxpool']).mean():.3%} bytes differ"
+    # without the accumulator dump the PRODUCT instantiation runs (magic-number rounding, no debug code in its loop)
+    pooled_product, _ = eng.debug_frontend(x.cuda(), want_acc=False)
+    assert np.array_equal(pooled_product, net.trace["maxpool"])
     eng.close()
 
 
