@@ -156,6 +156,27 @@ __device__ __forceinline__ void wait_or_die(uint64_t* bar, uint32_t parity, uint
     }
   }
 }
+// The same with the bounded spin OUT OF LINE: a wait site is one try_wait (which already parks the warp for up to the
+// suspend hint), a branch and a rarely taken call instead of thirty instructions of slow path inside a pipeline loop --
+// instruction fetch is a first-order cost in these kernels.  For kernels with registers to spare only (the fused front
+// end: 81.5 -> 79.5 us): at the 96-register cap of the conv kernels the call's register saves spill (56 -> 61 us).
+__device__ __noinline__ void wait_or_die_slow(uint64_t* bar, uint32_t parity, uint32_t code, unsigned int* flag) {
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > IEVM_WAIT_LIMIT_NS) {
+      if (flag) {
+        *reinterpret_cast<volatile unsigned int*>(flag) = code;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void wait_or_die_ool(uint64_t* bar, uint32_t parity, uint32_t code, unsigned int* flag) {
+  if (mbar_try_wait(bar, parity)) return;
+  wait_or_die_slow(bar, parity, code, flag);
+}
 
 #ifdef IEVM_EXP_TIMING
 // [slot][cta][16]: 0 mma loop clk, 1 mma wait tempty, 2 mma wait full, 3 mma loop ns, 4 producer loop clk, 5 producer wait empty,

@@ -220,7 +220,7 @@ __device__ __forceinline__ void f2_epilogue(const Frontend2Params& p, uint32_t t
 #ifdef IEVM_EXP_TIMING
       const long long tw0 = clock64();
 #endif
-      wait_or_die(&tmem_full[ts], ph, 0x840u | ts, p.stuck_flag);
+      wait_or_die_ool(&tmem_full[ts], ph, 0x840u | ts, p.stuck_flag);
 #ifdef IEVM_EXP_TIMING
       f2_tm_wait += clock64() - tw0;
 #endif
@@ -439,12 +439,12 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
           if (!mbar_try_wait5(b0, p0, b1, p1, b1, p1, b1, p1, b1, p1)) {
 #ifdef IEVM_EXP_TIMING
             const long long tw1 = clock64();
-            wait_or_die(b0, p0, 0x820u | (qn % kF2ChunkSlots), p.stuck_flag);
+            wait_or_die_ool(b0, p0, 0x820u | (qn % kF2ChunkSlots), p.stuck_flag);
             f2_wait_line += clock64() - tw1;
 #else
-            wait_or_die(b0, p0, 0x820u | (qn % kF2ChunkSlots), p.stuck_flag);
+            wait_or_die_ool(b0, p0, 0x820u | (qn % kF2ChunkSlots), p.stuck_flag);
 #endif
-            wait_or_die(b1, p1, 0x830u | ts, p.stuck_flag);
+            wait_or_die_ool(b1, p1, 0x830u | ts, p.stuck_flag);
           }
 #ifdef IEVM_EXP_TIMING
           f2_wait += clock64() - tw0;
@@ -504,7 +504,7 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
 #ifdef IEVM_EXP_TIMING
         const long long tw0 = clock64();
 #endif
-        wait_or_die(&raw_empty[slot], ((q / kF2RawSlots) & 1u) ^ 1u, 0x800u | slot, p.stuck_flag);
+        wait_or_die_ool(&raw_empty[slot], ((q / kF2RawSlots) & 1u) ^ 1u, 0x800u | slot, p.stuck_flag);
 #ifdef IEVM_EXP_TIMING
         f2_wait += clock64() - tw0;
 #endif
@@ -543,12 +543,12 @@ frontend2_kernel(const __grid_constant__ CUtensorMap tmap_x, const Frontend2Para
 #ifdef IEVM_EXP_TIMING
         const long long tw0 = clock64();
 #endif
-        wait_or_die(&raw_full[slot], (q / kF2RawSlots) & 1u, 0x810u | slot, p.stuck_flag);
+        wait_or_die_ool(&raw_full[slot], (q / kF2RawSlots) & 1u, 0x810u | slot, p.stuck_flag);
 #ifdef IEVM_EXP_TIMING
         const long long tw1 = clock64();
         f2_wait_raw += tw1 - tw0;
 #endif
-        wait_or_die(&line_empty[cs], ((q / kF2ChunkSlots) & 1u) ^ 1u, 0x818u | cs, p.stuck_flag);
+        wait_or_die_ool(&line_empty[cs], ((q / kF2ChunkSlots) & 1u) ^ 1u, 0x818u | cs, p.stuck_flag);
 #ifdef IEVM_EXP_TIMING
         f2_wait_line += clock64() - tw1;
 #endif
