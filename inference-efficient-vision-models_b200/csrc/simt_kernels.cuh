@@ -225,6 +225,7 @@ struct HeadParams {
 constexpr int kHeadThreads = 256;
 constexpr int kMaxClasses = 16;
 constexpr int kHeadLoadsInFlight = 8;         // 16-byte loads a thread issues before it starts adding
+constexpr int kHeadPackMax = 256;             // pixels a 16-bit lane of the INT8 head's packed sums can take (256 * 255 < 2^16)
 constexpr int kHeadWeightSmemMax = 30 * 1024; // dynamic shared memory the heads may use for the fc weights
 
 constexpr int kHeadSumWords = 4096;          // shared partial channel sums: pixel phases x channel pitch
@@ -266,9 +267,27 @@ head_i8_kernel(const uint8_t* __restrict__ in, float* __restrict__ logits, uint8
   const int ph = threadIdx.x / g_stride, g0 = threadIdx.x - ph * g_stride;
   if (ph < ph_count) {
     for (int g = g0; g < groups; g += g_stride) {
+      // two channels per 32-bit accumulator (bytes 0 / 2 and bytes 1 / 3 of every word as 16-bit lanes: one AND or one
+      // byte permute plus one add per two channels); a lane holds at most kHeadPackMax pixels x 255 < 2^16 before it is
+      // flushed into the 32-bit sums
       int sum[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) sum[j] = 0;
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pk[j] = 0u;
+      int packed = 0;
+      auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          sum[4 * k] += pk[2 * k] & 0xffffu;
+          sum[4 * k + 2] += pk[2 * k] >> 16;
+          sum[4 * k + 1] += pk[2 * k + 1] & 0xffffu;
+          sum[4 * k + 3] += pk[2 * k + 1] >> 16;
+          pk[2 * k] = pk[2 * k + 1] = 0u;
+        }
+        packed = 0;
+      };
       for (int px0 = ph; px0 < p.hw; px0 += kHeadLoadsInFlight * ph_count) {
         uint4 v[kHeadLoadsInFlight];
 #pragma unroll
@@ -276,18 +295,19 @@ head_i8_kernel(const uint8_t* __restrict__ in, float* __restrict__ logits, uint8
           const int px = px0 + it * ph_count;
           v[it] = px < p.hw ? __ldg(reinterpret_cast<const uint4*>(base + px * p.cpad + g * 16)) : make_uint4(0u, 0u, 0u, 0u);
         }
+        if (packed + kHeadLoadsInFlight > kHeadPackMax) flush();
 #pragma unroll
         for (int it = 0; it < kHeadLoadsInFlight; ++it) {
           const uint32_t wv[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            sum[4 * k] += wv[k] & 0xff;
-            sum[4 * k + 1] += (wv[k] >> 8) & 0xff;
-            sum[4 * k + 2] += (wv[k] >> 16) & 0xff;
-            sum[4 * k + 3] += wv[k] >> 24;
+            pk[2 * k] += wv[k] & 0x00ff00ffu;                          // bytes 0 and 2
+            pk[2 * k + 1] += __byte_perm(wv[k], 0u, 0x4341);           // bytes 1 and 3 (selector 4 = a zero byte)
           }
         }
+        packed += kHeadLoadsInFlight;
       }
+      flush();
 #pragma unroll
       for (int j = 0; j < 16; ++j) s_sum[ph * p.cpad + g * 16 + j] = sum[j];
     }
