@@ -39,7 +39,7 @@ for d in data:
         "registers": val(d, "launch__registers_per_thread", False),
         "grid": val(d, "launch__grid_size", False),
     })
-conv = [l for l in launches if l["kernel"].startswith(("conv_tc_kernel", "conv_dual_kernel"))]
+conv = [l for l in launches if l["kernel"].startswith(("conv_tc_kernel", "conv_dual_kernel", "conv_s2_kernel"))]
 summary = {
     "source": rep.split("/")[-1],
     "how": "ncu --set full --clock-control none, one forward at batch 256 (cold cache, serialised launches)",
