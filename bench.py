@@ -584,7 +584,7 @@ def run_b200(args, rank, world, local_rank):
         roof_burst = network_roofline_ms(rows, burst, pk["hbm_gbs"])
         roof_meas = network_roofline_ms(rows, tensor_peak, pk["hbm_gbs"])
         roofline = {
-            "kernel": "conv_tc_kernel / conv_dual_kernel (tcgen05 implicit GEMM, %d convs in %d launches/step)" % (len(tc), tc_launches),
+            "kernel": "conv_tc_kernel / conv_dual_kernel / conv_s2_kernel (tcgen05 implicit GEMM, %d convs in %d launches/step)" % (len(tc), tc_launches),
             "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
             "frac": achieved / tensor_peak if tensor_peak else None, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src,
