@@ -366,6 +366,44 @@ __device__ __forceinline__ void epilogue16_f16(const uint32_t (&v)[16], const fl
   }
 }
 
+// The same with the residual's 16 halves already in registers (fetched a chunk ahead, like the INT8 residual bytes: the
+// in-place loads above expose an L2 round trip per chunk -- 98 vs 66 us for the FP16 layer-1 convs with / without residual).
+template <bool kRelu>
+__device__ __forceinline__ void epilogue16_f16_pre(const uint32_t (&v)[16], const float* s_bias, const uint4 r0, const uint4 r1,
+                                                   __half* op, bool valid) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + 4 * j);
+    f[4 * j] = __uint_as_float(v[4 * j]) + b4.x;
+    f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+    f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+  }
+  const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&rw[j]));
+    f[2 * j] += r2.x;
+    f[2 * j + 1] += r2.y;
+  }
+  uint32_t hw2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x = f[2 * j], y = f[2 * j + 1];
+    if (kRelu) {
+      x = fmaxf(x, 0.0f);
+      y = fmaxf(y, 0.0f);
+    }
+    const __half2 h = __floats2half2_rn(x, y);
+    hw2[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  if (valid) {
+    *reinterpret_cast<uint4*>(op) = make_uint4(hw2[0], hw2[1], hw2[2], hw2[3]);
+    *reinterpret_cast<uint4*>(op + 8) = make_uint4(hw2[4], hw2[5], hw2[6], hw2[7]);
+  }
+}
+
 // One 16-column chunk of the epilogue for pixel row `m`.
 // Residual bytes for one 16-channel chunk of pixel row m (INT8), fetched ahead of the TMEM load so
 // that the L2 latency is hidden behind the wait for the accumulator.
@@ -374,13 +412,22 @@ __device__ __forceinline__ uint4 load_res16_i8(const ConvTcParams& p, int m, boo
   return __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch));
 }
 
+// FP16: the residual's 16 halves of one chunk (two 16-byte words; zeros for a row that does not exist).
+__device__ __forceinline__ void load_res16_f16(const ConvTcParams& p, int m, bool valid, int ch, uint4& a, uint4& b) {
+  a = b = make_uint4(0u, 0u, 0u, 0u);
+  if (!valid) return;
+  const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __half*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch);
+  a = __ldg(rp);
+  b = __ldg(rp + 1);
+}
+
 // kFastSel: -1 = ConvTcParams::fast_round decides per call (both forms compiled into the caller's loop), 0 / 1 = the caller
 // has already branched, once per tile, so the hot loop is straight-line code (40 % of the stall samples of the residual
 // kernels were `no_instructions`: instruction fetch behind taken branches and a footprint twice the size it needs to be).
 template <int kDtype, bool kHasRes, bool kResI2F = false, int kFastSel = -1>
 __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint32_t (&v)[16], const uint4 r4, int m,
                                                bool valid, int ch, const float* s_ep0, const float* s_ep1,
-                                               const AddReluConst& k) {
+                                               const AddReluConst& k, const uint4 r4b = make_uint4(0u, 0u, 0u, 0u)) {
   if (valid && p.dump_acc != nullptr) {
     int4* d = reinterpret_cast<int4*>(p.dump_acc + static_cast<size_t>(m) * p.dump_pitch + ch);
 #pragma unroll
@@ -404,9 +451,13 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
     if (valid) *reinterpret_cast<uint4*>(op) = o;
   } else {
     __half* op = static_cast<__half*>(p.out) + static_cast<size_t>(m) * p.out_pitch + ch;
-    const __half* rp = static_cast<const __half*>(p.res) + static_cast<size_t>(m) * p.res_pitch + ch;
-    if (p.relu) epilogue16_f16<kHasRes, true>(v, s_ep0 + ch, rp, op, valid);
-    else epilogue16_f16<kHasRes, false>(v, s_ep0 + ch, rp, op, valid);
+    if (kHasRes) {               // (r4, r4b): the residual halves, prefetched by the caller
+      if (p.relu) epilogue16_f16_pre<true>(v, s_ep0 + ch, r4, r4b, op, valid);
+      else epilogue16_f16_pre<false>(v, s_ep0 + ch, r4, r4b, op, valid);
+    } else {
+      if (p.relu) epilogue16_f16<false, true>(v, s_ep0 + ch, op, op, valid);
+      else epilogue16_f16<false, false>(v, s_ep0 + ch, op, op, valid);
+    }
   }
 }
 
@@ -825,6 +876,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int sub_x = row - sub_row * p.wp;
     const bool sub_ok = kMode == kModeHalo && row < p.sub_pos && sub_x < p.w_in;
     constexpr bool kResI8 = kHasRes && kDtype == kDtypeI8;
+    constexpr bool kResF16 = kHasRes && kDtype == kDtypeF16;
     // One tile (accumulator buffer `acc`) of output rows starting at pixel index m (valid = this thread's row exists).
     // Border class of output pixel (oy, ox) for the zero-point correction: which filter taps read inside the image.
     auto zcorr_row = [&](int oy, int ox) -> const int32_t* {
@@ -838,8 +890,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     };
     auto drain = [&](int acc, uint32_t acc_phase, int m, bool valid, int n0, const int32_t* zc = nullptr) {
       uint4 ra = make_uint4(0u, 0u, 0u, 0u), rb = ra;
+      uint4 sa = ra, sb = ra;                    // FP16: second half of a chunk's residual
       int c = sub;
       if (kResI8 && c < nchunks) ra = load_res16_i8(p, m, valid, n0 + c * 16);   // does not depend on the MMA
+      if (kResF16 && c < nchunks) load_res16_f16(p, m, valid, n0 + c * 16, ra, sa);
       IEVM_TIMED_WAIT(tm_wait_a, &tfull_bar[acc], acc_phase, 0x400u | acc, p.stuck_flag);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
@@ -857,8 +911,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (c + csub < nchunks) {
           tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + csub) * 16), vb);
           if (kResI8) rb = load_res16_i8(p, m, valid, n0 + (c + csub) * 16);
+          if (kResF16) load_res16_f16(p, m, valid, n0 + (c + csub) * 16, rb, sb);
         }
-        epilogue_chunk<kDtype, kHasRes>(p, va, ra, m, valid, n0 + c * 16, s_ep0, s_ep1, k);
+        epilogue_chunk<kDtype, kHasRes>(p, va, ra, m, valid, n0 + c * 16, s_ep0, s_ep1, k, sa);
         c += csub;
         if (c >= nchunks) break;
         tmem_ld_wait();
@@ -869,8 +924,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (c + csub < nchunks) {
           tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + csub) * 16), va);
           if (kResI8) ra = load_res16_i8(p, m, valid, n0 + (c + csub) * 16);
+          if (kResF16) load_res16_f16(p, m, valid, n0 + (c + csub) * 16, ra, sa);
         }
-        epilogue_chunk<kDtype, kHasRes>(p, vb, rb, m, valid, n0 + c * 16, s_ep0, s_ep1, k);
+        epilogue_chunk<kDtype, kHasRes>(p, vb, rb, m, valid, n0 + c * 16, s_ep0, s_ep1, k, sb);
         c += csub;
       }
       tc_fence_before();
@@ -887,7 +943,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr int kNch = kShape != 0 ? halo_shape_bn(kShape) / 16 : 1;
       uint4 rr[2];
       rr[0] = rr[1] = make_uint4(0u, 0u, 0u, 0u);
+      uint4 rq[2];                                // FP16: second half of a chunk's residual
+      rq[0] = rq[1] = rr[0];
       if (kResI8) rr[0] = load_res16_i8(p, m, valid, 0);
+      if (kResF16) load_res16_f16(p, m, valid, 0, rr[0], rq[0]);
       IEVM_TIMED_WAIT(tm_wait_a, &tfull_bar[acc], acc_phase, 0x400u | acc, p.stuck_flag);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
@@ -901,8 +960,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (c + 1 < kNch) {
             tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 1) * 16), vv[(c + 1) & 1]);
             if (kResI8) rr[(c + 1) & 1] = load_res16_i8(p, m, valid, (c + 1) * 16);
+            if (kResF16) load_res16_f16(p, m, valid, (c + 1) * 16, rr[(c + 1) & 1], rq[(c + 1) & 1]);
           }
-          epilogue_chunk<kDtype, kHasRes, false, kFs>(p, vv[c & 1], rr[c & 1], m, valid, c * 16, p.epc0, p.epc1, k);
+          epilogue_chunk<kDtype, kHasRes, false, kFs>(p, vv[c & 1], rr[c & 1], m, valid, c * 16, p.epc0, p.epc1, k, rq[c & 1]);
         }
       } else {
         // wide layers: the chunk loop stays a loop over chunk PAIRS (register budget); the tables are still read from
@@ -912,13 +972,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tmem_ld_wait();
           tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 1) * 16), vv[1]);
           if (kResI8) rr[1] = load_res16_i8(p, m, valid, (c + 1) * 16);
-          epilogue_chunk<kDtype, kHasRes, true, kFs>(p, vv[0], rr[0], m, valid, c * 16, p.epc0, p.epc1, k);
+          if (kResF16) load_res16_f16(p, m, valid, (c + 1) * 16, rr[1], rq[1]);
+          epilogue_chunk<kDtype, kHasRes, true, kFs>(p, vv[0], rr[0], m, valid, c * 16, p.epc0, p.epc1, k, rq[0]);
           tmem_ld_wait();
           if (c + 2 < kNch) {
             tmem_ld_32x32b_x16(t_row + static_cast<uint32_t>((c + 2) * 16), vv[0]);
             if (kResI8) rr[0] = load_res16_i8(p, m, valid, (c + 2) * 16);
+            if (kResF16) load_res16_f16(p, m, valid, (c + 2) * 16, rr[0], rq[0]);
           }
-          epilogue_chunk<kDtype, kHasRes, true, kFs>(p, vv[1], rr[1], m, valid, (c + 1) * 16, p.epc0, p.epc1, k);
+          epilogue_chunk<kDtype, kHasRes, true, kFs>(p, vv[1], rr[1], m, valid, (c + 1) * 16, p.epc0, p.epc1, k, rq[1]);
         }
       }
       tc_fence_before();

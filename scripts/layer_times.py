@@ -1,5 +1,5 @@
-"""Per-launch device times (us) of one INT8 forward at batch N, plus graph-replay step time.
-usage: layer_times.py [N] [tag]   (IEVM_LIB_PATH / IEVM_* env vars select the variant)"""
+"""Per-launch device times (us) of one forward at batch N, plus graph-replay step time.
+usage: layer_times.py [N] [tag] [i8|f16]   (IEVM_LIB_PATH / IEVM_* env vars select the variant)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,8 +8,12 @@ from ievm_b200 import synthetic as mf
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 tag = sys.argv[2] if len(sys.argv) > 2 else ""
-eng = ievm_b200.B200QuantizedResNet.from_converted(mf.static_quantize_fbgemm(mf.make_student()), max_batch=n)
-x = mf.synthetic_images(n).cuda()
+if len(sys.argv) > 3 and sys.argv[3] == "f16":
+    eng = ievm_b200.B200HalfResNet.from_half_module(mf.cast_fp16(mf.make_student()), max_batch=n)
+    x = mf.synthetic_images(n).half().cuda()
+else:
+    eng = ievm_b200.B200QuantizedResNet.from_converted(mf.static_quantize_fbgemm(mf.make_student()), max_batch=n)
+    x = mf.synthetic_images(n).cuda()
 for _ in range(3):
     y = eng(x)
 eng.set_option("profile", 1)
