@@ -218,6 +218,7 @@ struct ievm_handle {
   int opt_dual = 1;        // IEVM_DUAL=0 / option "dual": the 1x1 downsample convs run as launches of their own
   int opt_wide = 1;        // IEVM_WIDE=0: no pixel-pair form in dual launches (conv_dual.cuh)
   int opt_s2 = 1;          // IEVM_S2=0: no phase-patch form of the stride-2 dual launch (conv_s2.cuh)
+  int opt_tiny = 1;        // IEVM_TINY=0: no single-accumulator form of the halo layers at small batches (launch_conv)
   int front_chunk = 0;     // IEVM_FRONT_CHUNK: images per front-end chunk (0 = whole batch at once, default)
   // IEVM_HALO_RB128=1: 64-byte pixels use 128-byte shared-memory rows in halo mode
   int in_c = 0, in_h = 0, in_w = 0, classes = 0;
@@ -1133,7 +1134,16 @@ ConvTcParams make_conv_params(const ievm_handle* h, const LayerPlan& L, int n, i
 }
 
 int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32_t* dump_acc) {
-  const ConvTcParams p = make_conv_params(h, L, n, dump_acc);
+  ConvTcParams p = make_conv_params(h, L, n, dump_acc);
+  // Small batches: when no CTA of a halo layer gets more than one sub-tile, the accumulator ring is pointless and three
+  // of the four epilogue groups would idle.  One accumulator instead: all sixteen epilogue warps drain the one tile
+  // together (four per TMEM lane quadrant, interleaving 16-column chunks; the run-time-shaped kernel does that).
+  const bool tiny = h->opt_tiny && L.mode == kModeHalo && h->conv_impl == 0 && p.total_subs <= h->num_sms;
+  if (tiny) {
+    p.nacc = 1;
+    p.band_subs = 1;
+    p.tmem_cols = std::max(32, p.acc_stride);
+  }
   if (h->conv_impl == 1) {
     ConvDirectParams g;
     g.n = n; g.h = L.h; g.w = L.w; g.ho = L.ho; g.wo = L.wo;
@@ -1172,7 +1182,7 @@ int launch_conv(ievm_handle* h, const LayerPlan& L, int n, cudaStream_t s, int32
     else IEVM_LAUNCH(DT, RES, kModeIm2col, 1, 0);                          \
   } while (0)
   // the shape-specialised kernels assume a zero input zero point (true for every post-ReLU tensor); others take class 0
-  const int shape = (L.mode == kModeHalo && h->opt_halo_static && L.zcorr == nullptr) ? halo_shape_class(L.wp, L.kc_bytes, L.bn) : 0;
+  const int shape = (L.mode == kModeHalo && h->opt_halo_static && L.zcorr == nullptr && !tiny) ? halo_shape_class(L.wp, L.kc_bytes, L.bn) : 0;
   if (L.zcorr != nullptr && h->dtype == IEVM_DTYPE_I8) {
     // non-zero input zero point: the run-time-shaped kernels with the border-aware correction compiled in
 #define IEVM_LAUNCH_ZC(RES, MODE, CL)                                                                                        \
@@ -1751,6 +1761,7 @@ int ievm_create(const ievm_net_desc* nd, int device, int max_batch, ievm_handle*
   if (const char* e = getenv("IEVM_DUAL")) h->opt_dual = atoi(e);
   if (const char* e = getenv("IEVM_WIDE")) h->opt_wide = atoi(e);
   if (const char* e = getenv("IEVM_S2")) h->opt_s2 = atoi(e);
+  if (const char* e = getenv("IEVM_TINY")) h->opt_tiny = atoi(e);
   if (const char* e = getenv("IEVM_CLUSTER")) h->opt_cluster = atoi(e);
   if (const char* e = getenv("IEVM_HOST_CHUNK")) h->host_chunk = atoi(e);
   if (const char* e = getenv("IEVM_FUSED_FRONT")) h->opt_fused_front = atoi(e);

@@ -313,7 +313,8 @@ print("variant ok")
     {"IEVM_DUAL": "0"},                              # the 1x1 downsample convs as launches of their own
     {"IEVM_S2": "0"},                                # stride-2 dual launch as pixel pairs instead of phase patches (conv_s2.cuh off)
     {"IEVM_S2": "0", "IEVM_WIDE": "0"},              # ... and without the pixel-pair form (nine 64-byte-row taps)
-], ids=["halo_dynamic", "band1", "band3_kb1", "no_halo", "no_dual", "no_phase_patches", "no_pixel_pairs"])
+    {"IEVM_TINY": "0"},                              # small batches through the accumulator ring (no single-accumulator form)
+], ids=["halo_dynamic", "band1", "band3_kb1", "no_halo", "no_dual", "no_phase_patches", "no_pixel_pairs", "no_tiny"])
 def test_kernel_configuration_fallbacks_stay_bit_exact(env, tmp_path):
     script = tmp_path / "variant.py"
     script.write_text(_VARIANT)
